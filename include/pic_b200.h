@@ -1,0 +1,152 @@
+/* pic_b200.h -- C ABI of the B200-native 1D electrostatic PIC step.
+ *
+ * Drop-in boundary for ONE path of ZINZINBIN/Optimal-Control-1D-Electrostatic-Plasma: what
+ * `PIC.update_state` (src/env/pic.py:131-146) does and the getters around it.  The reference is pure Python and
+ * has no FFI of its own; these entry points are what a ctypes binding inside `src/env/pic.py` would call
+ * (INTEGRATION.md shows that binding).  Plain pointers and sizes only -- no torch, numpy or C++ types.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative PIC_E* code on failure; pic_last_error(h) gives the text
+ *     (pass NULL for errors of pic_create);
+ *   - one handle = one CUDA device + one stream; a handle is not thread-safe;
+ *   - work is enqueued asynchronously on the handle's stream; functions that fill HOST buffers synchronise it;
+ *   - particle arrays are SoA, env-major: x[env][particle], v[env][particle], float64 on the host side whatever the
+ *     device precision; mesh arrays are [env][N_mesh] float64;
+ *   - there is no CPU fallback: without a CUDA device pic_create fails with PIC_ENODEVICE.
+ */
+#ifndef PIC_B200_H
+#define PIC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)   /* the library is built with -fvisibility=hidden; these are its exports */
+#endif
+
+#define PIC_B200_ABI_VERSION 1
+
+enum { PIC_OK = 0, PIC_EINVAL = -1, PIC_ENODEVICE = -2, PIC_ECUDA = -3, PIC_ENOMEM = -4, PIC_ESTATE = -5,
+       PIC_ENUMERIC = -6, PIC_ENCCL = -7, PIC_EUNSUPPORTED = -8 };
+
+enum { PIC_F64 = 0, PIC_F32 = 1 };                       /* device precision of particles               */
+enum { PIC_MODE_AUTO = 0, PIC_MODE_RESIDENT = 1, PIC_MODE_STREAMING = 2 };
+enum { PIC_DEPOSIT_AUTO = -1, PIC_DEPOSIT_CAS64 = 0, PIC_DEPOSIT_SPLIT32 = 1 };
+
+/* per-env diagnostics record (pic_get_diag / pic_get_trace), doubles */
+enum { PIC_DIAG_KE = 0,        /* 0.5*sum(v^2)            src/env/util.py:144                       */
+       PIC_DIAG_PE_MESH = 1,   /* 0.5*sum(E_mesh^2)*dx    src/control/objective.py:31 (reward term) */
+       PIC_DIAG_SUM_V = 2,     /* sum(v)                                                            */
+       PIC_DIAG_SUM_E2 = 3,    /* sum(E_mesh^2)                                                     */
+       PIC_DIAG_N = 4 };
+
+typedef struct pic_handle pic_handle;
+
+/* Mirrors the keyword set of PIC.__init__ (src/env/pic.py:13-27, as passed at run_wo_oc.py:79-92) that the step
+ * itself needs, plus the batching / sharding / device knobs the reference does not have. */
+typedef struct pic_config {
+    int64_t n_particles;        /* particles per env stored on THIS handle (the local shard when sharded)      */
+    int64_t n_particles_total;  /* N of the whole env, enters n0*L/N/dx (interpolate.py:18); 0 => n_particles  */
+    int32_t n_mesh;             /* N_mesh                                                                      */
+    int32_t n_envs;             /* independent envs advanced together (>= 1)                                   */
+    double  n0;                 /* mean density                                                                */
+    double  L;                  /* box length                                                                  */
+    double  dt;                 /* time step AFTER the CFL clip of pic.py:71-72 (see pic_clip_dt)              */
+    int32_t precision;          /* PIC_F64 | PIC_F32                                                           */
+    int32_t mode;               /* PIC_MODE_*                                                                  */
+    int32_t deposit;            /* PIC_DEPOSIT_*                                                               */
+    int32_t fixed_bits;         /* fractional bits of the integer deposit; 0 => chosen from N / N_mesh         */
+    int32_t exact_weights;      /* 1 => CIC weights with IEEE division as interpolate.py:11-12 (slower)        */
+    int32_t device;             /* CUDA device ordinal                                                         */
+    int32_t max_mode;           /* actuator modes m (src/control/actuator.py:5); 0 => mesh-vector actuation only */
+    void*   stream;             /* cudaStream_t to enqueue on; NULL => the legacy default stream               */
+} pic_config;
+
+/* --- lifetime ---------------------------------------------------------------------------------------------- */
+int pic_abi_version(void);
+const char* pic_build_info(void);                    /* arch, flags, deposit flavours compiled in              */
+double pic_clip_dt(double dt, int64_t n_particles_total, double L);     /* src/env/pic.py:71-72               */
+int pic_create(const pic_config* cfg, pic_handle** out);                /* PIC.__init__ minus sampling         */
+int pic_destroy(pic_handle* h);
+const char* pic_last_error(const pic_handle* h);
+int pic_set_stream(pic_handle* h, void* cuda_stream);
+
+/* --- state -------------------------------------------------------------------------------------------------- */
+/* PIC.initialize after sampling (pic.py:66-77): takes x, v (host float64, [n_envs][n_particles]), wraps x in
+ * place (util.py:51), deposits and solves the self-consistent field so every getter is valid. */
+int pic_set_state(pic_handle* h, const double* x, const double* v);
+int pic_set_state_device(pic_handle* h, const void* x_dev, const void* v_dev);   /* device precision, same layout */
+/* PIC.get_state / .x / .v (pic.py:165-167): copies to host float64 and synchronises. */
+int pic_get_state(pic_handle* h, double* x, double* v);
+/* .n, .E_mesh (pic.py:101,117): [n_envs][n_mesh] each; either pointer may be NULL. */
+int pic_get_fields(pic_handle* h, double* n, double* E_mesh);
+/* fixed-point state density, [n_envs][n_mesh] uint64; value = sum(w) * 2^fixed_bits.  Bit-reproducible. */
+int pic_get_density_fixed(pic_handle* h, uint64_t* rho, int32_t* fixed_bits);
+/* [n_envs][PIC_DIAG_N] for the current state (get_energy / get_electric_energy are derived on the host side). */
+int pic_get_diag(pic_handle* h, double* diag);
+/* per-step records of the last pic_step_* call: [n_steps][n_envs][PIC_DIAG_N] */
+int pic_get_trace(pic_handle* h, double* trace, int32_t n_steps);
+/* cell index floor(x/dx), CIC weights and gathered field of the current state (pic.py:102-105,120);
+ * [n_envs][n_particles] each, any pointer may be NULL */
+int pic_get_cells(pic_handle* h, int32_t* indx_l, double* weight_l, double* weight_r, double* E_particles);
+
+/* --- the hot path -------------------------------------------------------------------------------------------- */
+/* PIC.update_state(E_external) (pic.py:131-146) n_steps times with the same external mesh field.
+ * E_ext: NULL (no control) or host float64 [n_envs][n_mesh] -- the (N_mesh,1) vector of util.py:102-103. */
+int pic_step_mesh(pic_handle* h, const double* E_ext, int32_t n_steps);
+/* Actuator basis tables of src/control/actuator.py:23-24, host float64 [n_mesh][m] each, m == cfg.max_mode. */
+int pic_set_actuator_basis(pic_handle* h, const double* basis_cos, const double* basis_sin, int32_t m);
+/* Fast path of E_field.compute_E (actuator.py:62) + update_state: coeffs host float64 [n_steps][n_envs][2m],
+ * cos coefficients first (run_ddpg.py:283: action[:m] -> cos, action[m:] -> sin). */
+int pic_step_coeffs(pic_handle* h, const double* coeffs, int32_t n_steps);
+/* Same two calls with DEVICE pointers (no copies, nothing synchronises). */
+int pic_step_mesh_device(pic_handle* h, const double* E_ext_dev, int32_t n_steps);
+int pic_step_coeffs_device(pic_handle* h, const double* coeffs_dev, int32_t n_steps);
+int pic_sync(pic_handle* h);
+/* sticky numeric flags raised on the device (bit 0: cell index out of range, bit 1: non-finite position) */
+int pic_get_error_flags(pic_handle* h, uint32_t* flags);
+
+/* --- zero-copy views for the policy side (device pointers owned by the handle) ------------------------------- */
+typedef struct pic_device_views {
+    void*   x;          /* [n_envs][ld] device precision */
+    void*   v;
+    int64_t ld;         /* env stride in elements */
+    double* n;          /* [n_envs][n_mesh] */
+    double* E_mesh;     /* [n_envs][n_mesh] */
+    double* diag;       /* [n_envs][PIC_DIAG_N] */
+    int32_t elem_size;  /* 8 or 4 */
+} pic_device_views;
+int pic_get_device_views(pic_handle* h, pic_device_views* out);
+
+/* --- particle sharding over several GPUs (one process per GPU) ------------------------------------------------ */
+/* Each rank holds n_particles of the n_particles_total; after every sub-stage deposit the fixed-point density is
+ * summed over ranks (integer sum => identical on every rank and independent of the rank count).
+ * nccl_comm: an initialised ncclComm_t for this device; the library resolves ncclAllReduce from the already
+ * loaded libnccl (the one torch ships) at run time. */
+int pic_comm_init(pic_handle* h, void* nccl_comm, int32_t rank, int32_t world_size);
+/* Or let the library build the communicator: rank 0 calls pic_nccl_unique_id, the 128 bytes are broadcast by any
+ * means (torch.distributed object broadcast, MPI, a file), then every rank calls pic_comm_init_rank. */
+int pic_nccl_unique_id(char* out128);
+int pic_comm_init_rank(pic_handle* h, const char* id128, int32_t rank, int32_t world_size);
+/* Alternative used when the collective is driven from the host side (e.g. torch.distributed): run sub-stage
+ * `stage` (0..3, or 4 = finalize, -1 = init deposit) only and leave the local density in the buffer returned by
+ * pic_stage_density (device pointer, [n_envs][n_mesh] uint64) for the caller to all-reduce in place. */
+int pic_run_stage(pic_handle* h, int32_t stage);
+int pic_stage_density(pic_handle* h, int32_t stage, uint64_t** rho_dev);
+int pic_set_stage_actuation(pic_handle* h, const double* E_ext_dev, const double* coeffs_dev);
+
+/* --- tuning / introspection ---------------------------------------------------------------------------------- */
+int pic_get_launch_info(pic_handle* h, int32_t* mode, int32_t* threads, int32_t* per_thread, int32_t* grid_x,
+                        int32_t* smem_bytes, int32_t* fixed_bits, int32_t* deposit);
+int pic_set_tuning(pic_handle* h, int32_t threads, int32_t unroll_or_ppt, int32_t ctas_per_sm);
+int64_t pic_kernel_launch_count(const pic_handle* h);        /* kernels enqueued by this handle so far */
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif /* PIC_B200_H */

@@ -1,0 +1,15 @@
+"""B200-native 1D electrostatic PIC step behind the reference's `PIC` interface.
+
+    from pic_b200 import PIC, BatchedPIC, Engine
+
+The CUDA library (lib/libpic_b200.so, sources under csrc/) is loaded on first use; there is no CPU fallback.
+"""
+from . import _lib
+from ._lib import PicError
+from .engine import Engine, DeviceArray
+from .pic import PIC
+from .batched import BatchedPIC
+from .dist import BumpOnTail, TwoStream
+from .actuator import E_field
+
+__all__ = ["PIC", "BatchedPIC", "Engine", "DeviceArray", "PicError", "BumpOnTail", "TwoStream", "E_field"]

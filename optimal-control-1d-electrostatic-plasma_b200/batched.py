@@ -1,0 +1,107 @@
+"""`BatchedPIC` -- thousands of independent plasma envs advanced together (BASELINE config 4).
+
+The reference has no batching: its RL loops step ONE `PIC` per process (src/control/rl/ppo.py:279, sac.py:354).
+This class keeps the per-env semantics of `PIC.update_state` (every env is bit-identical to the same env run alone
+through `PIC`) and adds the env axis: one CTA per env, particles in registers for the whole step, actuator
+coefficients in, (KE, PE_mesh) out, all on the device.
+
+Env sharding over GPUs: envs are independent, so rank r of W simply owns envs [lo, hi) = shard_range(n_envs, r, W);
+no communication is involved (DESIGN.md "Multi-GPU").
+"""
+from typing import Optional
+
+import numpy as np
+
+from . import _lib as L
+from .engine import Engine
+
+
+def shard_range(n_total: int, rank: int, world: int):
+    """Contiguous, balanced [lo, hi) slice of n_total items for `rank` of `world` (first n_total % world ranks get
+    one extra)."""
+    if world < 1 or not (0 <= rank < world):
+        raise ValueError("bad rank/world")
+    base, rem = divmod(int(n_total), int(world))
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+class BatchedPIC:
+    def __init__(self, n_envs: int, N: int = 5000, N_mesh: int = 250, n0: float = 1.0, L: float = 50.0,
+                 dt: float = 0.05, max_mode: int = 3, *, rank: int = 0, world_size: int = 1, device: int = 0,
+                 precision: str = "f64", mode: str = "auto", deposit: str = "auto", alpha: float = 1.0,
+                 beta: float = 1.0, n_actions: int = 10):
+        self.n_envs_total = int(n_envs)
+        self.env_lo, self.env_hi = shard_range(n_envs, rank, world_size)
+        self.n_envs = self.env_hi - self.env_lo
+        if self.n_envs < 1:
+            raise ValueError("rank %d of %d owns no env" % (rank, world_size))
+        self.N, self.N_mesh, self.n0, self.L, self.max_mode = int(N), int(N_mesh), n0, L, int(max_mode)
+        self.dx = L / N_mesh
+        self.dt = dt
+        if self.dt > 2 / np.sqrt(self.N / self.L):                  # src/env/pic.py:71-72
+            self.dt = 2 / np.sqrt(self.N / self.L)
+        self.engine = Engine(self.N, self.N_mesh, self.L, self.dt, n0=n0, n_envs=self.n_envs, precision=precision,
+                             mode=mode, deposit=deposit, device=device, max_mode=self.max_mode)
+        if self.max_mode > 0:
+            from .actuator import E_field
+            act = E_field(L, N_mesh, max_mode)
+            self.engine.set_actuator_basis(act.basis_cos, act.basis_sin)
+        # reward constants, src/control/rl/reward.py:32-33,71-76
+        self.alpha, self.beta = alpha, beta
+        self.r_pe_n = 1.0
+        self.r_ie_n = float(n_actions) * L * 0.25
+        self._pe_prev = None
+
+    # ---- state
+    def set_state(self, x, v):
+        """x, v: (n_envs_local, N) float64."""
+        self.engine.set_state(x, v)
+        self._pe_prev = self.engine.get_diag()[:, L.DIAG_PE_MESH].copy()
+
+    def reset_from_sampler(self, make_dist, A: float = 0.1, n_mode: int = 2, seed: Optional[int] = 42):
+        """Fills every local env from a host sampler: env e (global index) is seeded with seed + e, sampled by
+        `make_dist()` (a `BumpOnTail` / `TwoStream` factory) and perturbed as src/env/pic.py:68."""
+        xs = np.empty((self.n_envs, self.N)); vs = np.empty((self.n_envs, self.N))
+        for i in range(self.n_envs):
+            if seed is not None:
+                np.random.seed(seed + self.env_lo + i)
+            d = make_dist()
+            x, v = d.get_sample()
+            vs[i] = v * (1 + A * np.sin(2 * np.pi * n_mode * x / self.L))
+            xs[i] = x
+        self.set_state(xs, vs)
+        return xs, vs
+
+    def get_state(self):
+        """(n_envs_local, 2N): row e is `PIC.get_state()` of env e flattened (x then v)."""
+        x, v = self.engine.get_state()
+        return np.concatenate([x, v], axis=1)
+
+    # ---- stepping
+    def step(self, actions=None, n_steps: int = 1):
+        """Advance every env by n_steps.  actions: None (no control), (n_envs, 2m) held for all n_steps, or
+        (n_steps, n_envs, 2m).  Returns dict with per-step `pe_mesh`, `ke` (n_steps, n_envs) and the reference's
+        reward for each transition (computed on the PRE-step state, ddpg.py:455)."""
+        if actions is None:
+            self.engine.step_mesh(None, n_steps)
+            a = None
+        else:
+            a = np.asarray(actions, dtype=np.float64)
+            if a.ndim == 2:
+                a = np.broadcast_to(a, (n_steps,) + a.shape)
+            self.engine.step_coeffs(np.ascontiguousarray(a), n_steps)
+        tr = self.engine.get_trace(n_steps)
+        pe = tr[:, :, L.DIAG_PE_MESH]
+        pe_pre = np.concatenate([self._pe_prev[None, :], pe[:-1]], axis=0)
+        r = self.alpha * np.maximum(1.0 - pe_pre / self.r_pe_n, 0)
+        if a is not None:
+            ie = np.sum(a ** 2, axis=2) * self.L * 0.25                 # reward.py:52-54
+            r = r + self.beta * np.maximum(1.0 - ie / self.r_ie_n, 0)
+        else:
+            r = r + self.beta
+        self._pe_prev = pe[-1].copy()
+        return {"pe_mesh": pe, "ke": tr[:, :, L.DIAG_KE], "sum_v": tr[:, :, L.DIAG_SUM_V], "reward": r}
+
+    def views(self):
+        return self.engine.views()

@@ -1,0 +1,702 @@
+// C ABI (include/pic_b200.h) over the kernels: handle management, buffer rotation, sub-stage sequencing,
+// NCCL all-reduce of the fixed-point density for the particle-sharded mode.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/pic_b200.h"
+#include "pic_kernels.cuh"
+#include "pic_variants.h"
+
+using namespace pic;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+// ---- NCCL, resolved at run time from the libnccl already in the process (torch's) ---------------------------
+struct nccl_uid { char internal[128]; };               // ncclUniqueId is a 128-byte struct passed by value
+typedef int (*nccl_allreduce_fn)(const void*, void*, size_t, int, int, void*, cudaStream_t);
+typedef int (*nccl_uid_fn)(nccl_uid*);
+typedef int (*nccl_init_rank_fn2)(void**, int, nccl_uid, int);
+typedef int (*nccl_destroy_fn)(void*);
+typedef const char* (*nccl_errstr_fn)(int);
+constexpr int kNcclUint64 = 5, kNcclFloat64 = 8, kNcclSum = 0;
+
+struct NcclApi {
+    nccl_allreduce_fn allreduce = nullptr;
+    nccl_uid_fn get_uid = nullptr;
+    nccl_init_rank_fn2 init_rank = nullptr;
+    nccl_destroy_fn destroy = nullptr;
+    nccl_errstr_fn errstr = nullptr;
+    bool ok = false;
+};
+
+NcclApi& nccl_api() {
+    static NcclApi api;
+    static bool tried = false;
+    if (tried) return api;
+    tried = true;
+    void* lib = RTLD_DEFAULT;
+    if (!dlsym(RTLD_DEFAULT, "ncclAllReduce")) {
+        lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!lib) return api;
+    }
+    api.allreduce = (nccl_allreduce_fn)dlsym(lib, "ncclAllReduce");
+    api.get_uid = (nccl_uid_fn)dlsym(lib, "ncclGetUniqueId");
+    api.init_rank = (nccl_init_rank_fn2)dlsym(lib, "ncclCommInitRank");
+    api.destroy = (nccl_destroy_fn)dlsym(lib, "ncclCommDestroy");
+    api.errstr = (nccl_errstr_fn)dlsym(lib, "ncclGetErrorString");
+    api.ok = api.allreduce && api.get_uid && api.init_rank;
+    return api;
+}
+
+}  // namespace
+
+struct pic_handle {
+    pic_config cfg{};
+    int device = 0, sm_count = 0, max_smem = 0;
+    cudaStream_t stream = nullptr;
+    MeshConst mc{};
+    long long N = 0, ld = 0, Ntotal = 0;
+    int M = 0, n_envs = 1, esize = 8, fixed_bits = 0, dep = DEP_CAS64;
+    bool f32 = false, exact_w = false, resident = false;
+    double cs[4]{}, ds[4]{};
+
+    // tuning
+    int threads = 256, per_thread = 2, ctas_per_sm = 0, grid_x = 1, occ = 1;
+    size_t smem = 0;
+
+    // device buffers
+    void *x = nullptr, *v = nullptr;
+    unsigned long long* rho[4] = {nullptr, nullptr, nullptr, nullptr};   // W0, W1, W2, S
+    double *n = nullptr, *E = nullptr, *diag = nullptr, *vsum = nullptr, *partial = nullptr;
+    double *ext = nullptr, *coeffs = nullptr, *bcos = nullptr, *bsin = nullptr, *trace = nullptr;
+    double* stage64 = nullptr;                      // staging for f32 <-> f64 state conversion / cells
+    size_t stage64_elems = 0;
+    long long coeffs_cap = 0, trace_cap = 0;
+    int trace_steps = 0;
+    unsigned* err = nullptr;
+    int m = 0;
+    bool have_state = false, have_basis = false;
+
+    // staged single-stage driving (pic_run_stage)
+    const double *stage_ext = nullptr, *stage_coeffs = nullptr;
+
+    // sharding
+    void* comm = nullptr;
+    bool own_comm = false;
+    int rank = 0, world = 1;
+
+    long long launches = 0;
+    int ablate = 0;                                 // PIC_ABLATE (profiling only, see StreamArgs::ablate)
+    std::string last_error;
+};
+
+namespace {
+
+int fail(pic_handle* h, int code, const std::string& msg) {
+    if (h) h->last_error = msg; else g_create_error = msg;
+    return code;
+}
+#define CK(h, call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) \
+    return fail(h, PIC_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); } while (0)
+
+void yoshida(double cs[4], double ds[4]) {          // src/env/integration.py:62-69, same evaluation order
+    double phi = pow(2.0, 1.0 / 3.0);
+    double w0 = (-1) * phi / (2 - phi);
+    double w1 = 1 / (2 - phi);
+    cs[0] = cs[3] = 0.5 * w1;
+    cs[1] = cs[2] = 0.5 * (w0 + w1);
+    ds[0] = 0.0; ds[1] = w1; ds[2] = w0; ds[3] = w1;
+}
+
+const void* stream_kernel(const pic_handle* h, int mode) {
+    return h->f32 ? stream_kernel_f32(h->threads, h->per_thread, mode, h->dep, h->exact_w)
+                  : stream_kernel_f64(h->threads, h->per_thread, mode, h->dep, h->exact_w);
+}
+const void* resident_kernel(const pic_handle* h) {
+    return h->f32 ? resident_kernel_f32(h->threads, h->per_thread, h->dep, h->exact_w)
+                  : resident_kernel_f64(h->threads, h->per_thread, h->dep, h->exact_w);
+}
+size_t smem_for(const pic_handle* h) {
+    return h->f32 ? stream_smem_bytes<float>(h->M, h->threads) : stream_smem_bytes<double>(h->M, h->threads);
+}
+
+int configure_launch(pic_handle* h) {
+    h->smem = smem_for(h);
+    if ((int)h->smem > h->max_smem)
+        return fail(h, PIC_EUNSUPPORTED, "n_mesh too large for the shared-memory mesh tables (" +
+                    std::to_string(h->smem) + " B needed, " + std::to_string(h->max_smem) + " B available)");
+    if (h->resident) {
+        const void* k = resident_kernel(h);
+        if (!k) return fail(h, PIC_EUNSUPPORTED, "no resident kernel variant for threads=" + std::to_string(h->threads) +
+                            " per_thread=" + std::to_string(h->per_thread));
+        CK(h, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
+        h->grid_x = h->n_envs;
+        return PIC_OK;
+    }
+    int occ_min = 1 << 30;
+    for (int mode = 0; mode < 4; ++mode) {
+        const void* k = stream_kernel(h, mode);
+        if (!k) return fail(h, PIC_EUNSUPPORTED, "no streaming kernel variant for threads=" + std::to_string(h->threads) +
+                            " unroll=" + std::to_string(h->per_thread));
+        CK(h, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
+        int occ = 0;
+        CK(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, h->threads, h->smem));
+        if (occ < occ_min) occ_min = occ;
+    }
+    if (occ_min < 1) return fail(h, PIC_EUNSUPPORTED, "streaming kernel does not fit on an SM");
+    h->occ = h->ctas_per_sm > 0 ? (h->ctas_per_sm < occ_min ? h->ctas_per_sm : occ_min) : occ_min;
+    long long want = (long long)h->sm_count * h->occ / h->n_envs;
+    const int VEC = h->f32 ? 4 : 2;
+    long long tiles = (h->N / VEC + (long long)h->threads * h->per_thread - 1) / ((long long)h->threads * h->per_thread);
+    if (want > tiles) want = tiles;
+    if (want < 1) want = 1;
+    h->grid_x = (int)want;
+    if (h->partial) { cudaFree(h->partial); h->partial = nullptr; }
+    CK(h, cudaMalloc(&h->partial, sizeof(double) * 2 * (size_t)h->grid_x * h->n_envs));
+    const void* kf = (const void*)&field_finalize_kernel<256>;
+    CK(h, cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stream_smem_bytes<double>(h->M, 256)));
+    return PIC_OK;
+}
+
+int allreduce_u64(pic_handle* h, unsigned long long* buf, size_t count) {
+    if (h->world <= 1) return PIC_OK;
+    int r = nccl_api().allreduce(buf, buf, count, kNcclUint64, kNcclSum, h->comm, h->stream);
+    if (r != 0) return fail(h, PIC_ENCCL, std::string("ncclAllReduce(uint64): ") +
+                            (nccl_api().errstr ? nccl_api().errstr(r) : "error"));
+    return PIC_OK;
+}
+
+__global__ void apply_vsum_kernel(const double* vsum, double* diag, double* trace, int n_envs) {
+    int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < n_envs) {
+        diag[e * DIAG_N + DIAG_KE] = 0.5 * vsum[2 * e];
+        diag[e * DIAG_N + DIAG_SUM_V] = vsum[2 * e + 1];
+        if (trace) for (int k = 0; k < DIAG_N; ++k) trace[e * DIAG_N + k] = diag[e * DIAG_N + k];
+    }
+}
+
+template <typename R, bool EXACT_W>
+__global__ void cells_kernel(const R* __restrict__ x, long long N, long long ld, MeshConst mc, int* il,
+                             double* wl, double* wr, const double* __restrict__ Emesh, double* Ep) {
+    const PartConst<R> pc = make_part_const<R>(mc);
+    const int env = blockIdx.y;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (long long)gridDim.x * blockDim.x) {
+        R a, b; unsigned err = 0;
+        R xw = wrap_pos<R>(x[(size_t)env * ld + i], pc);
+        Cell c = cell_weights<R, EXACT_W>(xw, pc, mc.M, a, b, err);
+        size_t o = (size_t)env * N + i;
+        if (il) il[o] = c.il;
+        if (wl) wl[o] = (double)a;
+        if (wr) wr[o] = (double)b;
+        if (Ep) {                                      // pic.py:120
+            const double* E = Emesh + (size_t)env * mc.M;
+            Ep[o] = __dadd_rn(__dmul_rn((double)a, E[c.il]), __dmul_rn((double)b, E[c.ir == mc.M ? 0 : c.ir]));
+        }
+    }
+}
+
+// one streaming sub-stage: stage 0..3 = Yoshida stages, 4 = finalize, -1 = init deposit
+int run_stage(pic_handle* h, int stage, const double* ext, const double* coeffs, double* trace_row) {
+    if (stage == 4) {
+        FinalizeArgs f{};
+        f.mc = h->mc; f.rho = h->rho[3]; f.rho_zero = h->rho[2]; f.n_out = h->n; f.E_out = h->E; f.diag = h->diag;
+        f.partial = h->partial; f.vsum = h->vsum; f.n_partial = h->grid_x;
+        void* args[] = {&f};
+        CK(h, cudaLaunchKernel((const void*)&field_finalize_kernel<256>, dim3(h->n_envs), dim3(256), args,
+                               stream_smem_bytes<double>(h->M, 256), h->stream));
+        h->launches++;
+        if (h->world > 1) {
+            int r = nccl_api().allreduce(h->vsum, h->vsum, 2 * (size_t)h->n_envs, kNcclFloat64, kNcclSum, h->comm, h->stream);
+            if (r != 0) return fail(h, PIC_ENCCL, "ncclAllReduce(float64) failed");
+        }
+        if (h->world > 1 || trace_row) {
+            apply_vsum_kernel<<<(h->n_envs + 127) / 128, 128, 0, h->stream>>>(h->vsum, h->diag, trace_row, h->n_envs);
+            h->launches++;
+        }
+        return PIC_OK;
+    }
+    StreamArgs a{};
+    a.mc = h->mc; a.x = h->x; a.v = h->v; a.N = h->N; a.ld = h->ld;
+    a.act.ext = ext; a.act.coeffs = coeffs; a.act.bcos = h->bcos; a.act.bsin = h->bsin; a.act.m = h->m;
+    a.partial = h->partial; a.err = h->err; a.ablate = h->ablate;
+    int mode, out;
+    switch (stage) {
+        case -1: mode = MODE_INIT; a.rho_out = h->rho[3]; out = 3; a.c = 0; a.d = 0; break;
+        case 0: mode = MODE_DRIFT; a.rho_out = h->rho[0]; a.rho_zero = h->rho[3]; out = 0; break;
+        case 1: mode = MODE_KICK; a.rho_in = h->rho[0]; a.rho_out = h->rho[1]; out = 1; break;
+        case 2: mode = MODE_KICK; a.rho_in = h->rho[1]; a.rho_out = h->rho[2]; a.rho_zero = h->rho[0]; out = 2; break;
+        case 3: mode = MODE_FINAL; a.rho_in = h->rho[2]; a.rho_out = h->rho[3]; a.rho_zero = h->rho[1]; out = 3; break;
+        default: return fail(h, PIC_EINVAL, "stage must be -1..4");
+    }
+    if (stage >= 0) { a.c = h->cs[stage]; a.d = h->ds[stage]; }
+    if (stage == -1) CK(h, cudaMemsetAsync(h->rho[3], 0, sizeof(unsigned long long) * (size_t)h->M * h->n_envs, h->stream));
+    void* args[] = {&a};
+    CK(h, cudaLaunchKernel(stream_kernel(h, mode), dim3(h->grid_x, h->n_envs), dim3(h->threads), args, h->smem, h->stream));
+    h->launches++;
+    return allreduce_u64(h, h->rho[out], (size_t)h->M * h->n_envs);
+}
+
+int ensure_trace(pic_handle* h, int n_steps) {
+    long long need = (long long)n_steps * h->n_envs * DIAG_N;
+    if (need > h->trace_cap) {
+        if (h->trace) cudaFree(h->trace);
+        h->trace = nullptr; h->trace_cap = 0;
+        CK(h, cudaMalloc(&h->trace, sizeof(double) * need));
+        h->trace_cap = need;
+    }
+    h->trace_steps = n_steps;
+    return PIC_OK;
+}
+
+int launch_resident(pic_handle* h, int n_steps, const double* ext, const double* coeffs) {
+    ResidentArgs a{};
+    a.mc = h->mc; a.x = h->x; a.v = h->v; a.N = h->N; a.ld = h->ld; a.n_steps = n_steps;
+    a.act.ext = ext; a.act.coeffs = coeffs; a.act.bcos = h->bcos; a.act.bsin = h->bsin; a.act.m = h->m;
+    a.coeff_step_stride = (long long)h->n_envs * 2 * h->m; a.ext_step_stride = 0;
+    for (int i = 0; i < 4; ++i) { a.c[i] = h->cs[i]; a.d[i] = h->ds[i]; }
+    a.n_out = h->n; a.E_out = h->E; a.diag = h->diag; a.trace = n_steps > 0 ? h->trace : nullptr;
+    a.rho_out = h->rho[3]; a.err = h->err;
+    void* args[] = {&a};
+    CK(h, cudaLaunchKernel(resident_kernel(h), dim3(h->n_envs), dim3(h->threads), args, h->smem, h->stream));
+    h->launches++;
+    return PIC_OK;
+}
+
+// advance n_steps; ext / coeffs are DEVICE pointers (coeffs: [n_steps][n_envs][2m])
+int step_device(pic_handle* h, const double* ext, const double* coeffs, int n_steps) {
+    if (!h->have_state) return fail(h, PIC_ESTATE, "pic_set_state has not been called");
+    if (n_steps < 1) return fail(h, PIC_EINVAL, "n_steps must be >= 1");
+    if (coeffs && (!h->have_basis || h->m < 1)) return fail(h, PIC_ESTATE, "pic_set_actuator_basis has not been called");
+    int rc = ensure_trace(h, n_steps);
+    if (rc) return rc;
+    if (h->resident) return launch_resident(h, n_steps, ext, coeffs);
+    for (int s = 0; s < n_steps; ++s) {
+        const double* cf = coeffs ? coeffs + (size_t)s * h->n_envs * 2 * h->m : nullptr;
+        for (int st = 0; st < 4; ++st) if ((rc = run_stage(h, st, ext, cf, nullptr))) return rc;
+        if ((rc = run_stage(h, 4, nullptr, nullptr, h->trace + (size_t)s * h->n_envs * DIAG_N))) return rc;
+    }
+    return PIC_OK;
+}
+
+int init_fields(pic_handle* h) {
+    int rc;
+    if (h->resident) {
+        if ((rc = launch_resident(h, 0, nullptr, nullptr))) return rc;
+    } else {
+        if ((rc = run_stage(h, -1, nullptr, nullptr, nullptr))) return rc;
+        if ((rc = run_stage(h, 4, nullptr, nullptr, nullptr))) return rc;
+    }
+    h->have_state = true;
+    return PIC_OK;
+}
+
+int ensure_stage64(pic_handle* h, size_t elems) {
+    if (elems > h->stage64_elems) {
+        if (h->stage64) cudaFree(h->stage64);
+        h->stage64 = nullptr; h->stage64_elems = 0;
+        CK(h, cudaMalloc(&h->stage64, sizeof(double) * elems));
+        h->stage64_elems = elems;
+    }
+    return PIC_OK;
+}
+
+}  // namespace
+
+// =============================================================================================== C ABI
+extern "C" {
+
+int pic_abi_version(void) { return PIC_B200_ABI_VERSION; }
+
+const char* pic_build_info(void) {
+    return "pic_b200 sm_100a; deposits: cas64,split32; precisions: f64,f32; modes: resident,streaming; nccl: runtime-resolved";
+}
+
+double pic_clip_dt(double dt, int64_t n_total, double L) {
+    double lim = 2 / sqrt((double)n_total / L);          // src/env/pic.py:71-72
+    return dt > lim ? lim : dt;
+}
+
+const char* pic_last_error(const pic_handle* h) { return h ? h->last_error.c_str() : g_create_error.c_str(); }
+
+int pic_create(const pic_config* cfg, pic_handle** out) {
+    if (!cfg || !out) return fail(nullptr, PIC_EINVAL, "null argument");
+    *out = nullptr;
+    if (cfg->n_particles < 1 || cfg->n_mesh < 2 || cfg->n_envs < 1 || !(cfg->L > 0) || !(cfg->dt > 0) || !(cfg->n0 > 0))
+        return fail(nullptr, PIC_EINVAL, "invalid config (n_particles, n_mesh, n_envs, L, dt, n0 must be positive)");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1)
+        return fail(nullptr, PIC_ENODEVICE, "no CUDA device: this library has no CPU fallback");
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(nullptr, PIC_EINVAL, "device ordinal out of range");
+    pic_handle* h = new pic_handle();
+    h->cfg = *cfg;
+    h->device = cfg->device;
+    if (cudaSetDevice(h->device) != cudaSuccess) { delete h; return fail(nullptr, PIC_ECUDA, "cudaSetDevice failed"); }
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, h->device);
+    if (prop.major < 10) { delete h; return fail(nullptr, PIC_ENODEVICE, "device is not sm_100 class (built for sm_100a only)"); }
+    h->sm_count = prop.multiProcessorCount;
+    h->max_smem = (int)prop.sharedMemPerBlockOptin;
+    h->stream = (cudaStream_t)cfg->stream;
+    h->N = cfg->n_particles;
+    h->Ntotal = cfg->n_particles_total > 0 ? cfg->n_particles_total : cfg->n_particles;
+    h->M = cfg->n_mesh; h->n_envs = cfg->n_envs;
+    h->f32 = cfg->precision == PIC_F32; h->esize = h->f32 ? 4 : 8;
+    h->exact_w = cfg->exact_weights != 0;
+    h->m = cfg->max_mode > 0 ? cfg->max_mode : 0;
+    h->ld = (h->N + 15) / 16 * 16;
+    yoshida(h->cs, h->ds);
+    if (const char* ab = getenv("PIC_ABLATE")) h->ablate = atoi(ab);
+
+    MeshConst& mc = h->mc;
+    mc.M = h->M; mc.L = cfg->L; mc.dx = cfg->L / cfg->n_mesh; mc.inv_dx = 1.0 / mc.dx; mc.n0 = cfg->n0; mc.dt = cfg->dt;
+    mc.scale = cfg->n0 * cfg->L / (double)h->Ntotal / mc.dx;
+    int k = cfg->fixed_bits;
+    if (k <= 0) {                                         // headroom: 8x the mean per-cell weight sum below 2^62
+        double per_cell = (double)h->Ntotal / h->M;
+        if (per_cell < 1) per_cell = 1;
+        k = 62 - (int)ceil(log2(8.0 * per_cell));
+        if (k > 52) k = 52;
+        if (k < 20) k = 20;
+    }
+    if (k > 60) { delete h; return fail(nullptr, PIC_EINVAL, "fixed_bits must be <= 60"); }
+    h->fixed_bits = k;
+    mc.fix_scale = ldexp(1.0, k); mc.inv_fix = ldexp(1.0, -k);
+    mc.idx_thr = (double)h->M * (h->f32 ? ldexp(1.0, -20) : ldexp(1.0, -49));
+
+    h->dep = cfg->deposit == PIC_DEPOSIT_SPLIT32 ? DEP_SPLIT32 : DEP_CAS64;
+    int mode = cfg->mode;
+    const long long resident_cap = 256LL * 40;
+    if (mode == PIC_MODE_AUTO) mode = h->N <= resident_cap ? PIC_MODE_RESIDENT : PIC_MODE_STREAMING;
+    h->resident = mode == PIC_MODE_RESIDENT;
+    if (h->resident) {
+        h->threads = 256;
+        h->per_thread = resident_pick_ppt(256, h->N);
+        if (!h->per_thread) { delete h; return fail(nullptr, PIC_EUNSUPPORTED, "n_particles too large for resident mode"); }
+    } else {
+        h->threads = 256; h->per_thread = 2;
+    }
+
+    size_t pbytes = (size_t)h->ld * h->n_envs * h->esize, mbytes = sizeof(double) * (size_t)h->M * h->n_envs;
+    bool okm = cudaMalloc(&h->x, pbytes) == cudaSuccess && cudaMalloc(&h->v, pbytes) == cudaSuccess;
+    for (int i = 0; i < 4 && okm; ++i) okm = cudaMalloc(&h->rho[i], mbytes) == cudaSuccess;
+    okm = okm && cudaMalloc(&h->n, mbytes) == cudaSuccess && cudaMalloc(&h->E, mbytes) == cudaSuccess &&
+          cudaMalloc(&h->ext, mbytes) == cudaSuccess &&
+          cudaMalloc(&h->diag, sizeof(double) * DIAG_N * h->n_envs) == cudaSuccess &&
+          cudaMalloc(&h->vsum, sizeof(double) * 2 * h->n_envs) == cudaSuccess &&
+          cudaMalloc(&h->err, sizeof(unsigned)) == cudaSuccess;
+    if (okm && h->m > 0)
+        okm = cudaMalloc(&h->bcos, sizeof(double) * (size_t)h->M * h->m) == cudaSuccess &&
+              cudaMalloc(&h->bsin, sizeof(double) * (size_t)h->M * h->m) == cudaSuccess;
+    if (!okm) { std::string e = cudaGetErrorString(cudaGetLastError()); pic_destroy(h); return fail(nullptr, PIC_ENOMEM, "cudaMalloc: " + e); }
+    cudaMemsetAsync(h->x, 0, pbytes, h->stream);
+    cudaMemsetAsync(h->v, 0, pbytes, h->stream);
+    for (int i = 0; i < 4; ++i) cudaMemsetAsync(h->rho[i], 0, mbytes, h->stream);
+    cudaMemsetAsync(h->diag, 0, sizeof(double) * DIAG_N * h->n_envs, h->stream);
+    cudaMemsetAsync(h->vsum, 0, sizeof(double) * 2 * h->n_envs, h->stream);
+    cudaMemsetAsync(h->err, 0, sizeof(unsigned), h->stream);
+    int rc = configure_launch(h);
+    if (rc) { g_create_error = h->last_error; pic_destroy(h); return rc; }
+    *out = h;
+    return PIC_OK;
+}
+
+int pic_destroy(pic_handle* h) {
+    if (!h) return PIC_OK;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    if (h->own_comm && h->comm && nccl_api().destroy) nccl_api().destroy(h->comm);
+    void* bufs[] = {h->x, h->v, h->rho[0], h->rho[1], h->rho[2], h->rho[3], h->n, h->E, h->diag, h->vsum, h->partial,
+                    h->ext, h->coeffs, h->bcos, h->bsin, h->trace, h->stage64, h->err};
+    for (void* b : bufs) if (b) cudaFree(b);
+    delete h;
+    return PIC_OK;
+}
+
+int pic_set_stream(pic_handle* h, void* s) {
+    if (!h) return PIC_EINVAL;
+    cudaStreamSynchronize(h->stream);
+    h->stream = (cudaStream_t)s;
+    return PIC_OK;
+}
+
+int pic_set_tuning(pic_handle* h, int32_t threads, int32_t per_thread, int32_t ctas_per_sm) {
+    if (!h) return PIC_EINVAL;
+    int t0 = h->threads, p0 = h->per_thread, c0 = h->ctas_per_sm;
+    if (threads > 0) h->threads = threads;
+    if (per_thread > 0) h->per_thread = per_thread;
+    if (ctas_per_sm >= 0) h->ctas_per_sm = ctas_per_sm;
+    if (h->resident && (long long)h->threads * h->per_thread < h->N) {
+        h->threads = t0; h->per_thread = p0; h->ctas_per_sm = c0;
+        return fail(h, PIC_EINVAL, "threads * per_thread must cover n_particles in resident mode");
+    }
+    cudaStreamSynchronize(h->stream);
+    int rc = configure_launch(h);
+    if (rc) { h->threads = t0; h->per_thread = p0; h->ctas_per_sm = c0; configure_launch(h); }
+    return rc;
+}
+
+int pic_get_launch_info(pic_handle* h, int32_t* mode, int32_t* threads, int32_t* per_thread, int32_t* grid_x,
+                        int32_t* smem_bytes, int32_t* fixed_bits, int32_t* deposit) {
+    if (!h) return PIC_EINVAL;
+    if (mode) *mode = h->resident ? PIC_MODE_RESIDENT : PIC_MODE_STREAMING;
+    if (threads) *threads = h->threads;
+    if (per_thread) *per_thread = h->per_thread;
+    if (grid_x) *grid_x = h->grid_x;
+    if (smem_bytes) *smem_bytes = (int32_t)h->smem;
+    if (fixed_bits) *fixed_bits = h->fixed_bits;
+    if (deposit) *deposit = h->dep;
+    return PIC_OK;
+}
+
+int64_t pic_kernel_launch_count(const pic_handle* h) { return h ? h->launches : 0; }
+
+int pic_set_state_device(pic_handle* h, const void* xd, const void* vd) {
+    if (!h || !xd || !vd) return fail(h, PIC_EINVAL, "null argument");
+    CK(h, cudaSetDevice(h->device));
+    CK(h, cudaMemcpy2DAsync(h->x, (size_t)h->ld * h->esize, xd, (size_t)h->N * h->esize, (size_t)h->N * h->esize,
+                            h->n_envs, cudaMemcpyDeviceToDevice, h->stream));
+    CK(h, cudaMemcpy2DAsync(h->v, (size_t)h->ld * h->esize, vd, (size_t)h->N * h->esize, (size_t)h->N * h->esize,
+                            h->n_envs, cudaMemcpyDeviceToDevice, h->stream));
+    return init_fields(h);
+}
+
+int pic_set_state(pic_handle* h, const double* x, const double* v) {
+    if (!h || !x || !v) return fail(h, PIC_EINVAL, "null argument");
+    CK(h, cudaSetDevice(h->device));
+    const size_t row = (size_t)h->N;
+    if (!h->f32) {
+        CK(h, cudaMemcpy2DAsync(h->x, (size_t)h->ld * 8, x, row * 8, row * 8, h->n_envs, cudaMemcpyHostToDevice, h->stream));
+        CK(h, cudaMemcpy2DAsync(h->v, (size_t)h->ld * 8, v, row * 8, row * 8, h->n_envs, cudaMemcpyHostToDevice, h->stream));
+    } else {
+        int rc = ensure_stage64(h, (size_t)h->ld * h->n_envs);
+        if (rc) return rc;
+        const double* src[2] = {x, v};
+        void* dst[2] = {h->x, h->v};
+        for (int a = 0; a < 2; ++a) {
+            CK(h, cudaMemcpy2DAsync(h->stage64, (size_t)h->ld * 8, src[a], row * 8, row * 8, h->n_envs,
+                                    cudaMemcpyHostToDevice, h->stream));
+            convert_kernel<double, float><<<h->sm_count * 4, 256, 0, h->stream>>>(h->stage64, (float*)dst[a],
+                                                                                   (long long)h->ld * h->n_envs);
+            h->launches++;
+        }
+    }
+    return init_fields(h);
+}
+
+int pic_get_state(pic_handle* h, double* x, double* v) {
+    if (!h) return PIC_EINVAL;
+    if (!h->have_state) return fail(h, PIC_ESTATE, "no state");
+    CK(h, cudaSetDevice(h->device));
+    const size_t row = (size_t)h->N;
+    double* dst[2] = {x, v};
+    void* src[2] = {h->x, h->v};
+    for (int a = 0; a < 2; ++a) {
+        if (!dst[a]) continue;
+        if (!h->f32) {
+            CK(h, cudaMemcpy2DAsync(dst[a], row * 8, src[a], (size_t)h->ld * 8, row * 8, h->n_envs, cudaMemcpyDeviceToHost, h->stream));
+        } else {
+            int rc = ensure_stage64(h, (size_t)h->ld * h->n_envs);
+            if (rc) return rc;
+            convert_kernel<float, double><<<h->sm_count * 4, 256, 0, h->stream>>>((const float*)src[a], h->stage64,
+                                                                                   (long long)h->ld * h->n_envs);
+            h->launches++;
+            CK(h, cudaMemcpy2DAsync(dst[a], row * 8, h->stage64, (size_t)h->ld * 8, row * 8, h->n_envs, cudaMemcpyDeviceToHost, h->stream));
+            CK(h, cudaStreamSynchronize(h->stream));
+        }
+    }
+    CK(h, cudaStreamSynchronize(h->stream));
+    return PIC_OK;
+}
+
+int pic_get_fields(pic_handle* h, double* n, double* E) {
+    if (!h) return PIC_EINVAL;
+    if (!h->have_state) return fail(h, PIC_ESTATE, "no state");
+    size_t b = sizeof(double) * (size_t)h->M * h->n_envs;
+    if (n) CK(h, cudaMemcpyAsync(n, h->n, b, cudaMemcpyDeviceToHost, h->stream));
+    if (E) CK(h, cudaMemcpyAsync(E, h->E, b, cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));
+    return PIC_OK;
+}
+
+int pic_get_density_fixed(pic_handle* h, uint64_t* rho, int32_t* fixed_bits) {
+    if (!h) return PIC_EINVAL;
+    if (!h->have_state) return fail(h, PIC_ESTATE, "no state");
+    if (rho) CK(h, cudaMemcpyAsync(rho, h->rho[3], sizeof(uint64_t) * (size_t)h->M * h->n_envs, cudaMemcpyDeviceToHost, h->stream));
+    if (fixed_bits) *fixed_bits = h->fixed_bits;
+    CK(h, cudaStreamSynchronize(h->stream));
+    return PIC_OK;
+}
+
+int pic_get_diag(pic_handle* h, double* diag) {
+    if (!h || !diag) return PIC_EINVAL;
+    if (!h->have_state) return fail(h, PIC_ESTATE, "no state");
+    CK(h, cudaMemcpyAsync(diag, h->diag, sizeof(double) * DIAG_N * h->n_envs, cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));
+    return PIC_OK;
+}
+
+int pic_get_trace(pic_handle* h, double* trace, int32_t n_steps) {
+    if (!h || !trace) return PIC_EINVAL;
+    if (n_steps < 1 || n_steps > h->trace_steps) return fail(h, PIC_EINVAL, "n_steps exceeds the last call's step count");
+    CK(h, cudaMemcpyAsync(trace, h->trace, sizeof(double) * DIAG_N * h->n_envs * (size_t)n_steps, cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));
+    return PIC_OK;
+}
+
+int pic_get_cells(pic_handle* h, int32_t* il, double* wl, double* wr, double* Ep) {
+    if (!h) return PIC_EINVAL;
+    if (!h->have_state) return fail(h, PIC_ESTATE, "no state");
+    size_t n = (size_t)h->N * h->n_envs;
+    int rc = ensure_stage64(h, 4 * n);          // [wl | wr | Ep | il(int32)]
+    if (rc) return rc;
+    double* dwl = h->stage64; double* dwr = h->stage64 + n; double* dE = h->stage64 + 2 * n;
+    int* dil = (int*)(h->stage64 + 3 * n);
+    long long gx = (h->N + 255) / 256;
+    dim3 grid((unsigned)(gx < 4096 ? gx : 4096), h->n_envs);
+#define PIC_CELLS(R, EX) cells_kernel<R, EX><<<grid, 256, 0, h->stream>>>((const R*)h->x, h->N, h->ld, h->mc, dil, dwl, dwr, h->E, dE)
+    if (h->f32) { if (h->exact_w) PIC_CELLS(float, true); else PIC_CELLS(float, false); }
+    else        { if (h->exact_w) PIC_CELLS(double, true); else PIC_CELLS(double, false); }
+#undef PIC_CELLS
+    h->launches++;
+    if (il) CK(h, cudaMemcpyAsync(il, dil, sizeof(int) * n, cudaMemcpyDeviceToHost, h->stream));
+    if (wl) CK(h, cudaMemcpyAsync(wl, dwl, sizeof(double) * n, cudaMemcpyDeviceToHost, h->stream));
+    if (wr) CK(h, cudaMemcpyAsync(wr, dwr, sizeof(double) * n, cudaMemcpyDeviceToHost, h->stream));
+    if (Ep) CK(h, cudaMemcpyAsync(Ep, dE, sizeof(double) * n, cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));
+    return PIC_OK;
+}
+
+int pic_set_actuator_basis(pic_handle* h, const double* bc, const double* bs, int32_t m) {
+    if (!h || !bc || !bs) return fail(h, PIC_EINVAL, "null argument");
+    if (m != h->m || m < 1) return fail(h, PIC_EINVAL, "m must equal cfg.max_mode (> 0)");
+    size_t b = sizeof(double) * (size_t)h->M * m;
+    CK(h, cudaMemcpyAsync(h->bcos, bc, b, cudaMemcpyHostToDevice, h->stream));
+    CK(h, cudaMemcpyAsync(h->bsin, bs, b, cudaMemcpyHostToDevice, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));
+    h->have_basis = true;
+    return PIC_OK;
+}
+
+int pic_step_mesh_device(pic_handle* h, const double* ext_dev, int32_t n_steps) {
+    if (!h) return PIC_EINVAL;
+    CK(h, cudaSetDevice(h->device));
+    return step_device(h, ext_dev, nullptr, n_steps);
+}
+
+int pic_step_coeffs_device(pic_handle* h, const double* coeffs_dev, int32_t n_steps) {
+    if (!h || !coeffs_dev) return fail(h, PIC_EINVAL, "null argument");
+    CK(h, cudaSetDevice(h->device));
+    return step_device(h, nullptr, coeffs_dev, n_steps);
+}
+
+int pic_step_mesh(pic_handle* h, const double* ext, int32_t n_steps) {
+    if (!h) return PIC_EINVAL;
+    CK(h, cudaSetDevice(h->device));
+    if (ext) CK(h, cudaMemcpyAsync(h->ext, ext, sizeof(double) * (size_t)h->M * h->n_envs, cudaMemcpyHostToDevice, h->stream));
+    return step_device(h, ext ? h->ext : nullptr, nullptr, n_steps);
+}
+
+int pic_step_coeffs(pic_handle* h, const double* coeffs, int32_t n_steps) {
+    if (!h || !coeffs) return fail(h, PIC_EINVAL, "null argument");
+    if (h->m < 1) return fail(h, PIC_ESTATE, "handle was created with max_mode == 0");
+    if (n_steps < 1) return fail(h, PIC_EINVAL, "n_steps must be >= 1");
+    CK(h, cudaSetDevice(h->device));
+    long long need = (long long)n_steps * h->n_envs * 2 * h->m;
+    if (need > h->coeffs_cap) {
+        CK(h, cudaStreamSynchronize(h->stream));
+        if (h->coeffs) cudaFree(h->coeffs);
+        h->coeffs = nullptr; h->coeffs_cap = 0;
+        CK(h, cudaMalloc(&h->coeffs, sizeof(double) * need));
+        h->coeffs_cap = need;
+    }
+    CK(h, cudaMemcpyAsync(h->coeffs, coeffs, sizeof(double) * need, cudaMemcpyHostToDevice, h->stream));
+    return step_device(h, nullptr, h->coeffs, n_steps);
+}
+
+int pic_sync(pic_handle* h) {
+    if (!h) return PIC_EINVAL;
+    CK(h, cudaStreamSynchronize(h->stream));
+    return PIC_OK;
+}
+
+int pic_get_error_flags(pic_handle* h, uint32_t* flags) {
+    if (!h || !flags) return PIC_EINVAL;
+    CK(h, cudaMemcpyAsync(flags, h->err, sizeof(unsigned), cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));
+    return PIC_OK;
+}
+
+int pic_get_device_views(pic_handle* h, pic_device_views* out) {
+    if (!h || !out) return PIC_EINVAL;
+    out->x = h->x; out->v = h->v; out->ld = h->ld; out->n = h->n; out->E_mesh = h->E; out->diag = h->diag;
+    out->elem_size = h->esize;
+    return PIC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ sharding
+int pic_nccl_unique_id(char* out128) {
+    if (!out128) return PIC_EINVAL;
+    if (!nccl_api().ok) return fail(nullptr, PIC_ENCCL, "libnccl not available in this process");
+    nccl_uid id;
+    if (nccl_api().get_uid(&id) != 0) return fail(nullptr, PIC_ENCCL, "ncclGetUniqueId failed");
+    memcpy(out128, id.internal, 128);
+    return PIC_OK;
+}
+
+int pic_comm_init_rank(pic_handle* h, const char* id128, int32_t rank, int32_t world) {
+    if (!h || !id128) return PIC_EINVAL;
+    if (h->resident) return fail(h, PIC_EUNSUPPORTED, "particle sharding needs streaming mode");
+    if (!nccl_api().ok) return fail(h, PIC_ENCCL, "libnccl not available in this process");
+    CK(h, cudaSetDevice(h->device));
+    nccl_uid id; memcpy(id.internal, id128, 128);
+    void* comm = nullptr;
+    int r = nccl_api().init_rank(&comm, world, id, rank);
+    if (r != 0) return fail(h, PIC_ENCCL, std::string("ncclCommInitRank: ") + (nccl_api().errstr ? nccl_api().errstr(r) : "error"));
+    h->comm = comm; h->own_comm = true; h->rank = rank; h->world = world;
+    return PIC_OK;
+}
+
+int pic_comm_init(pic_handle* h, void* comm, int32_t rank, int32_t world) {
+    if (!h || !comm) return PIC_EINVAL;
+    if (h->resident) return fail(h, PIC_EUNSUPPORTED, "particle sharding needs streaming mode");
+    if (!nccl_api().ok) return fail(h, PIC_ENCCL, "libnccl not available in this process");
+    h->comm = comm; h->own_comm = false; h->rank = rank; h->world = world;
+    return PIC_OK;
+}
+
+int pic_set_stage_actuation(pic_handle* h, const double* ext_dev, const double* coeffs_dev) {
+    if (!h) return PIC_EINVAL;
+    h->stage_ext = ext_dev; h->stage_coeffs = coeffs_dev;
+    return PIC_OK;
+}
+
+int pic_run_stage(pic_handle* h, int32_t stage) {
+    if (!h) return PIC_EINVAL;
+    if (h->resident) return fail(h, PIC_EUNSUPPORTED, "pic_run_stage needs streaming mode");
+    CK(h, cudaSetDevice(h->device));
+    if (stage == 4 || stage == -1) {
+        int rc = run_stage(h, stage, nullptr, nullptr, nullptr);
+        if (!rc && stage == 4) h->have_state = true;
+        return rc;
+    }
+    return run_stage(h, stage, h->stage_ext, h->stage_coeffs, nullptr);
+}
+
+int pic_stage_density(pic_handle* h, int32_t stage, uint64_t** rho_dev) {
+    if (!h || !rho_dev) return PIC_EINVAL;
+    int idx = stage == -1 ? 3 : stage;
+    if (idx < 0 || idx > 3) return fail(h, PIC_EINVAL, "stage must be -1..3");
+    *rho_dev = (uint64_t*)h->rho[idx];
+    return PIC_OK;
+}
+
+}  // extern "C"

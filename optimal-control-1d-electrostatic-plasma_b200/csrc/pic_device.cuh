@@ -1,0 +1,325 @@
+// Device-side building blocks of the 1D electrostatic PIC step (sm_100a).
+//
+// Everything here restates *what* the reference computes
+//   deposit     src/env/interpolate.py:4-20  (CIC)   / src/env/util.py:48-62
+//   field       src/env/util.py:99-103, src/env/solve.py:27-53, src/env/util.py:7-46
+//   gather      src/env/util.py:106
+//   push        src/env/integration.py:22-47,60-75, src/env/pic.py:125-146
+// but not *how*: no dense matrices, no Thomas solve, no temporaries in memory.
+//
+// Numerical contract (DESIGN.md "Numerics"):
+//   * wrap and cell index are bit-exact with np.mod(np.mod(x,L),L) and
+//     floor(x/dx) (IEEE division) -- rn intrinsics keep ptxas from contracting
+//     index-critical expressions into FMAs.
+//   * push arithmetic replays the reference's operation order with rn
+//     intrinsics, so given the same mesh field x and v are bit-identical.
+//   * the deposit accumulates llrint(w * 2^k) in integers (associative =>
+//     independent of thread / CTA / GPU count); the field is one prefix sum.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace pic {
+
+constexpr int DIAG_KE = 0;        // 0.5 * sum v^2            (src/env/util.py:144)
+constexpr int DIAG_PE_MESH = 1;   // 0.5 * sum E_mesh^2 * dx  (src/control/objective.py:31)
+constexpr int DIAG_SUM_V = 2;     // sum v (momentum)
+constexpr int DIAG_SUM_E2 = 3;    // sum E_mesh^2
+constexpr int DIAG_N = 4;
+
+constexpr unsigned ERR_INDEX_RANGE = 1u;   // floor(x/dx) fell outside [0, N_mesh) (the reference would raise in np.bincount)
+constexpr unsigned ERR_NONFINITE = 2u;     // non-finite position reached the deposit
+
+// ---------------------------------------------------------------- real traits
+template <typename R> struct RT;
+
+template <> struct RT<double> {
+    using vec = double2;                       // 16-byte vector = 2 particles
+    static constexpr int VEC = 2;
+    static __device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
+    static __device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
+    static __device__ __forceinline__ double sub(double a, double b) { return __dsub_rn(a, b); }
+    static __device__ __forceinline__ double div(double a, double b) { return __ddiv_rn(a, b); }
+    static __device__ __forceinline__ double flo(double a) { return floor(a); }
+    static __device__ __forceinline__ double rnd(double a) { return rint(a); }
+    static __device__ __forceinline__ double mod(double a, double b) { return fmod(a, b); }
+    static __device__ __forceinline__ double abs(double a) { return fabs(a); }
+    static __device__ __forceinline__ long long fix(double w, double s) { return __double2ll_rn(__dmul_rn(w, s)); }
+    static __device__ __forceinline__ int toint(double a) { return __double2int_rd(a); }
+    static __device__ __forceinline__ double fromint(int a) { return __int2double_rn(a); }
+};
+
+template <> struct RT<float> {
+    using vec = float4;                        // 16-byte vector = 4 particles
+    static constexpr int VEC = 4;
+    static __device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
+    static __device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
+    static __device__ __forceinline__ float sub(float a, float b) { return __fsub_rn(a, b); }
+    static __device__ __forceinline__ float div(float a, float b) { return __fdiv_rn(a, b); }
+    static __device__ __forceinline__ float flo(float a) { return floorf(a); }
+    static __device__ __forceinline__ float rnd(float a) { return rintf(a); }
+    static __device__ __forceinline__ float mod(float a, float b) { return fmodf(a, b); }
+    static __device__ __forceinline__ float abs(float a) { return fabsf(a); }
+    static __device__ __forceinline__ long long fix(float w, double s) { return __double2ll_rn(__dmul_rn((double)w, s)); }
+    static __device__ __forceinline__ int toint(float a) { return __float2int_rd(a); }
+    static __device__ __forceinline__ float fromint(int a) { return __int2float_rn(a); }
+};
+
+// ------------------------------------------------------------ kernel parameters
+struct MeshConst {
+    int M;                 // N_mesh
+    double L, dx, inv_dx;  // dx = L / N_mesh (src/env/pic.py:36)
+    double n0;
+    double scale;          // n0 * L / N / dx, left to right (src/env/interpolate.py:18)
+    double fix_scale;      // 2^k
+    double inv_fix;        // 2^-k
+    double idx_thr;        // |q - rint(q)| below this => redo the cell index with IEEE division
+    double dt;
+};
+
+template <typename R> struct PartConst {   // per-particle constants in the particle precision
+    R L, twoL, dx, inv_dx, dt, idx_thr;
+};
+
+template <typename R>
+__host__ __device__ inline PartConst<R> make_part_const(const MeshConst& m) {
+    PartConst<R> c;
+    c.L = (R)m.L; c.twoL = (R)(2.0 * m.L); c.dx = (R)m.dx; c.inv_dx = (R)1 / c.dx; c.dt = (R)m.dt;
+    c.idx_thr = (R)m.idx_thr;
+    return c;
+}
+
+// ---------------------------------------------------------------- wrap / cell
+// np.mod(np.mod(x, L), L): util.py:51 followed by interpolate.py:6 (and pic.py:139 for the state itself).
+// np.mod = fmod, then +L when the remainder is non-zero and negative.  For |x| < 2L every branch below is the
+// exact value of that sequence: [L,2L) -> x-L is exact (Sterbenz); (-L,0) -> fl(x+L), which can round to L and
+// is then sent to 0 by the second mod.
+template <typename R>
+__device__ __forceinline__ R wrap_pos(R x, const PartConst<R>& c) {
+    if (x >= (R)0 && x < c.L) return x;
+    if (x >= c.L && x < c.twoL) return RT<R>::sub(x, c.L);
+    if (x < (R)0 && x > -c.L) {
+        R r = RT<R>::add(x, c.L);
+        return (r == c.L) ? (R)0 : r;
+    }
+    // far outside (or non-finite): the general definition
+    R r = RT<R>::mod(x, c.L);
+    if (r != (R)0) { if (r < (R)0) r = RT<R>::add(r, c.L); } else r = (R)0;
+    R r2 = RT<R>::mod(r, c.L);                       // second mod: only r == L changes
+    if (r2 != (R)0) { if (r2 < (R)0) r2 = RT<R>::add(r2, c.L); } else r2 = (R)0;
+    return r2;
+}
+
+struct Cell {
+    int il, ir;          // left / right cell; ir is NOT reduced mod M (tables are padded with one wrap cell)
+};
+
+// floor(xw / dx) with correctly rounded division (interpolate.py:8) and the two CIC weights (:11-12).
+// Fast path multiplies by 1/dx; whenever the product is within idx_thr of an integer the quotient is redone with
+// IEEE division, so the index is always the reference's.  EXACT_W selects true divisions for the weights as well.
+template <typename R, bool EXACT_W>
+__device__ __forceinline__ Cell cell_weights(R xw, const PartConst<R>& c, int M, R& wl, R& wr, unsigned& err) {
+    R q = RT<R>::mul(xw, c.inv_dx);
+    R f = RT<R>::flo(q);
+    if (RT<R>::abs(RT<R>::sub(q, RT<R>::rnd(q))) <= c.idx_thr) f = RT<R>::flo(RT<R>::div(xw, c.dx));
+    int il = RT<R>::toint(f);
+    if ((unsigned)il >= (unsigned)M) {               // also catches NaN -> INT_MIN
+        err |= (xw == xw) ? ERR_INDEX_RANGE : ERR_NONFINITE;
+        il = il < 0 ? 0 : M - 1;
+        f = RT<R>::fromint(il);
+    }
+    R fr = RT<R>::add(f, (R)1);
+    R nl = RT<R>::sub(RT<R>::mul(fr, c.dx), xw);     // indx_r * dx - x
+    R nr = RT<R>::sub(xw, RT<R>::mul(f, c.dx));      // x - indx_l * dx
+    if (EXACT_W) { wl = RT<R>::div(nl, c.dx); wr = RT<R>::div(nr, c.dx); }
+    else         { wl = RT<R>::mul(nl, c.inv_dx); wr = RT<R>::mul(nr, c.inv_dx); }
+    Cell k; k.il = il; k.ir = il + 1;
+    return k;
+}
+
+// ------------------------------------------------------------------ deposits
+// 64-bit integer accumulation in shared memory.  sm_100a has no native 64-bit (or floating point) shared
+// atomic add -- ptxas emits an ATOMS.CAST.SPIN loop -- so two flavours are provided:
+//   DEP_CAS64   : atomicAdd on unsigned long long (CAS loop), table hist64[M+1]
+//   DEP_SPLIT32 : two native 32-bit ATOMS.ADD, low word with return value to detect the carry, tables
+//                 lo[M+1], hi[M+1].  Exact: exactly one thread observes each wrap of the low word.
+constexpr int DEP_CAS64 = 0;
+constexpr int DEP_SPLIT32 = 1;
+
+template <int DEP> struct Hist;
+
+template <> struct Hist<DEP_CAS64> {
+    unsigned long long* h;
+    static __host__ __device__ constexpr size_t bytes(int M) { return (size_t)(M + 1) * 8; }
+    __device__ __forceinline__ void init(void* base, int M) { h = (unsigned long long*)base; }
+    __device__ __forceinline__ void zero(int M, int tid, int nthreads) {
+        for (int j = tid; j <= M; j += nthreads) h[j] = 0ull;
+    }
+    __device__ __forceinline__ void add(int cell, long long w) { atomicAdd(&h[cell], (unsigned long long)w); }
+    __device__ __forceinline__ unsigned long long get(int cell) const { return h[cell]; }
+};
+
+template <> struct Hist<DEP_SPLIT32> {
+    unsigned *lo, *hi;
+    static __host__ __device__ constexpr size_t bytes(int M) { return (size_t)(M + 1) * 8; }
+    __device__ __forceinline__ void init(void* base, int M) { lo = (unsigned*)base; hi = lo + (M + 1); }
+    __device__ __forceinline__ void zero(int M, int tid, int nthreads) {
+        for (int j = tid; j < 2 * (M + 1); j += nthreads) lo[j] = 0u;
+    }
+    __device__ __forceinline__ void add(int cell, long long w) {
+        unsigned wl = (unsigned)(unsigned long long)w, wh = (unsigned)((unsigned long long)w >> 32);
+        unsigned old = atomicAdd(&lo[cell], wl);
+        unsigned carry = (old + wl) < old ? 1u : 0u;
+        atomicAdd(&hi[cell], wh + carry);
+    }
+    __device__ __forceinline__ unsigned long long get(int cell) const {
+        return ((unsigned long long)hi[cell] << 32) | (unsigned long long)lo[cell];
+    }
+};
+
+// ------------------------------------------------------------ block primitives
+template <int THREADS>
+__device__ __forceinline__ double block_sum(double v, double* scratch /* THREADS/32 + 1 doubles */) {
+    constexpr int NW = THREADS / 32;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    __syncthreads();                       // scratch may still be read by a previous call
+    if (lane == 0) scratch[w] = v;
+    __syncthreads();
+    double t = 0.0;
+    if (w == 0) {
+        t = lane < NW ? scratch[lane] : 0.0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        if (lane == 0) scratch[NW] = t;
+    }
+    __syncthreads();
+    return scratch[NW];
+}
+
+// exclusive prefix over the per-thread totals, plus nothing else; returns the exclusive offset of this thread
+template <int THREADS>
+__device__ __forceinline__ double block_excl_scan(double v, double* scratch /* THREADS/32 + 1 */) {
+    constexpr int NW = THREADS / 32;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    double inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        double t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    __syncthreads();
+    if (lane == 31) scratch[w] = inc;
+    __syncthreads();
+    if (w == 0) {
+        double s = lane < NW ? scratch[lane] : 0.0;
+        double si = s;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            double t = __shfl_up_sync(0xffffffffu, si, o);
+            if (lane >= o) si += t;
+        }
+        if (lane < NW) scratch[lane] = si - s;      // exclusive warp offsets
+    }
+    __syncthreads();
+    return scratch[w] + (inc - v);
+}
+
+// ------------------------------------------------------------------ field solve
+// Periodic 3-point Poisson + centred difference in closed form (DESIGN.md "Field solve"):
+//   b_j = n_j - n0,  S_j = sum_{i<=j} b_i,  D_j = dx^2 (S_j - mean S),  E_j = -(D_j + D_{j-1}) / (2 dx)
+// which is the reference's Thomas/Sherman-Morrison solve of laplacian @ phi = b followed by -grad @ phi
+// (src/env/util.py:99-100) without forming phi.  Block-cooperative; every thread must call it.
+//
+//   rho      : M fixed-point cell sums (global or shared memory), already including the wrap cell
+//   E_s      : shared, M+1 entries of R: E_j (+ ext_j), entry M duplicates entry 0 for the gather
+//   D_s      : shared scratch, M doubles
+//   red      : shared scratch, THREADS/32 + 1 doubles
+//   ext      : nullptr or M doubles (global) added to what particles see (util.py:102-103)
+//   n_out/E_out : nullptr or global outputs of the density (interpolate.py:18) / self-consistent field
+// Returns sum_j E_j^2 of the self-consistent field (all threads) when WANT_E2, else 0.
+template <typename R, int THREADS, bool WANT_E2, typename RhoLoad>
+__device__ __forceinline__ double block_field(RhoLoad rho, R* E_s, double* D_s, double* red, const MeshConst& mc,
+                                              const double* __restrict__ ext, double* __restrict__ n_out,
+                                              double* __restrict__ E_out) {
+    const int M = mc.M, tid = threadIdx.x;
+    const int cpt = (M + THREADS - 1) / THREADS;
+    const int j0 = tid * cpt, j1 = min(M, j0 + cpt);
+    double run = 0.0, sumS_local = 0.0;
+    for (int j = j0; j < j1; ++j) {
+        double nj = (double)(long long)rho(j) * mc.inv_fix * mc.scale;
+        if (n_out) n_out[j] = nj;
+        run += nj - mc.n0;
+        D_s[j] = run;                                 // local inclusive prefix
+    }
+    const double off = block_excl_scan<THREADS>(run, red);
+    for (int j = j0; j < j1; ++j) {
+        double S = D_s[j] + off;
+        D_s[j] = S;
+        sumS_local += S;
+    }
+    const double meanS = block_sum<THREADS>(sumS_local, red) / (double)M;   // (syncs inside publish D_s)
+    const double dx2 = mc.dx * mc.dx, inv2dx = 1.0 / (2.0 * mc.dx);
+    double e2 = 0.0;
+    for (int j = j0; j < j1; ++j) {
+        const int jm = j == 0 ? M - 1 : j - 1;
+        double Dj = dx2 * (D_s[j] - meanS), Dm = dx2 * (D_s[jm] - meanS);
+        double E = -(Dj + Dm) * inv2dx;
+        if (E_out) E_out[j] = E;
+        if (WANT_E2) e2 += E * E;
+        double Et = ext ? E + ext[j] : E;
+        E_s[j] = (R)Et;
+        if (j == 0) E_s[M] = (R)Et;
+    }
+    double tot = 0.0;
+    if (WANT_E2) tot = block_sum<THREADS>(e2, red);
+    __syncthreads();
+    return tot;
+}
+
+// E_ext on the mesh from Fourier coefficients: basis_cos @ a + basis_sin @ b on the actuator's own node table
+// (src/control/actuator.py:62; tables are uploaded from the host so node positions are the reference's linspace).
+__device__ __forceinline__ double actuator_field_at(int j, int m, const double* __restrict__ bcos,
+                                                    const double* __restrict__ bsin,
+                                                    const double* __restrict__ coeff /* [2m]: cos then sin */) {
+    double ec = 0.0, es = 0.0;
+    for (int k = 0; k < m; ++k) {
+        ec = __dadd_rn(ec, __dmul_rn(bcos[j * m + k], coeff[k]));
+        es = __dadd_rn(es, __dmul_rn(bsin[j * m + k], coeff[m + k]));
+    }
+    return __dadd_rn(ec, es);
+}
+
+// ------------------------------------------------------------------- push step
+// One Yoshida sub-stage for one particle (integration.py:22-47 with f = [v; -E], pic.py:125-129):
+//   kick  : v <- v + (d * (-E_p)) * dt     E_p = w_l E[i_l] + w_r E[i_r] at the CURRENT (wrapped) position
+//   drift : x <- x + (c * v) * dt          x itself is carried unwrapped between sub-stages
+template <typename R, bool EXACT_W>
+__device__ __forceinline__ void kick(R x, R& v, const R* __restrict__ E_s, R d, const PartConst<R>& c, int M,
+                                     unsigned& err) {
+    R wl, wr;
+    R xw = wrap_pos<R>(x, c);
+    Cell k = cell_weights<R, EXACT_W>(xw, c, M, wl, wr, err);
+    R Ep = RT<R>::add(RT<R>::mul(wl, E_s[k.il]), RT<R>::mul(wr, E_s[k.ir]));
+    v = RT<R>::add(v, RT<R>::mul(RT<R>::mul(d, -Ep), c.dt));
+}
+
+template <typename R>
+__device__ __forceinline__ R drift(R x, R v, R cc, const PartConst<R>& c) {
+    return RT<R>::add(x, RT<R>::mul(RT<R>::mul(cc, v), c.dt));
+}
+
+template <typename R, bool EXACT_W, typename H>
+__device__ __forceinline__ void deposit(R xw, H& hist, const PartConst<R>& c, const MeshConst& mc, unsigned& err) {
+    R wl, wr;
+    Cell k = cell_weights<R, EXACT_W>(xw, c, mc.M, wl, wr, err);
+    hist.add(k.il, RT<R>::fix(wl, mc.fix_scale));
+    hist.add(k.ir, RT<R>::fix(wr, mc.fix_scale));
+}
+
+// streaming loads / stores (no reuse: keep the particle stream out of L1, evict-first in L2)
+template <typename V> __device__ __forceinline__ V ld_stream(const V* p) { return __ldcs(p); }
+template <typename V> __device__ __forceinline__ void st_stream(V* p, const V& v) { __stcs(p, v); }
+
+}  // namespace pic

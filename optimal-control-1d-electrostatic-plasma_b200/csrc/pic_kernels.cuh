@@ -1,0 +1,356 @@
+// Kernels of the PIC hot path (sm_100a).  See pic_device.cuh for the per-particle arithmetic.
+//
+//   push_stream_kernel   large-N "streaming" mode: one launch per Yoshida sub-stage.  Persistent CTAs stream the
+//                        SoA particle arrays once (16-byte loads/stores), every CTA rebuilds the mesh field from the
+//                        previous sub-stage's fixed-point density in its prologue (one block scan, no separate
+//                        Poisson launch), gathers/kicks/drifts, and deposits into a shared-memory privatised
+//                        histogram that is flushed with 64-bit global reductions.
+//   env_step_resident_kernel
+//                        small-N / batched mode: one CTA per env, particles live in registers for the whole launch,
+//                        all four sub-stages (and any number of env steps) run inside one launch.
+//   field_finalize_kernel
+//                        state field after a streaming step: density, self-consistent E, energies.
+#pragma once
+#include "pic_device.cuh"
+
+namespace pic {
+
+constexpr int MODE_DRIFT = 0;   // stage 0: d == 0, drift only                 (integration.py:71)
+constexpr int MODE_KICK = 1;    // stages 1,2: kick + drift                    (integration.py:72-73)
+constexpr int MODE_FINAL = 2;   // stage 3: kick + drift + state wrap (pic.py:139) + kinetic sums
+constexpr int MODE_INIT = 3;    // no motion: wrap in place + deposit          (pic.py:76 / util.py:51)
+
+struct ActuatorArgs {
+    const double* ext;       // mesh mode: [n_envs][M] (device) or nullptr
+    const double* coeffs;    // coefficient mode: [n_envs][2m] (device) or nullptr
+    const double* bcos;      // [M][m]
+    const double* bsin;      // [M][m]
+    int m;
+};
+
+struct StreamArgs {
+    MeshConst mc;
+    void* x;                           // [n_envs][ld] particle positions (R)
+    void* v;                           // [n_envs][ld] particle velocities (R)
+    long long N, ld;
+    const unsigned long long* rho_in;  // [n_envs][M] density of the previous sub-stage (MODE_KICK / MODE_FINAL)
+    unsigned long long* rho_out;       // [n_envs][M] must be zero on entry
+    unsigned long long* rho_zero;      // [n_envs][M] or nullptr: cleared for a later sub-stage
+    ActuatorArgs act;
+    double c, d;
+    double* partial;                   // [n_envs][gridDim.x][2] per-CTA sum v^2, sum v (MODE_FINAL / MODE_INIT)
+    unsigned* err;
+    int ablate;                        // profiling only (PIC_ABLATE env): bit0 skip deposit atomics, bit1 skip gather
+};
+
+template <typename R>
+__host__ __device__ constexpr size_t stream_smem_bytes(int M, int threads) {
+    return (size_t)(M + 1) * 8                       // histogram
+         + (((size_t)(M + 1) * sizeof(R) + 7) & ~(size_t)7)   // E_s
+         + (size_t)M * 8                             // D_s
+         + (size_t)M * 8                             // ext_s
+         + (size_t)(threads / 32 + 2) * 8;           // reduction scratch
+}
+
+template <typename R>
+struct SmemLayout {
+    void* hist; R* E_s; double* D_s; double* ext_s; double* red;
+    __device__ __forceinline__ SmemLayout(unsigned char* base, int M) {
+        hist = base;                         base += (size_t)(M + 1) * 8;
+        E_s = (R*)base;                      base += (((size_t)(M + 1) * sizeof(R) + 7) & ~(size_t)7);
+        D_s = (double*)base;                 base += (size_t)M * 8;
+        ext_s = (double*)base;               base += (size_t)M * 8;
+        red = (double*)base;
+    }
+};
+
+struct GlobalRho {
+    const unsigned long long* p;
+    __device__ __forceinline__ unsigned long long operator()(int j) const { return __ldcg(p + j); }
+};
+template <typename H> struct SharedRho {       // folds the wrap cell M into cell 0
+    const H* h; int M;
+    __device__ __forceinline__ unsigned long long operator()(int j) const {
+        return j == 0 ? h->get(0) + h->get(M) : h->get(j);
+    }
+};
+
+// prepares what the particles see on top of the self-consistent field; returns nullptr when there is no actuation
+template <int THREADS>
+__device__ __forceinline__ const double* stage_ext(const ActuatorArgs& act, int env, int M, double* ext_s) {
+    if (act.coeffs) {
+        const double* cf = act.coeffs + (size_t)env * 2 * act.m;
+        for (int j = threadIdx.x; j < M; j += THREADS) ext_s[j] = actuator_field_at(j, act.m, act.bcos, act.bsin, cf);
+        __syncthreads();
+        return ext_s;
+    }
+    if (act.ext) return act.ext + (size_t)env * M;
+    return nullptr;
+}
+
+template <typename R, int THREADS, int UNROLL, int MODE, int DEP, bool EXACT_W>
+__global__ void __launch_bounds__(THREADS) push_stream_kernel(const StreamArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    using V = typename RT<R>::vec;
+    constexpr int VEC = RT<R>::VEC;
+    constexpr bool KICK = (MODE == MODE_KICK || MODE == MODE_FINAL);
+    constexpr bool SUMS = (MODE == MODE_FINAL || MODE == MODE_INIT);
+    const int tid = threadIdx.x, env = blockIdx.y, M = a.mc.M;
+    SmemLayout<R> sm(smem_raw, M);
+    Hist<DEP> hist; hist.init(sm.hist, M);
+    const PartConst<R> pc = make_part_const<R>(a.mc);
+
+    hist.zero(M, tid, THREADS);
+    if (KICK) {
+        const double* ext = stage_ext<THREADS>(a.act, env, M, sm.ext_s);
+        GlobalRho rho{a.rho_in + (size_t)env * M};
+        block_field<R, THREADS, false>(rho, sm.E_s, sm.D_s, sm.red, a.mc, ext, nullptr, nullptr);
+    } else {
+        __syncthreads();
+    }
+    if (a.rho_zero) {
+        unsigned long long* z = a.rho_zero + (size_t)env * M;
+        for (int j = blockIdx.x * THREADS + tid; j < M; j += gridDim.x * THREADS) z[j] = 0ull;
+    }
+
+    R* xe = (R*)a.x + (size_t)env * a.ld;
+    R* ve = (R*)a.v + (size_t)env * a.ld;
+    V* xv = (V*)xe;
+    V* vv = (V*)ve;
+    const long long nvec = a.N / VEC;
+    const R cc = (R)a.c, dd = (R)a.d;
+    unsigned err = 0;
+    double s2 = 0.0, s1 = 0.0;
+
+    const bool do_dep = !(a.ablate & 1), do_gather = !(a.ablate & 2);
+    auto one = [&](R& x, R& v) {
+        if (KICK && do_gather) kick<R, EXACT_W>(x, v, sm.E_s, dd, pc, M, err);
+        if (MODE != MODE_INIT) x = drift<R>(x, v, cc, pc);
+        R xw = wrap_pos<R>(x, pc);
+        if (SUMS) { x = xw; s2 += (double)v * (double)v; s1 += (double)v; }
+        if (do_dep) deposit<R, EXACT_W>(xw, hist, pc, a.mc, err);
+    };
+
+    const long long stride = (long long)gridDim.x * THREADS * UNROLL;
+    for (long long base = (long long)blockIdx.x * THREADS * UNROLL + tid; base < nvec; base += stride) {
+        V xs[UNROLL], vs[UNROLL];
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            long long i = base + (long long)u * THREADS;
+            if (i < nvec) { xs[u] = ld_stream(xv + i); vs[u] = ld_stream(vv + i); }
+        }
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            long long i = base + (long long)u * THREADS;
+            if (i < nvec) {
+                R* px = reinterpret_cast<R*>(&xs[u]);
+                R* pv = reinterpret_cast<R*>(&vs[u]);
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) one(px[e], pv[e]);
+                st_stream(xv + i, xs[u]);
+                if (KICK) st_stream(vv + i, vs[u]);
+            }
+        }
+    }
+    // scalar tail (N not a multiple of the vector width)
+    if (blockIdx.x == 0) {
+        long long i = nvec * VEC + tid;
+        if (i < a.N) {
+            R x = xe[i], v = ve[i];
+            one(x, v);
+            xe[i] = x;
+            if (KICK) ve[i] = v;
+        }
+    }
+    __syncthreads();
+
+    // flush the CTA-private histogram: integer sums are associative, so the result does not depend on CTA order
+    unsigned long long* out = a.rho_out + (size_t)env * M;
+    for (int j = tid; j < M; j += THREADS) {
+        unsigned long long val = hist.get(j);
+        if (j == 0) val += hist.get(M);
+        if (val) atomicAdd(out + j, val);
+    }
+    if (SUMS) {
+        double t2 = block_sum<THREADS>(s2, sm.red);
+        double t1 = block_sum<THREADS>(s1, sm.red);
+        if (tid == 0) {
+            double* p = a.partial + ((size_t)env * gridDim.x + blockIdx.x) * 2;
+            p[0] = t2; p[1] = t1;
+        }
+    }
+    if (err) atomicOr(a.err, err);
+}
+
+// ----------------------------------------------------------------- finalize
+struct FinalizeArgs {
+    MeshConst mc;
+    const unsigned long long* rho;     // [n_envs][M] state density (fixed point)
+    unsigned long long* rho_zero;      // [n_envs][M] or nullptr
+    double* n_out;                     // [n_envs][M]
+    double* E_out;                     // [n_envs][M]
+    double* diag;                      // [n_envs][DIAG_N]
+    const double* partial;             // [n_envs][n_partial][2] or nullptr
+    double* vsum;                      // [n_envs][2] local sum v^2, sum v (all-reduced by the host when sharded)
+    int n_partial;
+};
+
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) field_finalize_kernel(const FinalizeArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int env = blockIdx.x, M = a.mc.M, tid = threadIdx.x;
+    SmemLayout<double> sm(smem_raw, M);
+    GlobalRho rho{a.rho + (size_t)env * M};
+    double e2 = block_field<double, THREADS, true>(rho, sm.E_s, sm.D_s, sm.red, a.mc, nullptr,
+                                                   a.n_out + (size_t)env * M, a.E_out + (size_t)env * M);
+    if (a.rho_zero) for (int j = tid; j < M; j += THREADS) a.rho_zero[(size_t)env * M + j] = 0ull;
+    double s2 = 0.0, s1 = 0.0;
+    if (a.partial) {
+        const double* p = a.partial + (size_t)env * a.n_partial * 2;
+        for (int i = tid; i < a.n_partial; i += THREADS) { s2 += p[2 * i]; s1 += p[2 * i + 1]; }
+        s2 = block_sum<THREADS>(s2, sm.red);
+        s1 = block_sum<THREADS>(s1, sm.red);
+    }
+    if (tid == 0) {
+        double* d = a.diag + (size_t)env * DIAG_N;
+        d[DIAG_PE_MESH] = 0.5 * e2 * a.mc.dx;
+        d[DIAG_SUM_E2] = e2;
+        if (a.partial) {
+            a.vsum[env * 2] = s2; a.vsum[env * 2 + 1] = s1;
+            d[DIAG_KE] = 0.5 * s2; d[DIAG_SUM_V] = s1;
+        }
+    }
+}
+
+// ----------------------------------------------------------------- resident
+struct ResidentArgs {
+    MeshConst mc;
+    void* x; void* v;                  // [n_envs][ld]
+    long long N, ld;
+    int n_steps;                       // 0 => init only (wrap + deposit + field)
+    ActuatorArgs act;                  // ext: [n_envs][M]; coeffs: [n_steps][n_envs][2m]
+    long long coeff_step_stride;       // elements between consecutive steps of coeffs (0 => same every step)
+    long long ext_step_stride;         // same for ext
+    double c[4], d[4];
+    double* n_out;                     // [n_envs][M] state density after the last step
+    double* E_out;                     // [n_envs][M] self-consistent field after the last step
+    double* diag;                      // [n_envs][DIAG_N] after the last step
+    double* trace;                     // nullptr or [n_steps][n_envs][DIAG_N]
+    unsigned long long* rho_out;       // nullptr or [n_envs][M] fixed-point state density (for parity tests)
+    unsigned* err;
+};
+
+template <typename R, int THREADS, int PPT, int DEP, bool EXACT_W>
+__global__ void __launch_bounds__(THREADS) env_step_resident_kernel(const ResidentArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int tid = threadIdx.x, env = blockIdx.x, M = a.mc.M;
+    SmemLayout<R> sm(smem_raw, M);
+    Hist<DEP> hist; hist.init(sm.hist, M);
+    const PartConst<R> pc = make_part_const<R>(a.mc);
+    R* xe = (R*)a.x + (size_t)env * a.ld;
+    R* ve = (R*)a.v + (size_t)env * a.ld;
+    const int N = (int)a.N;
+
+    R xs[PPT], vs[PPT];
+#pragma unroll
+    for (int j = 0; j < PPT; ++j) {
+        int i = j * THREADS + tid;
+        xs[j] = i < N ? xe[i] : (R)0;
+        vs[j] = i < N ? ve[i] : (R)0;
+    }
+    hist.zero(M, tid, THREADS);
+    __syncthreads();
+    unsigned err = 0;
+    SharedRho<Hist<DEP>> rho{&hist, M};
+    double* n_out = a.n_out + (size_t)env * M;
+    double* E_out = a.E_out + (size_t)env * M;
+
+    auto write_diag = [&](double e2, int step) {
+        double s2 = 0.0, s1 = 0.0;
+#pragma unroll
+        for (int j = 0; j < PPT; ++j) {       // padded particles carry v == 0
+            s2 += (double)vs[j] * (double)vs[j]; s1 += (double)vs[j];
+        }
+        s2 = block_sum<THREADS>(s2, sm.red);
+        s1 = block_sum<THREADS>(s1, sm.red);
+        if (tid == 0) {
+            double rec[DIAG_N];
+            rec[DIAG_KE] = 0.5 * s2; rec[DIAG_PE_MESH] = 0.5 * e2 * a.mc.dx; rec[DIAG_SUM_V] = s1; rec[DIAG_SUM_E2] = e2;
+            double* d = a.diag + (size_t)env * DIAG_N;
+#pragma unroll
+            for (int k = 0; k < DIAG_N; ++k) d[k] = rec[k];
+            if (a.trace && step >= 0) {
+                double* t = a.trace + ((size_t)step * gridDim.x + env) * DIAG_N;
+#pragma unroll
+                for (int k = 0; k < DIAG_N; ++k) t[k] = rec[k];
+            }
+        }
+    };
+    auto dump_rho = [&]() {
+        if (a.rho_out) for (int j = tid; j < M; j += THREADS) a.rho_out[(size_t)env * M + j] = rho(j);
+    };
+
+    if (a.n_steps == 0) {                                         // pic.py:76-77 on a fresh state
+#pragma unroll
+        for (int j = 0; j < PPT; ++j) {
+            if (j * THREADS + tid < N) {
+                xs[j] = wrap_pos<R>(xs[j], pc);
+                deposit<R, EXACT_W>(xs[j], hist, pc, a.mc, err);
+            }
+        }
+        __syncthreads();
+        dump_rho();
+        double e2 = block_field<R, THREADS, true>(rho, sm.E_s, sm.D_s, sm.red, a.mc, nullptr, n_out, E_out);
+        write_diag(e2, -1);
+    }
+
+    for (int step = 0; step < a.n_steps; ++step) {
+        ActuatorArgs act = a.act;
+        if (act.coeffs) act.coeffs += (size_t)step * a.coeff_step_stride;
+        if (act.ext) act.ext += (size_t)step * a.ext_step_stride;
+        const double* ext = stage_ext<THREADS>(act, env, M, sm.ext_s);
+        const bool last = step == a.n_steps - 1;
+#pragma unroll 1
+        for (int st = 0; st < 4; ++st) {
+            const R cc = (R)a.c[st], dd = (R)a.d[st];
+            const bool fin = st == 3;
+#pragma unroll
+            for (int j = 0; j < PPT; ++j) {
+                if (j * THREADS + tid < N) {
+                    if (st > 0) kick<R, EXACT_W>(xs[j], vs[j], sm.E_s, dd, pc, M, err);
+                    xs[j] = drift<R>(xs[j], vs[j], cc, pc);
+                    R xw = wrap_pos<R>(xs[j], pc);
+                    if (fin) xs[j] = xw;                           // pic.py:139
+                    deposit<R, EXACT_W>(xw, hist, pc, a.mc, err);
+                }
+            }
+            __syncthreads();
+            if (!fin) {
+                block_field<R, THREADS, false>(rho, sm.E_s, sm.D_s, sm.red, a.mc, ext, nullptr, nullptr);
+            } else {
+                if (last) dump_rho();
+                double e2 = block_field<R, THREADS, true>(rho, sm.E_s, sm.D_s, sm.red, a.mc, nullptr,
+                                                          last ? n_out : nullptr, last ? E_out : nullptr);
+                write_diag(e2, step);
+            }
+            hist.zero(M, tid, THREADS);
+            __syncthreads();
+        }
+    }
+
+#pragma unroll
+    for (int j = 0; j < PPT; ++j) {
+        int i = j * THREADS + tid;
+        if (i < N) { xe[i] = xs[j]; ve[i] = vs[j]; }
+    }
+    if (err) atomicOr(a.err, err);
+}
+
+// ------------------------------------------------------------- small helpers
+template <typename T, typename U>
+__global__ void convert_kernel(const T* __restrict__ in, U* __restrict__ out, long long n) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        out[i] = (U)in[i];
+}
+
+}  // namespace pic

@@ -1,0 +1,17 @@
+// Case macros for the per-group variant translation units (split so that nvcc runs on all cores).
+#pragma once
+#include "pic_kernels.cuh"
+#include "pic_variants.h"
+
+#define PIC_S_CASE(R, T, U, MD, DP, EX) \
+    if (threads == T && unroll == U && mode == MD && dep == DP && exact_w == EX) \
+        return (const void*)&pic::push_stream_kernel<R, T, U, MD, DP, EX>;
+#define PIC_S_MODES(R, T, U, DP, EX) \
+    PIC_S_CASE(R, T, U, pic::MODE_DRIFT, DP, EX) PIC_S_CASE(R, T, U, pic::MODE_KICK, DP, EX) \
+    PIC_S_CASE(R, T, U, pic::MODE_FINAL, DP, EX) PIC_S_CASE(R, T, U, pic::MODE_INIT, DP, EX)
+#define PIC_S_DEPS(R, T, U, EX) PIC_S_MODES(R, T, U, pic::DEP_CAS64, EX) PIC_S_MODES(R, T, U, pic::DEP_SPLIT32, EX)
+
+#define PIC_R_CASE(R, T, P, DP, EX) \
+    if (threads == T && ppt == P && dep == DP && exact_w == EX) \
+        return (const void*)&pic::env_step_resident_kernel<R, T, P, DP, EX>;
+#define PIC_R_DEPS(R, T, P, EX) PIC_R_CASE(R, T, P, pic::DEP_CAS64, EX) PIC_R_CASE(R, T, P, pic::DEP_SPLIT32, EX)

@@ -1,0 +1,205 @@
+"""Thin object wrapper over one pic_handle (include/pic_b200.h).  All array arguments are numpy float64 unless a
+``*_device`` method is used; nothing here computes physics on the host."""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib as L
+
+_PREC = {"f64": L.PIC_F64, "fp64": L.PIC_F64, "float64": L.PIC_F64, "f32": L.PIC_F32, "fp32": L.PIC_F32,
+         "float32": L.PIC_F32}
+_MODE = {"auto": L.PIC_MODE_AUTO, "resident": L.PIC_MODE_RESIDENT, "streaming": L.PIC_MODE_STREAMING}
+_DEP = {"auto": L.PIC_DEPOSIT_AUTO, "cas64": L.PIC_DEPOSIT_CAS64, "split32": L.PIC_DEPOSIT_SPLIT32}
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _f64(a, shape):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    if a.size != int(np.prod(shape)):
+        raise ValueError("expected %s elements, got array of shape %s" % (shape, a.shape))
+    return a.reshape(shape)
+
+
+class DeviceArray:
+    """Zero-copy view of a device buffer owned by an Engine (``__cuda_array_interface__`` v3), so that
+    ``torch.as_tensor(view, device='cuda')`` aliases the particle / mesh arrays without a copy."""
+
+    def __init__(self, ptr, shape, typestr, strides=None, owner=None):
+        self._owner = owner
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False),
+                                         "version": 3, "strides": strides}
+
+
+class Engine:
+    def __init__(self, n_particles, n_mesh, L_box, dt, n0=1.0, n_envs=1, n_particles_total=0, precision="f64",
+                 mode="auto", deposit="auto", fixed_bits=0, exact_weights=False, device=0, max_mode=0, stream=None):
+        self._lib = L.load()
+        self._h = C.c_void_p()
+        cfg = L.PicConfig(int(n_particles), int(n_particles_total), int(n_mesh), int(n_envs), float(n0), float(L_box),
+                          float(dt), _PREC[precision], _MODE[mode], _DEP[deposit], int(fixed_bits),
+                          int(bool(exact_weights)), int(device), int(max_mode), C.c_void_p(stream or 0))
+        rc = self._lib.pic_create(C.byref(cfg), C.byref(self._h))
+        if rc != 0:
+            msg = self._lib.pic_last_error(None)
+            self._h = None
+            raise L.PicError(rc, msg.decode() if msg else "")
+        self.N, self.M, self.n_envs, self.m = int(n_particles), int(n_mesh), int(n_envs), int(max_mode)
+        self.precision = "f32" if _PREC[precision] == L.PIC_F32 else "f64"
+        self.device = int(device)
+
+    # ---- lifetime
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.pic_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc != 0:
+            msg = self._lib.pic_last_error(self._h)
+            raise L.PicError(rc, msg.decode() if msg else "")
+
+    # ---- state
+    def set_state(self, x, v):
+        x = _f64(x, (self.n_envs, self.N)); v = _f64(v, (self.n_envs, self.N))
+        self._ck(self._lib.pic_set_state(self._h, _ptr(x), _ptr(v)))
+
+    def set_state_device(self, x_ptr, v_ptr):
+        self._ck(self._lib.pic_set_state_device(self._h, C.c_void_p(x_ptr), C.c_void_p(v_ptr)))
+
+    def get_state(self, want_x=True, want_v=True):
+        x = np.empty((self.n_envs, self.N)) if want_x else None
+        v = np.empty((self.n_envs, self.N)) if want_v else None
+        self._ck(self._lib.pic_get_state(self._h, _ptr(x), _ptr(v)))
+        return x, v
+
+    def get_state_into(self, x, v):
+        """Copies into caller-provided (e.g. pinned) float64 buffers."""
+        self._ck(self._lib.pic_get_state(self._h, C.c_void_p(x), C.c_void_p(v)))
+
+    def get_fields(self):
+        n = np.empty((self.n_envs, self.M)); E = np.empty((self.n_envs, self.M))
+        self._ck(self._lib.pic_get_fields(self._h, _ptr(n), _ptr(E)))
+        return n, E
+
+    def get_density_fixed(self):
+        rho = np.empty((self.n_envs, self.M), dtype=np.uint64)
+        k = C.c_int32()
+        self._ck(self._lib.pic_get_density_fixed(self._h, _ptr(rho), C.byref(k)))
+        return rho, k.value
+
+    def get_diag(self):
+        d = np.empty((self.n_envs, L.DIAG_N))
+        self._ck(self._lib.pic_get_diag(self._h, _ptr(d)))
+        return d
+
+    def get_trace(self, n_steps):
+        t = np.empty((n_steps, self.n_envs, L.DIAG_N))
+        self._ck(self._lib.pic_get_trace(self._h, _ptr(t), n_steps))
+        return t
+
+    def get_cells(self, want_weights=True, want_E=True):
+        il = np.empty((self.n_envs, self.N), dtype=np.int32)
+        wl = np.empty((self.n_envs, self.N)) if want_weights else None
+        wr = np.empty((self.n_envs, self.N)) if want_weights else None
+        E = np.empty((self.n_envs, self.N)) if want_E else None
+        self._ck(self._lib.pic_get_cells(self._h, _ptr(il), _ptr(wl), _ptr(wr), _ptr(E)))
+        return il, wl, wr, E
+
+    # ---- hot path
+    def step_mesh(self, E_ext=None, n_steps=1):
+        e = None if E_ext is None else _f64(E_ext, (self.n_envs, self.M))
+        self._ck(self._lib.pic_step_mesh(self._h, _ptr(e), int(n_steps)))
+
+    def step_mesh_ptr(self, host_ptr, n_steps=1):
+        self._ck(self._lib.pic_step_mesh(self._h, C.c_void_p(host_ptr), int(n_steps)))
+
+    def set_actuator_basis(self, basis_cos, basis_sin):
+        bc = _f64(basis_cos, (self.M, self.m)); bs = _f64(basis_sin, (self.M, self.m))
+        self._ck(self._lib.pic_set_actuator_basis(self._h, _ptr(bc), _ptr(bs), self.m))
+
+    def step_coeffs(self, coeffs, n_steps=1):
+        c = _f64(coeffs, (n_steps, self.n_envs, 2 * self.m))
+        self._ck(self._lib.pic_step_coeffs(self._h, _ptr(c), int(n_steps)))
+
+    def step_coeffs_ptr(self, host_ptr, n_steps=1):
+        self._ck(self._lib.pic_step_coeffs(self._h, C.c_void_p(host_ptr), int(n_steps)))
+
+    def step_mesh_device(self, dev_ptr, n_steps=1):
+        self._ck(self._lib.pic_step_mesh_device(self._h, C.c_void_p(dev_ptr or 0), int(n_steps)))
+
+    def step_coeffs_device(self, dev_ptr, n_steps=1):
+        self._ck(self._lib.pic_step_coeffs_device(self._h, C.c_void_p(dev_ptr), int(n_steps)))
+
+    def sync(self):
+        self._ck(self._lib.pic_sync(self._h))
+
+    def set_stream(self, stream_ptr):
+        self._ck(self._lib.pic_set_stream(self._h, C.c_void_p(stream_ptr or 0)))
+
+    def error_flags(self):
+        f = C.c_uint32()
+        self._ck(self._lib.pic_get_error_flags(self._h, C.byref(f)))
+        return f.value
+
+    # ---- staged driving / sharding
+    def run_stage(self, stage):
+        self._ck(self._lib.pic_run_stage(self._h, int(stage)))
+
+    def stage_density_ptr(self, stage):
+        p = C.c_void_p()
+        self._ck(self._lib.pic_stage_density(self._h, int(stage), C.byref(p)))
+        return p.value
+
+    def set_stage_actuation(self, ext_dev=None, coeffs_dev=None):
+        self._ck(self._lib.pic_set_stage_actuation(self._h, C.c_void_p(ext_dev or 0), C.c_void_p(coeffs_dev or 0)))
+
+    def comm_init_rank(self, uid: bytes, rank, world):
+        self._ck(self._lib.pic_comm_init_rank(self._h, uid, int(rank), int(world)))
+
+    @staticmethod
+    def nccl_unique_id():
+        buf = C.create_string_buffer(128)
+        rc = L.load().pic_nccl_unique_id(buf)
+        if rc != 0:
+            raise L.PicError(rc, (L.load().pic_last_error(None) or b"").decode())
+        return buf.raw
+
+    # ---- introspection
+    def launch_info(self):
+        v = [C.c_int32() for _ in range(7)]
+        self._ck(self._lib.pic_get_launch_info(self._h, *[C.byref(a) for a in v]))
+        keys = ("mode", "threads", "per_thread", "grid_x", "smem_bytes", "fixed_bits", "deposit")
+        d = dict(zip(keys, [a.value for a in v]))
+        d["mode"] = "resident" if d["mode"] == L.PIC_MODE_RESIDENT else "streaming"
+        d["deposit"] = "split32" if d["deposit"] == L.PIC_DEPOSIT_SPLIT32 else "cas64"
+        return d
+
+    def set_tuning(self, threads=0, per_thread=0, ctas_per_sm=-1):
+        self._ck(self._lib.pic_set_tuning(self._h, int(threads), int(per_thread), int(ctas_per_sm)))
+
+    def launch_count(self):
+        return int(self._lib.pic_kernel_launch_count(self._h))
+
+    def views(self):
+        """Zero-copy device views: x, v as (n_envs, N) with env stride ld; n, E_mesh (n_envs, M); diag (n_envs, 4)."""
+        dv = L.PicDeviceViews()
+        self._ck(self._lib.pic_get_device_views(self._h, C.byref(dv)))
+        es = dv.elem_size
+        ts = "<f8" if es == 8 else "<f4"
+        return {
+            "x": DeviceArray(dv.x, (self.n_envs, self.N), ts, (dv.ld * es, es), self),
+            "v": DeviceArray(dv.v, (self.n_envs, self.N), ts, (dv.ld * es, es), self),
+            "n": DeviceArray(dv.n, (self.n_envs, self.M), "<f8", None, self),
+            "E_mesh": DeviceArray(dv.E_mesh, (self.n_envs, self.M), "<f8", None, self),
+            "diag": DeviceArray(dv.diag, (self.n_envs, L.DIAG_N), "<f8", None, self),
+            "ld": int(dv.ld),
+        }

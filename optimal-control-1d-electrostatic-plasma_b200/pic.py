@@ -1,0 +1,213 @@
+"""`PIC` -- the reference's env class (src/env/pic.py:11-173) with the step on a B200.
+
+Same constructor keywords, methods and attributes as the reference class, so `run_wo_oc.py` / `run_ddpg.py` and the
+DDPG / PPO / SAC trainers use it unchanged (see run.py for the launcher that injects it as `src.env.pic`).  What
+differs is where the work happens: `update_state` enqueues the Yoshida-4 step on the device through the C ABI
+(include/pic_b200.h); `.x`, `.v`, `.n`, `.E_mesh`, ... are fetched lazily and cached until the next step.
+There is no CPU implementation of the step in this package.
+"""
+from typing import Optional
+
+import numpy as np
+
+from . import _lib as L
+from .engine import Engine
+
+
+class PIC:
+    def __init__(self, N: int = 40000, N_mesh: int = 400, n0: float = 1.0, L: float = 50.0, dt: float = 1.0,
+                 tmin: float = 0.0, tmax: float = 50.0, gamma: float = 5.0, A: float = 0.1, n_mode: int = 4,
+                 interpol: str = "CIC", init_dist=None, *, device: int = 0, precision: str = "f64",
+                 mode: str = "auto", deposit: str = "auto", exact_weights: bool = False, max_mode: int = 0):
+        if interpol != "CIC":
+            raise NotImplementedError("interpol=%r: only the CIC deposit (src/env/interpolate.py:4) is on the device "
+                                      "path; TSC is listed as 'next' in DESIGN.md" % (interpol,))
+        self.N = N
+        self.N_mesh = N_mesh
+        self.n0 = n0
+        self.L = L
+        self.dt = dt
+        self.tmin = tmin
+        self.tmax = tmax
+        self.dx = L / N_mesh
+        self.gamma = gamma           # the reference's Sherman-Morrison parameter; E does not depend on it
+        self.A = A
+        self.n_mode = n_mode
+        self.init_dist = init_dist
+        self.interpol = interpol
+        self._opts = dict(device=device, precision=precision, mode=mode, deposit=deposit,
+                          exact_weights=exact_weights, max_mode=max_mode)
+        self._eng: Optional[Engine] = None
+        self._cache = {}
+        self._basis_set = False
+        if init_dist is not None:
+            self.initialize()
+
+    # ------------------------------------------------------------------ engine
+    def _engine(self) -> Engine:
+        if self._eng is None:
+            o = self._opts
+            self._eng = Engine(self.N, self.N_mesh, self.L, self.dt, n0=self.n0, n_envs=1, precision=o["precision"],
+                               mode=o["mode"], deposit=o["deposit"], exact_weights=o["exact_weights"],
+                               device=o["device"], max_mode=o["max_mode"])
+        return self._eng
+
+    @property
+    def engine(self) -> Engine:
+        return self._engine()
+
+    # ------------------------------------------------------- src/env/pic.py:63-91
+    def initialize(self):
+        self.init_dist.reinit()
+        x, v = self.init_dist.get_sample()
+        x = np.asarray(x, dtype=np.float64).reshape(-1, 1)
+        v = np.asarray(v, dtype=np.float64).reshape(-1, 1)
+        v *= (1 + self.A * np.sin(2 * np.pi * self.n_mode * x / self.L))     # pic.py:68
+        if self.dt > 2 / np.sqrt(self.N / self.L):                           # pic.py:71-73
+            self.dt = 2 / np.sqrt(self.N / self.L)
+            print("CFL condtion invalid: change dt = {:.4f}".format(self.dt))
+            if self._eng is not None:
+                self._eng.close()
+                self._eng = None
+        self.set_state(x, v)
+
+    def reinit(self):
+        self.initialize()
+
+    def set_state(self, x, v):
+        """Env checkpoint restore: load particles and rebuild density / field on the device (pic.py:76-77)."""
+        self._engine().set_state(np.asarray(x, dtype=np.float64).reshape(1, -1),
+                                 np.asarray(v, dtype=np.float64).reshape(1, -1))
+        self._cache = {}
+
+    # ----------------------------------------------------- src/env/pic.py:131-146
+    def update_state(self, E_external: Optional[np.ndarray] = None):
+        eng = self._engine()
+        if E_external is None:
+            eng.step_mesh(None, 1)
+        else:
+            eng.step_mesh(np.asarray(E_external, dtype=np.float64).reshape(1, self.N_mesh), 1)
+        self._cache = {}
+
+    def update_state_coeffs(self, coeff_cos, coeff_sin, basis_cos=None, basis_sin=None):
+        """update_state(E_field.compute_E()) without building the mesh vector on the host: the device evaluates
+        basis_cos @ a + basis_sin @ b (src/control/actuator.py:62).  Needs max_mode at construction."""
+        eng = self._engine()
+        if basis_cos is not None:
+            eng.set_actuator_basis(basis_cos, basis_sin)
+            self._basis_set = True
+        if not self._basis_set:
+            raise RuntimeError("pass basis_cos / basis_sin (E_field.basis_cos / .basis_sin) on the first call")
+        c = np.concatenate([np.asarray(coeff_cos, dtype=np.float64).ravel(),
+                            np.asarray(coeff_sin, dtype=np.float64).ravel()])
+        eng.step_coeffs(c.reshape(1, 1, -1), 1)
+        self._cache = {}
+
+    # ------------------------------------------------------------------ getters
+    def _state(self):
+        if "xv" not in self._cache:
+            x, v = self._engine().get_state()
+            self._cache["xv"] = (x.reshape(-1, 1), v.reshape(-1, 1))
+        return self._cache["xv"]
+
+    @property
+    def x(self):
+        return self._state()[0]
+
+    @x.setter
+    def x(self, value):
+        self.set_state(value, self._state()[1])
+
+    @property
+    def v(self):
+        return self._state()[1]
+
+    @v.setter
+    def v(self, value):
+        self.set_state(self._state()[0], value)
+
+    def get_state(self):                                               # pic.py:165-167
+        x, v = self._state()
+        return np.concatenate([x.copy().reshape(-1, 1), v.copy().reshape(-1, 1)], axis=0)
+
+    def _diag(self):
+        if "diag" not in self._cache:
+            self._cache["diag"] = self._engine().get_diag()[0]
+        return self._cache["diag"]
+
+    def get_electric_energy(self):                                     # util.py:119-131
+        PE = float(self._diag()[L.DIAG_PE_MESH])
+        PE *= self.N / self.L
+        return PE
+
+    def get_energy(self):                                              # util.py:133-147
+        return float(self._diag()[L.DIAG_KE]) + self.get_electric_energy()
+
+    def get_kinetic_energy(self):
+        return float(self._diag()[L.DIAG_KE])
+
+    def get_mesh_energy(self):
+        """0.5 * sum(E_mesh^2) * dx of the self-consistent field: the reward's energy term
+        (src/control/objective.py:31) for the current state."""
+        return float(self._diag()[L.DIAG_PE_MESH])
+
+    def _fields(self):
+        if "fields" not in self._cache:
+            n, E = self._engine().get_fields()
+            self._cache["fields"] = (n[0], E[0].reshape(-1, 1))
+        return self._cache["fields"]
+
+    @property
+    def n(self):
+        return self._fields()[0]
+
+    @property
+    def E_mesh(self):
+        return self._fields()[1]
+
+    def _cells(self):
+        if "cells" not in self._cache:
+            il, wl, wr, E = self._engine().get_cells()
+            self._cache["cells"] = (il[0].astype(np.int64).reshape(-1, 1), wl[0].reshape(-1, 1), wr[0].reshape(-1, 1),
+                                    E[0].reshape(-1, 1))
+        return self._cache["cells"]
+
+    @property
+    def indx_l(self):
+        return self._cells()[0]
+
+    @property
+    def indx_r(self):
+        return np.mod(self._cells()[0] + 1, self.N_mesh)
+
+    @property
+    def weight_l(self):
+        return self._cells()[1]
+
+    @property
+    def weight_r(self):
+        return self._cells()[2]
+
+    @property
+    def E(self):
+        return self._cells()[3]
+
+    indx_m = None
+    weight_m = None
+
+    def update_params(self, **kwargs):                                 # pic.py:79-82
+        for key in kwargs.keys():
+            if hasattr(self, key) is True and kwargs[key] is not None:
+                setattr(self, key, kwargs[key])
+
+    def simulate(self, E_external_traj=None, n_steps: Optional[int] = None):
+        """Trajectory driver in the spirit of pic.py:175 (unused by the runners): returns (snapshot (2N, Nt+1),
+        H (Nt+1,), PE (Nt+1,))."""
+        Nt = int(np.ceil((self.tmax - self.tmin) / self.dt)) if n_steps is None else int(n_steps)
+        snap = [self.get_state()]
+        H = [self.get_energy()]
+        PE = [self.get_electric_energy()]
+        for i in range(Nt):
+            self.update_state(None if E_external_traj is None else E_external_traj[i])
+            snap.append(self.get_state()); H.append(self.get_energy()); PE.append(self.get_electric_energy())
+        return np.concatenate(snap, axis=1), np.array(H), np.array(PE)

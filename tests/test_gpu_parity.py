@@ -1,0 +1,251 @@
+"""Parity of the CUDA path (through the C ABI / the PIC duck-type) against the golden vectors of the reference and
+against the oracle.  Tolerances (DESIGN.md "Numerics"): cell indices bit-exact; fp64 per step |dx|,|dv| <= 1e-12,
+|dE_mesh| <= 1e-12*max|E|; 500-step energy trace rel 1e-9."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from oracle import pic_oracle as O  # noqa: E402  (checker only)
+
+
+def _engine(N, M, L, dt, **kw):
+    from pic_b200 import Engine
+    return Engine(N, M, L, dt, **kw)
+
+
+CONFIGS = [dict(mode="resident", deposit="cas64"), dict(mode="resident", deposit="split32"),
+           dict(mode="streaming", deposit="cas64"), dict(mode="streaming", deposit="split32")]
+
+
+@pytest.mark.parametrize("cfg", CONFIGS, ids=lambda c: c["mode"] + "-" + c["deposit"])
+@pytest.mark.parametrize("LM", [(50.0, 250), (50.0, 500), (50.0, 4096), (10.0, 64)])
+def test_wrap_index_deposit_edge_cases(golden, cfg, LM):
+    """np.mod(np.mod(x,L),L), floor(x/dx) and the CIC density on adversarial positions (cell edges +-1ulp, 0, -0, L,
+    far outside) -- wrap and index bit-exact."""
+    g = golden("deposit_edges")
+    L, M = LM
+    key = f"L{L:g}_M{M}"
+    x = g[key + "_x"]
+    N = x.shape[0]
+    eng = _engine(N, M, L, 0.01, **cfg)
+    eng.set_state(x[None], np.zeros((1, N)))
+    xs, _ = eng.get_state()
+    assert np.array_equal(xs[0], g[key + "_xw"])
+    il, wl, wr, _ = eng.get_cells()
+    assert np.array_equal(il[0], g[key + "_cic_il"])
+    assert np.abs(wl[0] - g[key + "_cic_wl"]).max() < 4e-16 * M      # 1/dx multiply vs divide: <= 1 ulp of x/dx
+    assert np.abs(wr[0] - g[key + "_cic_wr"]).max() < 4e-16 * M
+    n, _ = eng.get_fields()
+    assert np.abs(n[0] - g[key + "_cic_n"]).max() < 1e-12 * g[key + "_cic_n"].max()
+    assert eng.error_flags() == 0
+    rho, k = eng.get_density_fixed()
+    assert abs(int(rho.sum()) - N * (1 << k)) <= N                    # total charge: every particle deposits w_l + w_r = 1
+
+
+@pytest.mark.parametrize("cfg", CONFIGS, ids=lambda c: c["mode"] + "-" + c["deposit"])
+@pytest.mark.parametrize("name", ["bump_vb3", "twostream_vb3"])
+def test_steps_vs_reference_golden(golden, cfg, name):
+    g = golden(name)
+    N, M, L, dt = int(g["N"]), int(g["N_mesh"]), float(g["L"]), float(g["dt"])
+    eng = _engine(N, M, L, dt, **cfg)
+    eng.set_state(g["t0_x"][None], g["t0_v"][None])
+    n, E = eng.get_fields()
+    assert np.abs(n[0] - g["t0_n"]).max() < 1e-12
+    assert np.abs(E[0] - g["t0_E_mesh"]).max() < 1e-12 * np.abs(g["t0_E_mesh"]).max()
+    d = eng.get_diag()[0]
+    assert abs(d[1] * N / L - g["PE"][0]) < 1e-11 * g["PE"][0]
+    assert abs(d[0] + d[1] * N / L - g["H"][0]) < 1e-12 * g["H"][0]
+    done = 0
+    for t in (1, 10):
+        eng.step_mesh(None, t - done)
+        done = t
+        x, v = eng.get_state()
+        assert np.abs(x[0] - g[f"t{t}_x"]).max() < 1e-12
+        assert np.abs(v[0] - g[f"t{t}_v"]).max() < 1e-12
+        il, wl, wr, Ep = eng.get_cells()
+        assert np.array_equal(il[0], g[f"t{t}_indx_l"])
+        n, E = eng.get_fields()
+        assert np.abs(n[0] - g[f"t{t}_n"]).max() < 1e-12
+        assert np.abs(E[0] - g[f"t{t}_E_mesh"]).max() < 1e-12 * np.abs(g[f"t{t}_E_mesh"]).max()
+        assert np.abs(Ep[0] - g[f"t{t}_E"]).max() < 1e-12 * np.abs(g[f"t{t}_E"]).max()
+        d = eng.get_diag()[0]
+        assert abs(d[1] - g["PE_mesh"][t]) < 1e-11 * g["PE_mesh"][t]
+        assert abs(d[0] + d[1] * N / L - g["H"][t]) < 1e-12 * g["H"][t]
+        assert abs(d[2] - g["sum_v"][t]) < 1e-9
+    assert eng.error_flags() == 0
+
+
+@pytest.mark.parametrize("mode", ["resident", "streaming"])
+@pytest.mark.parametrize("name,rate", [("bump_vb3", -0.001295), ("twostream_vb3", 0.021354), ("bump_vb5", 0.005568)])
+def test_500_step_energy_trace_and_growth_rate(golden, mode, name, rate):
+    g = golden(name)
+    N, M, L, dt = int(g["N"]), int(g["N_mesh"]), float(g["L"]), float(g["dt"])
+    eng = _engine(N, M, L, dt, mode=mode)
+    eng.set_state(g["t0_x"][None], g["t0_v"][None])
+    eng.step_mesh(None, 500)
+    tr = eng.get_trace(500)[:, 0, :]
+    pe = tr[:, 1]
+    assert np.max(np.abs(pe - g["PE_mesh"][1:]) / g["PE_mesh"][1:]) < 1e-9
+    H = tr[:, 0] + pe * N / L
+    assert np.max(np.abs(H - g["H"][1:]) / g["H"][1:]) < 1e-10
+    assert np.max(np.abs(tr[:, 2] - g["sum_v"][0])) < 1e-9                  # momentum conserved without control
+    assert abs(O.growth_rate(pe, 50.0) - rate) < 1e-6
+    x, v = eng.get_state()
+    assert np.abs(x[0] - g["t500_x"]).max() < 1e-6                          # chaos-amplified ulp noise
+    il, *_ = eng.get_cells(False, False)
+    assert np.array_equal(il[0], g["t500_indx_l"])
+
+
+@pytest.mark.parametrize("mode", ["resident", "streaming"])
+@pytest.mark.parametrize("name,steps,m", [("bump_vb3_constctrl", 10, 3), ("bump_vb3_randctrl", 200, 3), ("sac_cfg", 40, 5)])
+@pytest.mark.parametrize("path", ["mesh", "coeffs"])
+def test_controlled_runs(golden, mode, name, steps, m, path):
+    """E_external as the reference's (N_mesh,1) vector (util.py:102-103) and through the coefficient fast path."""
+    g = golden(name)
+    N, M, L, dt = int(g["N"]), int(g["N_mesh"]), float(g["L"]), float(g["dt"])
+    eng = _engine(N, M, L, dt, mode=mode, max_mode=m)
+    eng.set_state(g["t0_x"][None], g["t0_v"][None])
+    pe = []
+    if path == "mesh":
+        for t in range(steps):
+            eng.step_mesh(g["E_ext"][t][None], 1)
+            pe.append(eng.get_diag()[0, 1])
+    else:
+        eng.set_actuator_basis(g["basis_cos"], g["basis_sin"])
+        eng.step_coeffs(g["coeffs"][:steps, None, :], steps)
+        pe = list(eng.get_trace(steps)[:, 0, 1])
+    pe = np.array(pe)
+    assert np.max(np.abs(pe - g["PE_mesh"][1:steps + 1]) / g["PE_mesh"][1:steps + 1]) < 1e-9
+    x, v = eng.get_state()
+    tol = 1e-12 if steps <= 10 else 1e-8
+    assert np.abs(x[0] - g[f"t{steps}_x"]).max() < tol
+    assert np.abs(v[0] - g[f"t{steps}_v"]).max() < tol
+    il, *_ = eng.get_cells(False, False)
+    assert np.array_equal(il[0], g[f"t{steps}_indx_l"])
+    # reward of every transition uses the PRE-step field energy (ddpg.py:455, reward.py:71-76)
+    pe_pre = np.concatenate([[g["PE_mesh"][0]], pe[:-1]])
+    r = [O.reward(pe_pre[t], g["coeffs"][t], L) for t in range(steps)]
+    assert np.max(np.abs(np.array(r) - g["rewards"][:steps])) < 1e-9
+
+
+def test_dt_clip_case(golden):
+    g = golden("clip_dt")
+    N, M, L, dt = int(g["N"]), int(g["N_mesh"]), float(g["L"]), float(g["dt"])
+    import pic_b200
+    assert pic_b200._lib.load().pic_clip_dt(0.1, N, L) == dt
+    eng = _engine(N, M, L, dt)
+    assert eng.launch_info()["mode"] == "streaming"
+    eng.set_state(g["t0_x"][None], g["t0_v"][None])
+    eng.step_mesh(None, 5)
+    x, v = eng.get_state()
+    assert np.abs(x[0] - g["t5_x"]).max() < 1e-12
+    assert np.abs(v[0] - g["t5_v"]).max() < 1e-12
+    d = eng.get_diag()[0]
+    assert abs(d[0] + d[1] * N / L - g["H"][5]) < 1e-12 * g["H"][5]
+
+
+def test_bitwise_reproducibility_across_kernels(golden):
+    """The integer deposit makes the density -- and with it x, v -- independent of kernel flavour, thread count and
+    CTA count: resident vs streaming, cas64 vs split32, different launch shapes give IDENTICAL bits."""
+    g = golden("bump_vb3")
+    N, M, L, dt = int(g["N"]), int(g["N_mesh"]), float(g["L"]), float(g["dt"])
+    outs = []
+    variants = [dict(mode="resident", deposit="cas64"), dict(mode="resident", deposit="split32"),
+                dict(mode="streaming", deposit="cas64"), dict(mode="streaming", deposit="split32")]
+    tunings = [None, None, (512, 1, 1), (256, 4, 2)]
+    for cfg, tune in zip(variants, tunings):
+        eng = _engine(N, M, L, dt, **cfg)
+        if tune:
+            eng.set_tuning(*tune)
+        eng.set_state(g["t0_x"][None], g["t0_v"][None])
+        eng.step_mesh(None, 25)
+        x, v = eng.get_state()
+        rho, k = eng.get_density_fixed()
+        outs.append((x, v, rho))
+    for o in outs[1:]:
+        assert np.array_equal(o[0], outs[0][0]) and np.array_equal(o[1], outs[0][1]) and np.array_equal(o[2], outs[0][2])
+
+
+@pytest.mark.parametrize("N,M", [(1_000_003, 4096), (300_000, 1000)])
+def test_streaming_large_vs_oracle(N, M):
+    """Ragged N (odd, not a multiple of any tile) against the lean oracle for two steps with an external field."""
+    rng = np.random.RandomState(5)
+    L = 50.0
+    x = rng.uniform(0, L, N)
+    v = rng.normal(0, 1, N) + 3.0 * (rng.uniform(size=N) < 0.2)
+    dt = O.clip_dt(0.1, N, L)
+    p = O.PicParams(N=N, N_mesh=M, n0=1.0, L=L, dt=dt)
+    ext = 0.3 * np.sin(2 * np.pi * np.arange(M) / M) + 0.1
+    eng = _engine(N, M, L, dt, mode="streaming")
+    eng.set_state(x[None], v[None])
+    xo, vo = x, v
+    for _ in range(2):
+        o = O.step(xo, vo, p, ext)
+        xo, vo = o["x"], o["v"]
+    eng.step_mesh(ext[None], 2)
+    xg, vg = eng.get_state()
+    assert np.abs(xg[0] - xo).max() < 1e-12
+    assert np.abs(vg[0] - vo).max() < 1e-12
+    il, *_ = eng.get_cells(False, False)
+    assert np.array_equal(il[0], o["indx_l"])
+    n, E = eng.get_fields()
+    assert np.abs(E[0] - o["E_mesh"]).max() < 1e-11 * max(1.0, np.abs(o["E_mesh"]).max())
+    assert eng.error_flags() == 0
+
+
+def test_batched_envs_match_single_env(golden):
+    """Env b of a batch is bit-identical to the same env advanced alone (same kernel, same integer deposit)."""
+    from pic_b200 import BatchedPIC, Engine
+    from pic_b200.dist import BumpOnTail
+    B, N, M, L = 6, 5000, 250, 50.0
+    bp = BatchedPIC(B, N=N, N_mesh=M, L=L, dt=0.05, max_mode=3)
+    xs, vs = bp.reset_from_sampler(lambda: BumpOnTail(a=0.2, v0=3.0, sigma=1.0, n_samples=N, L=L), seed=42)
+    rng = np.random.RandomState(0)
+    acts = rng.uniform(-1, 1, size=(7, B, 6))
+    out = bp.step(acts, n_steps=7)
+    state = bp.get_state()
+    bc, bs = O.actuator_basis(L, M, 3)
+    for b in (0, 3, 5):
+        e1 = Engine(N, M, L, 0.05, max_mode=3)
+        e1.set_actuator_basis(bc, bs)
+        e1.set_state(xs[b][None], vs[b][None])
+        e1.step_coeffs(acts[:, b:b + 1, :], 7)
+        x1, v1 = e1.get_state()
+        assert np.array_equal(state[b, :N], x1[0]) and np.array_equal(state[b, N:], v1[0])
+        assert np.array_equal(out["pe_mesh"][:, b], e1.get_trace(7)[:, 0, 1])
+    # env 0 against the oracle (seed 42 + 0 is the runner's own sample #1; any seed works for parity)
+    p = O.PicParams(N=N, N_mesh=M, n0=1.0, L=L, dt=0.05)
+    xo, vo = xs[0], vs[0]
+    pe_pre = O.pe_mesh(O.mesh_field_of_state(xo, p), p.dx)
+    for t in range(7):
+        o = O.step(xo, vo, p, O.actuator_field(bc, bs, acts[t, 0, :3], acts[t, 0, 3:]))
+        assert abs(out["reward"][t, 0] - O.reward(pe_pre, acts[t, 0], L)) < 1e-9
+        xo, vo = o["x"], o["v"]
+        pe_pre = O.pe_mesh(o["E_mesh"], p.dx)
+        assert abs(out["pe_mesh"][t, 0] - pe_pre) < 1e-10 * max(1.0, pe_pre)
+    assert np.abs(state[0, :N] - xo).max() < 1e-11 and np.abs(state[0, N:] - vo).max() < 1e-11
+
+
+def test_pic_class_is_a_drop_in(golden):
+    """The reference's constructor sequence through our classes: seed 42, dist ctor (sample discarded), PIC()
+    (second sample, perturbation, fields), then the runner loop of run_wo_oc.py:108-122."""
+    from pic_b200 import PIC
+    from pic_b200.dist import BumpOnTail
+    g = golden("bump_vb3")
+    np.random.seed(42)                                   # what importing src/env/pic.py does (pic.py:12)
+    dist = BumpOnTail(a=0.2, v0=3.0, sigma=1.0, n_samples=5000, L=50.0)
+    sim = PIC(N=5000, N_mesh=250, n0=1.0, L=50.0, dt=0.1, tmin=0.0, tmax=50.0, gamma=5.0, A=0.1, n_mode=2,
+              interpol="CIC", init_dist=dist)
+    assert np.array_equal(sim.x[:, 0], g["t0_x"]) and np.array_equal(sim.v[:, 0], g["t0_v"])
+    assert sim.x.shape == (5000, 1) and sim.get_state().shape == (10000, 1)
+    assert abs(sim.get_energy() - g["H"][0]) < 1e-12 * g["H"][0]
+    for t in range(1, 11):
+        sim.update_state(None)
+        assert abs(sim.get_energy() - g["H"][t]) < 1e-12 * g["H"][t]
+        assert abs(sim.get_electric_energy() - g["PE"][t]) < 1e-11 * g["PE"][t]
+    assert np.abs(sim.x[:, 0] - g["t10_x"]).max() < 1e-12
+    assert np.array_equal(sim.indx_l[:, 0], g["t10_indx_l"].astype(np.int64))
+    assert np.abs(sim.E_mesh[:, 0] - g["t10_E_mesh"]).max() < 1e-12
+    with pytest.raises(NotImplementedError):
+        PIC(N=100, N_mesh=10, interpol="TSC", init_dist=dist)
