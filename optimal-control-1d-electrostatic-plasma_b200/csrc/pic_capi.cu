@@ -95,7 +95,6 @@ struct pic_handle {
     int rank = 0, world = 1;
 
     long long launches = 0;
-    int ablate = 0;                                 // PIC_ABLATE (profiling only, see StreamArgs::ablate)
     std::string last_error;
 };
 
@@ -126,7 +125,8 @@ const void* resident_kernel(const pic_handle* h) {
                   : resident_kernel_f64(h->threads, h->per_thread, h->dep, h->exact_w);
 }
 size_t smem_for(const pic_handle* h) {
-    return h->f32 ? stream_smem_bytes<float>(h->M, h->threads) : stream_smem_bytes<double>(h->M, h->threads);
+    return h->f32 ? smem_plan_bytes<float>(h->M, h->threads, h->resident)
+                  : smem_plan_bytes<double>(h->M, h->threads, h->resident);
 }
 
 int configure_launch(pic_handle* h) {
@@ -163,7 +163,7 @@ int configure_launch(pic_handle* h) {
     if (h->partial) { cudaFree(h->partial); h->partial = nullptr; }
     CK(h, cudaMalloc(&h->partial, sizeof(double) * 2 * (size_t)h->grid_x * h->n_envs));
     const void* kf = (const void*)&field_finalize_kernel<256>;
-    CK(h, cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stream_smem_bytes<double>(h->M, 256)));
+    CK(h, cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_plan_bytes<double>(h->M, 256, false)));
     return PIC_OK;
 }
 
@@ -191,7 +191,7 @@ __global__ void cells_kernel(const R* __restrict__ x, long long N, long long ld,
     const int env = blockIdx.y;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (long long)gridDim.x * blockDim.x) {
         R a, b; unsigned err = 0;
-        R xw = wrap_pos<R>(x[(size_t)env * ld + i], pc);
+        R xw = wrap_pos<R>(x[(size_t)env * ld + i], pc, err);
         Cell c = cell_weights<R, EXACT_W>(xw, pc, mc.M, a, b, err);
         size_t o = (size_t)env * N + i;
         if (il) il[o] = c.il;
@@ -212,7 +212,7 @@ int run_stage(pic_handle* h, int stage, const double* ext, const double* coeffs,
         f.partial = h->partial; f.vsum = h->vsum; f.n_partial = h->grid_x;
         void* args[] = {&f};
         CK(h, cudaLaunchKernel((const void*)&field_finalize_kernel<256>, dim3(h->n_envs), dim3(256), args,
-                               stream_smem_bytes<double>(h->M, 256), h->stream));
+                               smem_plan_bytes<double>(h->M, 256, false), h->stream));
         h->launches++;
         if (h->world > 1) {
             int r = nccl_api().allreduce(h->vsum, h->vsum, 2 * (size_t)h->n_envs, kNcclFloat64, kNcclSum, h->comm, h->stream);
@@ -227,7 +227,7 @@ int run_stage(pic_handle* h, int stage, const double* ext, const double* coeffs,
     StreamArgs a{};
     a.mc = h->mc; a.x = h->x; a.v = h->v; a.N = h->N; a.ld = h->ld;
     a.act.ext = ext; a.act.coeffs = coeffs; a.act.bcos = h->bcos; a.act.bsin = h->bsin; a.act.m = h->m;
-    a.partial = h->partial; a.err = h->err; a.ablate = h->ablate;
+    a.partial = h->partial; a.err = h->err;
     int mode, out;
     switch (stage) {
         case -1: mode = MODE_INIT; a.rho_out = h->rho[3]; out = 3; a.c = 0; a.d = 0; break;
@@ -354,7 +354,6 @@ int pic_create(const pic_config* cfg, pic_handle** out) {
     h->m = cfg->max_mode > 0 ? cfg->max_mode : 0;
     h->ld = (h->N + 15) / 16 * 16;
     yoshida(h->cs, h->ds);
-    if (const char* ab = getenv("PIC_ABLATE")) h->ablate = atoi(ab);
 
     MeshConst& mc = h->mc;
     mc.M = h->M; mc.L = cfg->L; mc.dx = cfg->L / cfg->n_mesh; mc.inv_dx = 1.0 / mc.dx; mc.n0 = cfg->n0; mc.dt = cfg->dt;
@@ -364,12 +363,12 @@ int pic_create(const pic_config* cfg, pic_handle** out) {
         double per_cell = (double)h->Ntotal / h->M;
         if (per_cell < 1) per_cell = 1;
         k = 62 - (int)ceil(log2(8.0 * per_cell));
-        if (k > 52) k = 52;
+        if (k > 50) k = 50;
         if (k < 20) k = 20;
     }
-    if (k > 60) { delete h; return fail(nullptr, PIC_EINVAL, "fixed_bits must be <= 60"); }
+    if (k > 50) { delete h; return fail(nullptr, PIC_EINVAL, "fixed_bits must be <= 50"); }
     h->fixed_bits = k;
-    mc.fix_scale = ldexp(1.0, k); mc.inv_fix = ldexp(1.0, -k);
+    mc.fix_scale = ldexp(1.0, k); mc.inv_fix = ldexp(1.0, -k); mc.fix_one = 1LL << k;
     mc.idx_thr = (double)h->M * (h->f32 ? ldexp(1.0, -20) : ldexp(1.0, -49));
 
     h->dep = cfg->deposit == PIC_DEPOSIT_SPLIT32 ? DEP_SPLIT32 : DEP_CAS64;

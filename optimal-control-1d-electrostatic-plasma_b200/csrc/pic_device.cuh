@@ -44,9 +44,16 @@ template <> struct RT<double> {
     static __device__ __forceinline__ double rnd(double a) { return rint(a); }
     static __device__ __forceinline__ double mod(double a, double b) { return fmod(a, b); }
     static __device__ __forceinline__ double abs(double a) { return fabs(a); }
-    static __device__ __forceinline__ long long fix(double w, double s) { return __double2ll_rn(__dmul_rn(w, s)); }
     static __device__ __forceinline__ int toint(double a) { return __double2int_rd(a); }
     static __device__ __forceinline__ double fromint(int a) { return __int2double_rn(a); }
+    // round-to-nearest-even integer of q (|q| < 2^31) on the fp64 add pipe: adding 2^52+2^51 leaves rint(q) in the
+    // low mantissa word.  No F2I / FRND (those run at a fraction of the DADD rate).
+    static __device__ __forceinline__ double rint_magic(double q, int& i) {
+        const double MAGIC = 6755399441055744.0;
+        double t = __dadd_rn(q, MAGIC);
+        i = __double2loint(t);
+        return __dsub_rn(t, MAGIC);
+    }
 };
 
 template <> struct RT<float> {
@@ -60,10 +67,29 @@ template <> struct RT<float> {
     static __device__ __forceinline__ float rnd(float a) { return rintf(a); }
     static __device__ __forceinline__ float mod(float a, float b) { return fmodf(a, b); }
     static __device__ __forceinline__ float abs(float a) { return fabsf(a); }
-    static __device__ __forceinline__ long long fix(float w, double s) { return __double2ll_rn(__dmul_rn((double)w, s)); }
     static __device__ __forceinline__ int toint(float a) { return __float2int_rd(a); }
     static __device__ __forceinline__ float fromint(int a) { return __int2float_rn(a); }
+    static __device__ __forceinline__ float rint_magic(float q, int& i) {       // |q| < 2^22
+        const float MAGIC = 12582912.0f;
+        float t = __fadd_rn(q, MAGIC);
+        i = __float_as_int(t) - __float_as_int(MAGIC);
+        return __fsub_rn(t, MAGIC);
+    }
 };
+
+// llrint(w * 2^k) for |w * 2^k| < 2^51 without a conversion instruction: one fused multiply-add against the magic
+// constant rounds (w*2^k is exact) to an integer held in the mantissa.
+__device__ __forceinline__ long long fix_weight(double w, double fix_scale) {
+    const double MAGIC = 6755399441055744.0;
+    double t = __fma_rn(w, fix_scale, MAGIC);
+    return __double_as_longlong(t) - __double_as_longlong(MAGIC);
+}
+
+// gather table entry: (E_j, E_{j+1 mod M}) side by side so that the CIC gather is ONE 16-byte (8-byte in f32)
+// shared load instead of two loads with independent bank conflicts
+template <typename R> struct PairT;
+template <> struct PairT<double> { using type = double2; };
+template <> struct PairT<float> { using type = float2; };
 
 // ------------------------------------------------------------ kernel parameters
 struct MeshConst {
@@ -73,6 +99,7 @@ struct MeshConst {
     double scale;          // n0 * L / N / dx, left to right (src/env/interpolate.py:18)
     double fix_scale;      // 2^k
     double inv_fix;        // 2^-k
+    long long fix_one;     // 2^k as an integer: what one particle deposits in total
     double idx_thr;        // |q - rint(q)| below this => redo the cell index with IEEE division
     double dt;
 };
@@ -95,39 +122,72 @@ __host__ __device__ inline PartConst<R> make_part_const(const MeshConst& m) {
 // exact value of that sequence: [L,2L) -> x-L is exact (Sterbenz); (-L,0) -> fl(x+L), which can round to L and
 // is then sent to 0 by the second mod.
 template <typename R>
-__device__ __forceinline__ R wrap_pos(R x, const PartConst<R>& c) {
+__device__ __noinline__ R wrap_pos_far(R x, R L, unsigned* err) {       // cold: |x| >= 2L or non-finite
+    if (!(RT<R>::abs(x) <= (R)3.0e38)) { *err |= ERR_NONFINITE; return (R)0; }
+    R r = RT<R>::mod(x, L);
+    if (r != (R)0) { if (r < (R)0) r = RT<R>::add(r, L); } else r = (R)0;
+    R r2 = RT<R>::mod(r, L);                         // second mod: only r == L changes
+    if (r2 != (R)0) { if (r2 < (R)0) r2 = RT<R>::add(r2, L); } else r2 = (R)0;
+    return r2;
+}
+
+template <typename R>
+__device__ __forceinline__ R wrap_pos(R x, const PartConst<R>& c, unsigned& err) {
     if (x >= (R)0 && x < c.L) return x;
     if (x >= c.L && x < c.twoL) return RT<R>::sub(x, c.L);
     if (x < (R)0 && x > -c.L) {
         R r = RT<R>::add(x, c.L);
         return (r == c.L) ? (R)0 : r;
     }
-    // far outside (or non-finite): the general definition
-    R r = RT<R>::mod(x, c.L);
-    if (r != (R)0) { if (r < (R)0) r = RT<R>::add(r, c.L); } else r = (R)0;
-    R r2 = RT<R>::mod(r, c.L);                       // second mod: only r == L changes
-    if (r2 != (R)0) { if (r2 < (R)0) r2 = RT<R>::add(r2, c.L); } else r2 = (R)0;
-    return r2;
+    unsigned e = 0;
+    R r = wrap_pos_far<R>(x, c.L, &e);
+    err |= e;
+    return r;
 }
+
+template <typename R>
+__device__ __noinline__ int clamp_cell(int il, int M, R* f) {           // cold: index outside the mesh
+    il = il < 0 ? 0 : M - 1;
+    *f = RT<R>::fromint(il);
+    return il;
+}
+
+// cold: exact quotient for positions within rounding distance of a cell edge
+template <typename R>
+__device__ __noinline__ R floor_div_exact(R xw, R dx) { return RT<R>::flo(RT<R>::div(xw, dx)); }
 
 struct Cell {
     int il, ir;          // left / right cell; ir is NOT reduced mod M (tables are padded with one wrap cell)
 };
 
-// floor(xw / dx) with correctly rounded division (interpolate.py:8) and the two CIC weights (:11-12).
-// Fast path multiplies by 1/dx; whenever the product is within idx_thr of an integer the quotient is redone with
-// IEEE division, so the index is always the reference's.  EXACT_W selects true divisions for the weights as well.
+// floor(xw / dx) with correctly rounded division (interpolate.py:8).  Fast path: q = xw * (1/dx), r = rint(q) by the
+// magic-number add, floor = r or r-1 by the sign of q - r.  Whenever q is within idx_thr of an integer (where the
+// reciprocal multiply could land on the other side of it) the quotient is redone with IEEE division, so the index
+// is always the reference's.  xw must be finite and in [0, L] (wrap_pos guarantees it).  Returns floor as R in f.
+template <typename R>
+__device__ __forceinline__ int cell_index(R xw, const PartConst<R>& c, int M, R& f, unsigned& err) {
+    R q = RT<R>::mul(xw, c.inv_dx);
+    int il;
+    R r = RT<R>::rint_magic(q, il);
+    R diff = RT<R>::sub(q, r);
+    if (diff < (R)0) { r = RT<R>::sub(r, (R)1); il -= 1; }
+    if (RT<R>::abs(diff) <= c.idx_thr) {                 // rare: exact quotient
+        r = floor_div_exact<R>(xw, c.dx);
+        il = RT<R>::toint(r);
+    }
+    if (__builtin_expect((unsigned)il >= (unsigned)M, 0)) {   // the reference raises in np.bincount here
+        err |= ERR_INDEX_RANGE;
+        il = clamp_cell<R>(il, M, &r);
+    }
+    f = r;
+    return il;
+}
+
+// the two CIC weights (interpolate.py:11-12); EXACT_W selects true divisions instead of multiplying by 1/dx
 template <typename R, bool EXACT_W>
 __device__ __forceinline__ Cell cell_weights(R xw, const PartConst<R>& c, int M, R& wl, R& wr, unsigned& err) {
-    R q = RT<R>::mul(xw, c.inv_dx);
-    R f = RT<R>::flo(q);
-    if (RT<R>::abs(RT<R>::sub(q, RT<R>::rnd(q))) <= c.idx_thr) f = RT<R>::flo(RT<R>::div(xw, c.dx));
-    int il = RT<R>::toint(f);
-    if ((unsigned)il >= (unsigned)M) {               // also catches NaN -> INT_MIN
-        err |= (xw == xw) ? ERR_INDEX_RANGE : ERR_NONFINITE;
-        il = il < 0 ? 0 : M - 1;
-        f = RT<R>::fromint(il);
-    }
+    R f;
+    int il = cell_index<R>(xw, c, M, f, err);
     R fr = RT<R>::add(f, (R)1);
     R nl = RT<R>::sub(RT<R>::mul(fr, c.dx), xw);     // indx_r * dx - x
     R nr = RT<R>::sub(xw, RT<R>::mul(f, c.dx));      // x - indx_l * dx
@@ -140,9 +200,14 @@ __device__ __forceinline__ Cell cell_weights(R xw, const PartConst<R>& c, int M,
 // ------------------------------------------------------------------ deposits
 // 64-bit integer accumulation in shared memory.  sm_100a has no native 64-bit (or floating point) shared
 // atomic add -- ptxas emits an ATOMS.CAST.SPIN loop -- so two flavours are provided:
-//   DEP_CAS64   : atomicAdd on unsigned long long (CAS loop), table hist64[M+1]
-//   DEP_SPLIT32 : two native 32-bit ATOMS.ADD, low word with return value to detect the carry, tables
-//                 lo[M+1], hi[M+1].  Exact: exactly one thread observes each wrap of the low word.
+//   DEP_CAS64   : atomicAdd on unsigned long long (CAS loop): 2^k - W_r to cell i_l, W_r to cell i_l + 1
+//                 (table of M+1 cells, the wrap cell M is folded into cell 0 when read).
+//   DEP_SPLIT32 : native 32-bit ATOMS.ADD only.  Each particle touches ONLY its own cell i_l: a particle count
+//                 cnt[i_l] += 1 and the 64-bit sum S[i_l] += W_r kept as two 32-bit words (the low-word add
+//                 returns the old value, so exactly one thread sees each carry and forwards it to the high word).
+//                 The cell density in fixed point is then  cnt[j] 2^k - S[j] + S[j-1]  -- three atomics per
+//                 particle instead of four and no wrap cell.
+// Both give the identical integer density (tests/test_gpu_parity.py::test_bitwise_reproducibility_across_kernels).
 constexpr int DEP_CAS64 = 0;
 constexpr int DEP_SPLIT32 = 1;
 
@@ -150,30 +215,40 @@ template <int DEP> struct Hist;
 
 template <> struct Hist<DEP_CAS64> {
     unsigned long long* h;
+    int M;
     static __host__ __device__ constexpr size_t bytes(int M) { return (size_t)(M + 1) * 8; }
-    __device__ __forceinline__ void init(void* base, int M) { h = (unsigned long long*)base; }
-    __device__ __forceinline__ void zero(int M, int tid, int nthreads) {
+    __device__ __forceinline__ void init(void* base, int M_) { h = (unsigned long long*)base; M = M_; }
+    __device__ __forceinline__ void zero(int tid, int nthreads) {
         for (int j = tid; j <= M; j += nthreads) h[j] = 0ull;
     }
-    __device__ __forceinline__ void add(int cell, long long w) { atomicAdd(&h[cell], (unsigned long long)w); }
-    __device__ __forceinline__ unsigned long long get(int cell) const { return h[cell]; }
+    __device__ __forceinline__ void deposit(int il, long long Wr, long long one) {
+        atomicAdd(&h[il], (unsigned long long)(one - Wr));
+        atomicAdd(&h[il + 1], (unsigned long long)Wr);
+    }
+    __device__ __forceinline__ unsigned long long get(int j, long long) const {
+        return j == 0 ? h[0] + h[M] : h[j];
+    }
 };
 
 template <> struct Hist<DEP_SPLIT32> {
-    unsigned *lo, *hi;
-    static __host__ __device__ constexpr size_t bytes(int M) { return (size_t)(M + 1) * 8; }
-    __device__ __forceinline__ void init(void* base, int M) { lo = (unsigned*)base; hi = lo + (M + 1); }
-    __device__ __forceinline__ void zero(int M, int tid, int nthreads) {
-        for (int j = tid; j < 2 * (M + 1); j += nthreads) lo[j] = 0u;
+    unsigned *cnt, *lo, *hi;
+    int M;
+    static __host__ __device__ constexpr size_t bytes(int M) { return (size_t)M * 12 + 8; }
+    __device__ __forceinline__ void init(void* base, int M_) { M = M_; cnt = (unsigned*)base; lo = cnt + M; hi = lo + M; }
+    __device__ __forceinline__ void zero(int tid, int nthreads) {
+        for (int j = tid; j < 3 * M; j += nthreads) cnt[j] = 0u;
     }
-    __device__ __forceinline__ void add(int cell, long long w) {
-        unsigned wl = (unsigned)(unsigned long long)w, wh = (unsigned)((unsigned long long)w >> 32);
-        unsigned old = atomicAdd(&lo[cell], wl);
-        unsigned carry = (old + wl) < old ? 1u : 0u;
-        atomicAdd(&hi[cell], wh + carry);
+    __device__ __forceinline__ void deposit(int il, long long Wr, long long) {
+        const unsigned wl = (unsigned)(unsigned long long)Wr, wh = (unsigned)((unsigned long long)Wr >> 32);
+        const unsigned old = atomicAdd(&lo[il], wl);
+        atomicAdd(&cnt[il], 1u);
+        atomicAdd(&hi[il], wh + ((old + wl) < old ? 1u : 0u));
     }
-    __device__ __forceinline__ unsigned long long get(int cell) const {
-        return ((unsigned long long)hi[cell] << 32) | (unsigned long long)lo[cell];
+    __device__ __forceinline__ unsigned long long S(int j) const {
+        return ((unsigned long long)hi[j] << 32) | (unsigned long long)lo[j];
+    }
+    __device__ __forceinline__ unsigned long long get(int j, long long one) const {
+        return (unsigned long long)cnt[j] * (unsigned long long)one - S(j) + S(j == 0 ? M - 1 : j - 1);
     }
 };
 
@@ -226,6 +301,34 @@ __device__ __forceinline__ double block_excl_scan(double v, double* scratch /* T
     return scratch[w] + (inc - v);
 }
 
+// E_ext on the mesh from Fourier coefficients: basis_cos @ a + basis_sin @ b on the actuator's own node table
+// (src/control/actuator.py:62; tables are uploaded from the host so node positions are the reference's linspace).
+__device__ __forceinline__ double actuator_field_at(int j, int m, const double* __restrict__ bcos,
+                                                    const double* __restrict__ bsin,
+                                                    const double* __restrict__ coeff /* [2m]: cos then sin */) {
+    double ec = 0.0, es = 0.0;
+    for (int k = 0; k < m; ++k) {
+        ec = __dadd_rn(ec, __dmul_rn(bcos[j * m + k], coeff[k]));
+        es = __dadd_rn(es, __dmul_rn(bsin[j * m + k], coeff[m + k]));
+    }
+    return __dadd_rn(ec, es);
+}
+
+// What the particles see on top of the self-consistent field (util.py:102-103): nothing, a mesh vector, or the
+// actuator's Fourier series evaluated on the fly.
+struct ExtSrc {
+    const double* ext;     // [M] or nullptr
+    const double* coeff;   // [2m] or nullptr (takes precedence)
+    const double* bcos;    // [M][m]
+    const double* bsin;    // [M][m]
+    int m;
+    __device__ __forceinline__ bool any() const { return ext != nullptr || coeff != nullptr; }
+    __device__ __forceinline__ double at(int j) const {
+        if (coeff) return actuator_field_at(j, m, bcos, bsin, coeff);
+        return ext[j];
+    }
+};
+
 // ------------------------------------------------------------------ field solve
 // Periodic 3-point Poisson + centred difference in closed form (DESIGN.md "Field solve"):
 //   b_j = n_j - n0,  S_j = sum_{i<=j} b_i,  D_j = dx^2 (S_j - mean S),  E_j = -(D_j + D_{j-1}) / (2 dx)
@@ -233,16 +336,18 @@ __device__ __forceinline__ double block_excl_scan(double v, double* scratch /* T
 // (src/env/util.py:99-100) without forming phi.  Block-cooperative; every thread must call it.
 //
 //   rho      : M fixed-point cell sums (global or shared memory), already including the wrap cell
-//   E_s      : shared, M+1 entries of R: E_j (+ ext_j), entry M duplicates entry 0 for the gather
+//   E_s      : shared, M pairs (E_j + ext_j, E_{j+1 mod M} + ext_{j+1 mod M}) for the gather
 //   D_s      : shared scratch, M doubles
 //   red      : shared scratch, THREADS/32 + 1 doubles
-//   ext      : nullptr or M doubles (global) added to what particles see (util.py:102-103)
+//   ext      : external field source added to what particles see (util.py:102-103)
 //   n_out/E_out : nullptr or global outputs of the density (interpolate.py:18) / self-consistent field
 // Returns sum_j E_j^2 of the self-consistent field (all threads) when WANT_E2, else 0.
 template <typename R, int THREADS, bool WANT_E2, typename RhoLoad>
-__device__ __forceinline__ double block_field(RhoLoad rho, R* E_s, double* D_s, double* red, const MeshConst& mc,
-                                              const double* __restrict__ ext, double* __restrict__ n_out,
+__device__ __forceinline__ double block_field(RhoLoad rho, typename PairT<R>::type* E_s, double* D_s, double* red,
+                                              const MeshConst& mc,
+                                              const ExtSrc& ext, double* __restrict__ n_out,
                                               double* __restrict__ E_out) {
+    const bool has_ext = ext.any();
     const int M = mc.M, tid = threadIdx.x;
     const int cpt = (M + THREADS - 1) / THREADS;
     const int j0 = tid * cpt, j1 = min(M, j0 + cpt);
@@ -268,9 +373,9 @@ __device__ __forceinline__ double block_field(RhoLoad rho, R* E_s, double* D_s, 
         double E = -(Dj + Dm) * inv2dx;
         if (E_out) E_out[j] = E;
         if (WANT_E2) e2 += E * E;
-        double Et = ext ? E + ext[j] : E;
-        E_s[j] = (R)Et;
-        if (j == 0) E_s[M] = (R)Et;
+        double Et = has_ext ? E + ext.at(j) : E;
+        E_s[j].x = (R)Et;
+        E_s[jm].y = (R)Et;
     }
     double tot = 0.0;
     if (WANT_E2) tot = block_sum<THREADS>(e2, red);
@@ -278,30 +383,18 @@ __device__ __forceinline__ double block_field(RhoLoad rho, R* E_s, double* D_s, 
     return tot;
 }
 
-// E_ext on the mesh from Fourier coefficients: basis_cos @ a + basis_sin @ b on the actuator's own node table
-// (src/control/actuator.py:62; tables are uploaded from the host so node positions are the reference's linspace).
-__device__ __forceinline__ double actuator_field_at(int j, int m, const double* __restrict__ bcos,
-                                                    const double* __restrict__ bsin,
-                                                    const double* __restrict__ coeff /* [2m]: cos then sin */) {
-    double ec = 0.0, es = 0.0;
-    for (int k = 0; k < m; ++k) {
-        ec = __dadd_rn(ec, __dmul_rn(bcos[j * m + k], coeff[k]));
-        es = __dadd_rn(es, __dmul_rn(bsin[j * m + k], coeff[m + k]));
-    }
-    return __dadd_rn(ec, es);
-}
-
 // ------------------------------------------------------------------- push step
 // One Yoshida sub-stage for one particle (integration.py:22-47 with f = [v; -E], pic.py:125-129):
 //   kick  : v <- v + (d * (-E_p)) * dt     E_p = w_l E[i_l] + w_r E[i_r] at the CURRENT (wrapped) position
 //   drift : x <- x + (c * v) * dt          x itself is carried unwrapped between sub-stages
 template <typename R, bool EXACT_W>
-__device__ __forceinline__ void kick(R x, R& v, const R* __restrict__ E_s, R d, const PartConst<R>& c, int M,
-                                     unsigned& err) {
+__device__ __forceinline__ void kick(R x, R& v, const typename PairT<R>::type* __restrict__ E_s, R d,
+                                     const PartConst<R>& c, int M, unsigned& err) {
     R wl, wr;
-    R xw = wrap_pos<R>(x, c);
+    R xw = wrap_pos<R>(x, c, err);
     Cell k = cell_weights<R, EXACT_W>(xw, c, M, wl, wr, err);
-    R Ep = RT<R>::add(RT<R>::mul(wl, E_s[k.il]), RT<R>::mul(wr, E_s[k.ir]));
+    const typename PairT<R>::type e = E_s[k.il];
+    R Ep = RT<R>::add(RT<R>::mul(wl, e.x), RT<R>::mul(wr, e.y));
     v = RT<R>::add(v, RT<R>::mul(RT<R>::mul(d, -Ep), c.dt));
 }
 
@@ -310,12 +403,18 @@ __device__ __forceinline__ R drift(R x, R v, R cc, const PartConst<R>& c) {
     return RT<R>::add(x, RT<R>::mul(RT<R>::mul(cc, v), c.dt));
 }
 
+// CIC deposit in fixed point.  The right weight is rounded to k fractional bits, W_r = llrint(w_r 2^k), and the left
+// cell receives 2^k - W_r, so every particle deposits exactly 2^k: total charge is conserved to the bit and the sum
+// over cells is independent of summation order.  (The reference's w_l differs from 1 - w_r by at most one rounding
+// of 1.0, i.e. 1.1e-16 -- four orders below the stated density tolerance.)
 template <typename R, bool EXACT_W, typename H>
 __device__ __forceinline__ void deposit(R xw, H& hist, const PartConst<R>& c, const MeshConst& mc, unsigned& err) {
-    R wl, wr;
-    Cell k = cell_weights<R, EXACT_W>(xw, c, mc.M, wl, wr, err);
-    hist.add(k.il, RT<R>::fix(wl, mc.fix_scale));
-    hist.add(k.ir, RT<R>::fix(wr, mc.fix_scale));
+    R f;
+    int il = cell_index<R>(xw, c, mc.M, f, err);
+    R nr = RT<R>::sub(xw, RT<R>::mul(f, c.dx));
+    R wr = EXACT_W ? RT<R>::div(nr, c.dx) : RT<R>::mul(nr, c.inv_dx);
+    long long Wr = fix_weight((double)wr, mc.fix_scale);
+    hist.deposit(il, Wr, mc.fix_one);
 }
 
 // streaming loads / stores (no reuse: keep the particle stream out of L1, evict-first in L2)

@@ -40,26 +40,29 @@ struct StreamArgs {
     double c, d;
     double* partial;                   // [n_envs][gridDim.x][2] per-CTA sum v^2, sum v (MODE_FINAL / MODE_INIT)
     unsigned* err;
-    int ablate;                        // profiling only (PIC_ABLATE env): bit0 skip deposit atomics, bit1 skip gather
 };
 
+// Shared-memory plan of one CTA.  SEPARATE_D: the prefix-sum scratch gets its own region (needed when the density
+// is read from the shared histogram itself, i.e. the resident kernel); otherwise it aliases the histogram, which is
+// idle while the field is rebuilt from the global density.
+constexpr size_t hist_region_bytes(int M) { return (size_t)M * 12 + 16; }      // max over deposit flavours, 8-aligned
+
 template <typename R>
-__host__ __device__ constexpr size_t stream_smem_bytes(int M, int threads) {
-    return (size_t)(M + 1) * 8                       // histogram
-         + (((size_t)(M + 1) * sizeof(R) + 7) & ~(size_t)7)   // E_s
-         + (size_t)M * 8                             // D_s
-         + (size_t)M * 8                             // ext_s
+__host__ __device__ constexpr size_t smem_plan_bytes(int M, int threads, bool separate_d) {
+    return (size_t)M * 2 * sizeof(R)                 // gather pair table
+         + (((size_t)M * 12 + 16 + 15) & ~(size_t)15)   // histogram
+         + (separate_d ? (size_t)M * 8 : 0)          // D_s
          + (size_t)(threads / 32 + 2) * 8;           // reduction scratch
 }
 
 template <typename R>
 struct SmemLayout {
-    void* hist; R* E_s; double* D_s; double* ext_s; double* red;
-    __device__ __forceinline__ SmemLayout(unsigned char* base, int M) {
-        hist = base;                         base += (size_t)(M + 1) * 8;
-        E_s = (R*)base;                      base += (((size_t)(M + 1) * sizeof(R) + 7) & ~(size_t)7);
-        D_s = (double*)base;                 base += (size_t)M * 8;
-        ext_s = (double*)base;               base += (size_t)M * 8;
+    void* hist; typename PairT<R>::type* E_s; double* D_s; double* red;
+    __device__ __forceinline__ SmemLayout(unsigned char* base, int M, bool separate_d) {
+        E_s = (typename PairT<R>::type*)base;   base += (size_t)M * 2 * sizeof(R);
+        hist = base;                            base += (((size_t)M * 12 + 16 + 15) & ~(size_t)15);
+        D_s = separate_d ? (double*)base : (double*)hist;
+        if (separate_d) base += (size_t)M * 8;
         red = (double*)base;
     }
 };
@@ -68,24 +71,18 @@ struct GlobalRho {
     const unsigned long long* p;
     __device__ __forceinline__ unsigned long long operator()(int j) const { return __ldcg(p + j); }
 };
-template <typename H> struct SharedRho {       // folds the wrap cell M into cell 0
-    const H* h; int M;
-    __device__ __forceinline__ unsigned long long operator()(int j) const {
-        return j == 0 ? h->get(0) + h->get(M) : h->get(j);
-    }
+template <typename H> struct SharedRho {
+    const H* h; long long one;
+    __device__ __forceinline__ unsigned long long operator()(int j) const { return h->get(j, one); }
 };
 
-// prepares what the particles see on top of the self-consistent field; returns nullptr when there is no actuation
-template <int THREADS>
-__device__ __forceinline__ const double* stage_ext(const ActuatorArgs& act, int env, int M, double* ext_s) {
-    if (act.coeffs) {
-        const double* cf = act.coeffs + (size_t)env * 2 * act.m;
-        for (int j = threadIdx.x; j < M; j += THREADS) ext_s[j] = actuator_field_at(j, act.m, act.bcos, act.bsin, cf);
-        __syncthreads();
-        return ext_s;
-    }
-    if (act.ext) return act.ext + (size_t)env * M;
-    return nullptr;
+// what the particles of env `env` see on top of the self-consistent field
+__device__ __forceinline__ ExtSrc stage_ext(const ActuatorArgs& act, int env, int M) {
+    ExtSrc e;
+    e.ext = act.ext ? act.ext + (size_t)env * M : nullptr;
+    e.coeff = act.coeffs ? act.coeffs + (size_t)env * 2 * act.m : nullptr;
+    e.bcos = act.bcos; e.bsin = act.bsin; e.m = act.m;
+    return e;
 }
 
 template <typename R, int THREADS, int UNROLL, int MODE, int DEP, bool EXACT_W>
@@ -96,18 +93,17 @@ __global__ void __launch_bounds__(THREADS) push_stream_kernel(const StreamArgs a
     constexpr bool KICK = (MODE == MODE_KICK || MODE == MODE_FINAL);
     constexpr bool SUMS = (MODE == MODE_FINAL || MODE == MODE_INIT);
     const int tid = threadIdx.x, env = blockIdx.y, M = a.mc.M;
-    SmemLayout<R> sm(smem_raw, M);
+    SmemLayout<R> sm(smem_raw, M, false);
     Hist<DEP> hist; hist.init(sm.hist, M);
     const PartConst<R> pc = make_part_const<R>(a.mc);
 
-    hist.zero(M, tid, THREADS);
-    if (KICK) {
-        const double* ext = stage_ext<THREADS>(a.act, env, M, sm.ext_s);
+    if (KICK) {                                         // D_s aliases the histogram: solve first, then clear
+        const ExtSrc ext = stage_ext(a.act, env, M);
         GlobalRho rho{a.rho_in + (size_t)env * M};
         block_field<R, THREADS, false>(rho, sm.E_s, sm.D_s, sm.red, a.mc, ext, nullptr, nullptr);
-    } else {
-        __syncthreads();
     }
+    hist.zero(tid, THREADS);
+    __syncthreads();
     if (a.rho_zero) {
         unsigned long long* z = a.rho_zero + (size_t)env * M;
         for (int j = blockIdx.x * THREADS + tid; j < M; j += gridDim.x * THREADS) z[j] = 0ull;
@@ -122,13 +118,12 @@ __global__ void __launch_bounds__(THREADS) push_stream_kernel(const StreamArgs a
     unsigned err = 0;
     double s2 = 0.0, s1 = 0.0;
 
-    const bool do_dep = !(a.ablate & 1), do_gather = !(a.ablate & 2);
     auto one = [&](R& x, R& v) {
-        if (KICK && do_gather) kick<R, EXACT_W>(x, v, sm.E_s, dd, pc, M, err);
+        if (KICK) kick<R, EXACT_W>(x, v, sm.E_s, dd, pc, M, err);
         if (MODE != MODE_INIT) x = drift<R>(x, v, cc, pc);
-        R xw = wrap_pos<R>(x, pc);
+        R xw = wrap_pos<R>(x, pc, err);
         if (SUMS) { x = xw; s2 += (double)v * (double)v; s1 += (double)v; }
-        if (do_dep) deposit<R, EXACT_W>(xw, hist, pc, a.mc, err);
+        deposit<R, EXACT_W>(xw, hist, pc, a.mc, err);
     };
 
     const long long stride = (long long)gridDim.x * THREADS * UNROLL;
@@ -167,8 +162,7 @@ __global__ void __launch_bounds__(THREADS) push_stream_kernel(const StreamArgs a
     // flush the CTA-private histogram: integer sums are associative, so the result does not depend on CTA order
     unsigned long long* out = a.rho_out + (size_t)env * M;
     for (int j = tid; j < M; j += THREADS) {
-        unsigned long long val = hist.get(j);
-        if (j == 0) val += hist.get(M);
+        unsigned long long val = hist.get(j, a.mc.fix_one);
         if (val) atomicAdd(out + j, val);
     }
     if (SUMS) {
@@ -199,9 +193,10 @@ template <int THREADS>
 __global__ void __launch_bounds__(THREADS) field_finalize_kernel(const FinalizeArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int env = blockIdx.x, M = a.mc.M, tid = threadIdx.x;
-    SmemLayout<double> sm(smem_raw, M);
+    SmemLayout<double> sm(smem_raw, M, false);
     GlobalRho rho{a.rho + (size_t)env * M};
-    double e2 = block_field<double, THREADS, true>(rho, sm.E_s, sm.D_s, sm.red, a.mc, nullptr,
+    const ExtSrc none{nullptr, nullptr, nullptr, nullptr, 0};
+    double e2 = block_field<double, THREADS, true>(rho, sm.E_s, sm.D_s, sm.red, a.mc, none,
                                                    a.n_out + (size_t)env * M, a.E_out + (size_t)env * M);
     if (a.rho_zero) for (int j = tid; j < M; j += THREADS) a.rho_zero[(size_t)env * M + j] = 0ull;
     double s2 = 0.0, s1 = 0.0;
@@ -244,7 +239,7 @@ template <typename R, int THREADS, int PPT, int DEP, bool EXACT_W>
 __global__ void __launch_bounds__(THREADS) env_step_resident_kernel(const ResidentArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x, env = blockIdx.x, M = a.mc.M;
-    SmemLayout<R> sm(smem_raw, M);
+    SmemLayout<R> sm(smem_raw, M, true);
     Hist<DEP> hist; hist.init(sm.hist, M);
     const PartConst<R> pc = make_part_const<R>(a.mc);
     R* xe = (R*)a.x + (size_t)env * a.ld;
@@ -258,12 +253,13 @@ __global__ void __launch_bounds__(THREADS) env_step_resident_kernel(const Reside
         xs[j] = i < N ? xe[i] : (R)0;
         vs[j] = i < N ? ve[i] : (R)0;
     }
-    hist.zero(M, tid, THREADS);
+    hist.zero(tid, THREADS);
     __syncthreads();
     unsigned err = 0;
-    SharedRho<Hist<DEP>> rho{&hist, M};
+    SharedRho<Hist<DEP>> rho{&hist, a.mc.fix_one};
     double* n_out = a.n_out + (size_t)env * M;
     double* E_out = a.E_out + (size_t)env * M;
+    const ExtSrc none{nullptr, nullptr, nullptr, nullptr, 0};
 
     auto write_diag = [&](double e2, int step) {
         double s2 = 0.0, s1 = 0.0;
@@ -294,13 +290,13 @@ __global__ void __launch_bounds__(THREADS) env_step_resident_kernel(const Reside
 #pragma unroll
         for (int j = 0; j < PPT; ++j) {
             if (j * THREADS + tid < N) {
-                xs[j] = wrap_pos<R>(xs[j], pc);
+                xs[j] = wrap_pos<R>(xs[j], pc, err);
                 deposit<R, EXACT_W>(xs[j], hist, pc, a.mc, err);
             }
         }
         __syncthreads();
         dump_rho();
-        double e2 = block_field<R, THREADS, true>(rho, sm.E_s, sm.D_s, sm.red, a.mc, nullptr, n_out, E_out);
+        double e2 = block_field<R, THREADS, true>(rho, sm.E_s, sm.D_s, sm.red, a.mc, none, n_out, E_out);
         write_diag(e2, -1);
     }
 
@@ -308,7 +304,7 @@ __global__ void __launch_bounds__(THREADS) env_step_resident_kernel(const Reside
         ActuatorArgs act = a.act;
         if (act.coeffs) act.coeffs += (size_t)step * a.coeff_step_stride;
         if (act.ext) act.ext += (size_t)step * a.ext_step_stride;
-        const double* ext = stage_ext<THREADS>(act, env, M, sm.ext_s);
+        const ExtSrc ext = stage_ext(act, env, M);
         const bool last = step == a.n_steps - 1;
 #pragma unroll 1
         for (int st = 0; st < 4; ++st) {
@@ -319,7 +315,7 @@ __global__ void __launch_bounds__(THREADS) env_step_resident_kernel(const Reside
                 if (j * THREADS + tid < N) {
                     if (st > 0) kick<R, EXACT_W>(xs[j], vs[j], sm.E_s, dd, pc, M, err);
                     xs[j] = drift<R>(xs[j], vs[j], cc, pc);
-                    R xw = wrap_pos<R>(xs[j], pc);
+                    R xw = wrap_pos<R>(xs[j], pc, err);
                     if (fin) xs[j] = xw;                           // pic.py:139
                     deposit<R, EXACT_W>(xw, hist, pc, a.mc, err);
                 }
@@ -329,11 +325,11 @@ __global__ void __launch_bounds__(THREADS) env_step_resident_kernel(const Reside
                 block_field<R, THREADS, false>(rho, sm.E_s, sm.D_s, sm.red, a.mc, ext, nullptr, nullptr);
             } else {
                 if (last) dump_rho();
-                double e2 = block_field<R, THREADS, true>(rho, sm.E_s, sm.D_s, sm.red, a.mc, nullptr,
+                double e2 = block_field<R, THREADS, true>(rho, sm.E_s, sm.D_s, sm.red, a.mc, none,
                                                           last ? n_out : nullptr, last ? E_out : nullptr);
                 write_diag(e2, step);
             }
-            hist.zero(M, tid, THREADS);
+            hist.zero(tid, THREADS);
             __syncthreads();
         }
     }

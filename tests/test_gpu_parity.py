@@ -28,6 +28,8 @@ def test_wrap_index_deposit_edge_cases(golden, cfg, LM):
     key = f"L{L:g}_M{M}"
     x = g[key + "_x"]
     N = x.shape[0]
+    if cfg["mode"] == "resident" and N > 10240:
+        pytest.skip("more particles than one CTA keeps in registers")
     eng = _engine(N, M, L, 0.01, **cfg)
     eng.set_state(x[None], np.zeros((1, N)))
     xs, _ = eng.get_state()
@@ -40,7 +42,7 @@ def test_wrap_index_deposit_edge_cases(golden, cfg, LM):
     assert np.abs(n[0] - g[key + "_cic_n"]).max() < 1e-12 * g[key + "_cic_n"].max()
     assert eng.error_flags() == 0
     rho, k = eng.get_density_fixed()
-    assert abs(int(rho.sum()) - N * (1 << k)) <= N                    # total charge: every particle deposits w_l + w_r = 1
+    assert sum(int(r) for r in rho.ravel()) == N * (1 << k)           # every particle deposits exactly 2^k
 
 
 @pytest.mark.parametrize("cfg", CONFIGS, ids=lambda c: c["mode"] + "-" + c["deposit"])
