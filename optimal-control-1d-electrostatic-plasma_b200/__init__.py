@@ -8,8 +8,9 @@ from . import _lib
 from ._lib import PicError
 from .engine import Engine, DeviceArray
 from .pic import PIC
-from .batched import BatchedPIC
+from .batched import BatchedPIC, shard_range
+from .sharded import ShardedPIC
 from .dist import BumpOnTail, TwoStream
 from .actuator import E_field
 
-__all__ = ["PIC", "BatchedPIC", "Engine", "DeviceArray", "PicError", "BumpOnTail", "TwoStream", "E_field"]
+__all__ = ["PIC", "BatchedPIC", "ShardedPIC", "shard_range", "Engine", "DeviceArray", "PicError", "BumpOnTail", "TwoStream", "E_field"]

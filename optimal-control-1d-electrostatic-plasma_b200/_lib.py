@@ -43,6 +43,8 @@ SIGNATURES = {
     "pic_set_stream": (C.c_int, [_H, C.c_void_p]),
     "pic_set_state": (C.c_int, [_H, C.c_void_p, C.c_void_p]),
     "pic_set_state_device": (C.c_int, [_H, C.c_void_p, C.c_void_p]),
+    "pic_sample_state": (C.c_int, [_H, C.c_int32, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int32,
+                                   C.c_uint64, C.c_int64, C.c_int64]),
     "pic_get_state": (C.c_int, [_H, C.c_void_p, C.c_void_p]),
     "pic_get_fields": (C.c_int, [_H, C.c_void_p, C.c_void_p]),
     "pic_get_density_fixed": (C.c_int, [_H, C.c_void_p, C.POINTER(C.c_int32)]),

@@ -1,6 +1,7 @@
 // C ABI (include/pic_b200.h) over the kernels: handle management, buffer rotation, sub-stage sequencing,
 // NCCL all-reduce of the fixed-point density for the particle-sharded mode.
 #include <cuda_runtime.h>
+#include <curand_kernel.h>
 #include <dlfcn.h>
 #include <math.h>
 #include <stdio.h>
@@ -201,6 +202,35 @@ __global__ void cells_kernel(const R* __restrict__ x, long long N, long long ld,
             const double* E = Emesh + (size_t)env * mc.M;
             Ep[o] = __dadd_rn(__dmul_rn((double)a, E[c.il]), __dmul_rn((double)b, E[c.ir == mc.M ? 0 : c.ir]));
         }
+    }
+}
+
+// Device-side initial sampler: the distributions of src/env/dist.py:70-102 (two-stream) and :151-189
+// (bump-on-tail) drawn with Philox instead of host rejection sampling -- same densities (Gaussians truncated to the
+// reference's proposal range |v| <= 10, x uniform on [0, L)), same deterministic split of the particle index range
+// between the populations, followed by the velocity perturbation of src/env/pic.py:68.  Statistical, not bitwise,
+// parity with the host sampler.  Particle i of env e uses Philox subsequence (e * n_global + global index), so the
+// result does not depend on the launch shape or on how particles are sharded over ranks.
+template <typename R>
+__global__ void sample_kernel(R* __restrict__ x, R* __restrict__ v, long long N, long long ld, long long offset,
+                              long long n_global, int kind, double a, double v0, double sigma, double A, int n_mode,
+                              double L, unsigned long long seed) {
+    const int env = blockIdx.y;
+    const long long n_first = kind == 0 ? (long long)((double)n_global * (1.0 / (1.0 + a))) : n_global / 2;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (long long)gridDim.x * blockDim.x) {
+        const long long g = offset + i;
+        curandStatePhilox4_32_10_t st;
+        curand_init(seed, (unsigned long long)env * (unsigned long long)n_global + (unsigned long long)g, 0, &st);
+        double mean, sd;
+        if (kind == 0) { mean = g < n_first ? 0.0 : v0; sd = g < n_first ? 1.0 : sigma; }   // bump-on-tail
+        else           { mean = g < n_first ? v0 : -v0; sd = sigma; }                      // two-stream
+        double xx = curand_uniform_double(&st) * L;             // (0, 1] * L
+        if (xx >= L) xx = 0.0;
+        double vv;
+        do { vv = mean + sd * curand_normal_double(&st); } while (fabs(vv) > 10.0);
+        vv *= (1 + A * sin(2 * 3.141592653589793 * n_mode * xx / L));
+        x[(size_t)env * ld + i] = (R)xx;
+        v[(size_t)env * ld + i] = (R)vv;
     }
 }
 
@@ -488,6 +518,23 @@ int pic_set_state(pic_handle* h, const double* x, const double* v) {
             h->launches++;
         }
     }
+    return init_fields(h);
+}
+
+int pic_sample_state(pic_handle* h, int32_t kind, double a, double v0, double sigma, double A, int32_t n_mode,
+                     uint64_t seed, int64_t global_offset, int64_t n_global) {
+    if (!h) return PIC_EINVAL;
+    if (kind != 0 && kind != 1) return fail(h, PIC_EINVAL, "kind: 0 = bump-on-tail, 1 = two-stream");
+    if (n_global <= 0) n_global = h->Ntotal;
+    CK(h, cudaSetDevice(h->device));
+    long long gx = (h->N + 255) / 256;
+    dim3 grid((unsigned)(gx < 65535 ? gx : 65535), h->n_envs);
+    if (h->f32) sample_kernel<float><<<grid, 256, 0, h->stream>>>((float*)h->x, (float*)h->v, h->N, h->ld, global_offset,
+                                                                  n_global, kind, a, v0, sigma, A, n_mode, h->mc.L, seed);
+    else sample_kernel<double><<<grid, 256, 0, h->stream>>>((double*)h->x, (double*)h->v, h->N, h->ld, global_offset,
+                                                            n_global, kind, a, v0, sigma, A, n_mode, h->mc.L, seed);
+    h->launches++;
+    CK(h, cudaGetLastError());
     return init_fields(h);
 }
 
