@@ -333,7 +333,7 @@ def main():
     ap.add_argument("--particles", type=float, default=N_FULL)
     ap.add_argument("--deposit", default="split32")
     ap.add_argument("--threads", type=int, default=1024)
-    ap.add_argument("--unroll", type=int, default=1)
+    ap.add_argument("--unroll", type=int, default=2)
     ap.add_argument("--ctas", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-batched", action="store_true")

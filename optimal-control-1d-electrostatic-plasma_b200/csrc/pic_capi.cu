@@ -401,17 +401,18 @@ int pic_create(const pic_config* cfg, pic_handle** out) {
     mc.fix_scale = ldexp(1.0, k); mc.inv_fix = ldexp(1.0, -k); mc.fix_one = 1LL << k;
     mc.idx_thr = (double)h->M * (h->f32 ? ldexp(1.0, -20) : ldexp(1.0, -49));
 
-    h->dep = cfg->deposit == PIC_DEPOSIT_SPLIT32 ? DEP_SPLIT32 : DEP_CAS64;
+    h->dep = cfg->deposit == PIC_DEPOSIT_CAS64 ? DEP_CAS64 : DEP_SPLIT32;     // auto: native 32-bit atomics
+    if (h->f32) h->dep = DEP_SPLIT32;
     int mode = cfg->mode;
-    const long long resident_cap = 256LL * 40;
-    if (mode == PIC_MODE_AUTO) mode = h->N <= resident_cap ? PIC_MODE_RESIDENT : PIC_MODE_STREAMING;
+    if (mode == PIC_MODE_AUTO) mode = h->N <= resident_capacity(h->f32) ? PIC_MODE_RESIDENT : PIC_MODE_STREAMING;
     h->resident = mode == PIC_MODE_RESIDENT;
     if (h->resident) {
-        h->threads = 256;
-        h->per_thread = resident_pick_ppt(256, h->N);
-        if (!h->per_thread) { delete h; return fail(nullptr, PIC_EUNSUPPORTED, "n_particles too large for resident mode"); }
+        if (!resident_pick_shape(h->N, h->f32, &h->threads, &h->per_thread)) {
+            delete h;
+            return fail(nullptr, PIC_EUNSUPPORTED, "n_particles too large for resident mode");
+        }
     } else {
-        h->threads = 256; h->per_thread = 2;
+        h->threads = 1024; h->per_thread = 2;       // measured best: 1024 threads x 2 vectors in flight, 1 CTA per SM
     }
 
     size_t pbytes = (size_t)h->ld * h->n_envs * h->esize, mbytes = sizeof(double) * (size_t)h->M * h->n_envs;

@@ -122,8 +122,8 @@ __host__ __device__ inline PartConst<R> make_part_const(const MeshConst& m) {
 // exact value of that sequence: [L,2L) -> x-L is exact (Sterbenz); (-L,0) -> fl(x+L), which can round to L and
 // is then sent to 0 by the second mod.
 template <typename R>
-__device__ __noinline__ R wrap_pos_far(R x, R L, unsigned* err) {       // cold: |x| >= 2L or non-finite
-    if (!(RT<R>::abs(x) <= (R)3.0e38)) { *err |= ERR_NONFINITE; return (R)0; }
+__device__ __noinline__ R wrap_pos_far(R x, R L) {                      // cold: |x| >= 2L or non-finite (-> -1)
+    if (!(RT<R>::abs(x) <= (R)3.0e38)) return (R)-1;
     R r = RT<R>::mod(x, L);
     if (r != (R)0) { if (r < (R)0) r = RT<R>::add(r, L); } else r = (R)0;
     R r2 = RT<R>::mod(r, L);                         // second mod: only r == L changes
@@ -139,17 +139,9 @@ __device__ __forceinline__ R wrap_pos(R x, const PartConst<R>& c, unsigned& err)
         R r = RT<R>::add(x, c.L);
         return (r == c.L) ? (R)0 : r;
     }
-    unsigned e = 0;
-    R r = wrap_pos_far<R>(x, c.L, &e);
-    err |= e;
+    R r = wrap_pos_far<R>(x, c.L);
+    if (r < (R)0) { err |= ERR_NONFINITE; r = (R)0; }
     return r;
-}
-
-template <typename R>
-__device__ __noinline__ int clamp_cell(int il, int M, R* f) {           // cold: index outside the mesh
-    il = il < 0 ? 0 : M - 1;
-    *f = RT<R>::fromint(il);
-    return il;
 }
 
 // cold: exact quotient for positions within rounding distance of a cell edge
@@ -177,7 +169,8 @@ __device__ __forceinline__ int cell_index(R xw, const PartConst<R>& c, int M, R&
     }
     if (__builtin_expect((unsigned)il >= (unsigned)M, 0)) {   // the reference raises in np.bincount here
         err |= ERR_INDEX_RANGE;
-        il = clamp_cell<R>(il, M, &r);
+        il = il < 0 ? 0 : M - 1;
+        r = RT<R>::fromint(il);
     }
     f = r;
     return il;
@@ -225,24 +218,47 @@ template <> struct Hist<DEP_CAS64> {
         atomicAdd(&h[il], (unsigned long long)(one - Wr));
         atomicAdd(&h[il + 1], (unsigned long long)Wr);
     }
+    // `count` particles of cell il with right-weight sum S
+    __device__ __forceinline__ void deposit_group(int il, unsigned long long S, unsigned count, long long one) {
+        atomicAdd(&h[il], (unsigned long long)count * (unsigned long long)one - S);
+        atomicAdd(&h[il + 1], S);
+    }
     __device__ __forceinline__ unsigned long long get(int j, long long) const {
         return j == 0 ? h[0] + h[M] : h[j];
     }
 };
 
+// native 32-bit shared atomics by address in the shared window (inline PTX: keeps ptxas from wrapping constant
+// increments in its own MATCH.ANY-based warp aggregation, and needs no generic-to-shared conversion per access)
+__device__ __forceinline__ void red_shared_u32(unsigned addr, unsigned v) {
+    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned atom_shared_u32(unsigned addr, unsigned v) {
+    unsigned old;
+    asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(addr), "r"(v) : "memory");
+    return old;
+}
+
 template <> struct Hist<DEP_SPLIT32> {
     unsigned *cnt, *lo, *hi;
+    unsigned cnt_a, lo_a, hi_a;          // the same arrays as shared-window byte addresses
     int M;
     static __host__ __device__ constexpr size_t bytes(int M) { return (size_t)M * 12 + 8; }
-    __device__ __forceinline__ void init(void* base, int M_) { M = M_; cnt = (unsigned*)base; lo = cnt + M; hi = lo + M; }
+    __device__ __forceinline__ void init(void* base, int M_) {
+        M = M_; cnt = (unsigned*)base; lo = cnt + M; hi = lo + M;
+        cnt_a = (unsigned)__cvta_generic_to_shared(cnt); lo_a = cnt_a + 4u * M; hi_a = lo_a + 4u * M;
+    }
     __device__ __forceinline__ void zero(int tid, int nthreads) {
         for (int j = tid; j < 3 * M; j += nthreads) cnt[j] = 0u;
     }
-    __device__ __forceinline__ void deposit(int il, long long Wr, long long) {
-        const unsigned wl = (unsigned)(unsigned long long)Wr, wh = (unsigned)((unsigned long long)Wr >> 32);
-        const unsigned old = atomicAdd(&lo[il], wl);
-        atomicAdd(&cnt[il], 1u);
-        atomicAdd(&hi[il], wh + ((old + wl) < old ? 1u : 0u));
+    __device__ __forceinline__ void deposit_group(int il, unsigned long long S, unsigned count, long long) {
+        const unsigned wl = (unsigned)S, wh = (unsigned)(S >> 32), off = 4u * (unsigned)il;
+        const unsigned old = atom_shared_u32(lo_a + off, wl);
+        red_shared_u32(cnt_a + off, count);
+        red_shared_u32(hi_a + off, wh + ((old + wl) < old ? 1u : 0u));
+    }
+    __device__ __forceinline__ void deposit(int il, long long Wr, long long one) {
+        deposit_group(il, (unsigned long long)Wr, 1u, one);
     }
     __device__ __forceinline__ unsigned long long S(int j) const {
         return ((unsigned long long)hi[j] << 32) | (unsigned long long)lo[j];
@@ -415,6 +431,108 @@ __device__ __forceinline__ void deposit(R xw, H& hist, const PartConst<R>& c, co
     R wr = EXACT_W ? RT<R>::div(nr, c.dx) : RT<R>::mul(nr, c.inv_dx);
     long long Wr = fix_weight((double)wr, mc.fix_scale);
     hist.deposit(il, Wr, mc.fix_one);
+}
+
+// ---------------------------------------------------------------- fast path
+// The functions above are the reference semantics with every rare case handled in place (far wrap, positions within
+// rounding distance of a cell edge, indices outside the mesh, non-finite input).  Executed as is they cost ~120
+// instructions per particle, a third of them branch / reconvergence overhead around cases that almost never occur.
+// The hot loops therefore run `particle_fast`: straight-line code whose result is exact whenever, for the position
+// it looks at, x * (1/dx) is farther than idx_thr from an integer and its floor is a cell of the mesh -- which
+// together imply 0 <= x < L (no wrap needed) and floor(x * (1/dx)) == floor(x / dx).  Anything else (including NaN
+// and Inf, through the unordered compare) raises one flag and the particle is redone from its original (x, v) by
+// the full-semantics code in a cold block.  Same bits either way.
+template <typename R>
+__device__ __forceinline__ bool fast_cell(R xw, const PartConst<R>& c, int M, int& il, R& f) {
+    R q = RT<R>::mul(xw, c.inv_dx);
+    int i;
+    R r = RT<R>::rint_magic(q, i);
+    R diff = RT<R>::sub(q, r);
+    const bool neg = diff < (R)0;
+    f = neg ? RT<R>::sub(r, (R)1) : r;
+    il = neg ? i - 1 : i;
+    return !(RT<R>::abs(diff) > c.idx_thr) | ((unsigned)il >= (unsigned)M);
+}
+
+template <typename R, bool KICK, bool MOVE, bool EXACT_W>
+__device__ __forceinline__ bool particle_fast(R x, R v, R& xn, R& vn, int& il_dep, long long& Wr_dep,
+                                              const typename PairT<R>::type* __restrict__ E_s, R cc, R dd,
+                                              const PartConst<R>& c, const MeshConst& mc) {
+    bool slow = false;
+    vn = v;
+    if (KICK) {
+        int il; R f;
+        slow = fast_cell<R>(x, c, mc.M, il, f);
+        il = (unsigned)il < (unsigned)mc.M ? il : 0;            // keep the gather address legal on the slow path
+        R fr = RT<R>::add(f, (R)1);
+        R nl = RT<R>::sub(RT<R>::mul(fr, c.dx), x);
+        R nr = RT<R>::sub(x, RT<R>::mul(f, c.dx));
+        R wl = EXACT_W ? RT<R>::div(nl, c.dx) : RT<R>::mul(nl, c.inv_dx);
+        R wr = EXACT_W ? RT<R>::div(nr, c.dx) : RT<R>::mul(nr, c.inv_dx);
+        const typename PairT<R>::type e = E_s[il];
+        R Ep = RT<R>::add(RT<R>::mul(wl, e.x), RT<R>::mul(wr, e.y));
+        vn = RT<R>::add(v, RT<R>::mul(RT<R>::mul(dd, -Ep), c.dt));
+    }
+    xn = MOVE ? RT<R>::add(x, RT<R>::mul(RT<R>::mul(cc, vn), c.dt)) : x;
+    R f2;
+    slow |= fast_cell<R>(xn, c, mc.M, il_dep, f2);
+    R nr2 = RT<R>::sub(xn, RT<R>::mul(f2, c.dx));
+    R wr2 = EXACT_W ? RT<R>::div(nr2, c.dx) : RT<R>::mul(nr2, c.inv_dx);
+    Wr_dep = fix_weight((double)wr2, mc.fix_scale);
+    return slow;
+}
+
+// Reference semantics, every case handled (cold block; reached by ~1e-5 .. 1e-2 of the particles).
+// wrap_state: the position written back is the wrapped one (pic.py:139 / util.py:51), else the unwrapped drift.
+template <typename R, bool KICK, bool MOVE, bool EXACT_W>
+__device__ __forceinline__ void particle_careful(R& x, R& v, int& il_dep, long long& Wr_dep,
+                                                 const typename PairT<R>::type* __restrict__ E_s, R cc, R dd,
+                                                 const PartConst<R>& c, const MeshConst& mc, bool wrap_state,
+                                                 unsigned& err) {
+    if (KICK) kick<R, EXACT_W>(x, v, E_s, dd, c, mc.M, err);
+    if (MOVE) x = drift<R>(x, v, cc, c);
+    R xw = wrap_pos<R>(x, c, err);
+    R f;
+    il_dep = cell_index<R>(xw, c, mc.M, f, err);
+    R nr = RT<R>::sub(xw, RT<R>::mul(f, c.dx));
+    R wr = EXACT_W ? RT<R>::div(nr, c.dx) : RT<R>::mul(nr, c.inv_dx);
+    Wr_dep = fix_weight((double)wr, mc.fix_scale);
+    if (wrap_state) x = xw;
+}
+
+// Deposit of one particle per lane, all 32 lanes of the warp calling together.  When every lane hits the same
+// cell (cell-sorted particles) the warp sums its weights with two REDUX instructions and one lane issues the
+// atomics -- instead of 32 serialised same-address atomics.  Integer sums: grouping never changes the result.
+template <typename H>
+__device__ __forceinline__ void deposit_full_warp(H& hist, int il, long long Wr, long long one) {
+    constexpr unsigned FULL = 0xffffffffu;
+    const int il0 = __shfl_sync(FULL, il, 0);
+    if (__all_sync(FULL, il == il0)) {
+        const unsigned long long W = (unsigned long long)Wr;           // 0 <= Wr <= 2^50: two 25-bit halves,
+        const unsigned a = __reduce_add_sync(FULL, (unsigned)(W & 0x1FFFFFFu));   // 32 of them sum below 2^30
+        const unsigned b = __reduce_add_sync(FULL, (unsigned)(W >> 25));
+        if ((threadIdx.x & 31) == 0)
+            hist.deposit_group(il, (unsigned long long)a + ((unsigned long long)b << 25), 32u, one);
+    } else {
+        hist.deposit(il, Wr, one);
+    }
+}
+
+// One sub-stage for one particle: fast path, careful fallback, deposit.  x, v are updated in place.
+// FULL_WARP: the caller guarantees that all 32 lanes of the warp execute this call (enables the aggregated deposit).
+template <typename R, bool KICK, bool MOVE, bool EXACT_W, bool FULL_WARP, typename H>
+__device__ __forceinline__ void particle_substage(R& x, R& v, H& hist, const typename PairT<R>::type* __restrict__ E_s,
+                                                  R cc, R dd, const PartConst<R>& c, const MeshConst& mc,
+                                                  bool wrap_state, unsigned& err) {
+    R xn, vn; int il; long long Wr;
+    const bool slow = particle_fast<R, KICK, MOVE, EXACT_W>(x, v, xn, vn, il, Wr, E_s, cc, dd, c, mc);
+    if (__builtin_expect(slow, 0)) {
+        particle_careful<R, KICK, MOVE, EXACT_W>(x, v, il, Wr, E_s, cc, dd, c, mc, wrap_state, err);
+    } else {
+        x = xn; v = vn;                                   // inside [0, L): wrapped == unwrapped
+    }
+    if (FULL_WARP) deposit_full_warp(hist, il, Wr, mc.fix_one);
+    else hist.deposit(il, Wr, mc.fix_one);
 }
 
 // streaming loads / stores (no reuse: keep the particle stream out of L1, evict-first in L2)

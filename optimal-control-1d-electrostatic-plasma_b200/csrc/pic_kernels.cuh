@@ -11,6 +11,8 @@
 //   field_finalize_kernel
 //                        state field after a streaming step: density, self-consistent E, energies.
 #pragma once
+#include <type_traits>
+
 #include "pic_device.cuh"
 
 namespace pic {
@@ -118,41 +120,48 @@ __global__ void __launch_bounds__(THREADS) push_stream_kernel(const StreamArgs a
     unsigned err = 0;
     double s2 = 0.0, s1 = 0.0;
 
-    auto one = [&](R& x, R& v) {
-        if (KICK) kick<R, EXACT_W>(x, v, sm.E_s, dd, pc, M, err);
-        if (MODE != MODE_INIT) x = drift<R>(x, v, cc, pc);
-        R xw = wrap_pos<R>(x, pc, err);
-        if (SUMS) { x = xw; s2 += (double)v * (double)v; s1 += (double)v; }
-        deposit<R, EXACT_W>(xw, hist, pc, a.mc, err);
+    auto one = [&](R& x, R& v, auto full_warp) {
+        particle_substage<R, KICK, MODE != MODE_INIT, EXACT_W, decltype(full_warp)::value>(
+            x, v, hist, sm.E_s, cc, dd, pc, a.mc, SUMS, err);
+        if (SUMS) { s2 += (double)v * (double)v; s1 += (double)v; }
+    };
+    auto vec_pair = [&](long long i, auto full_warp) {      // one 16-byte vector of x and of v
+        V xq = ld_stream(xv + i), vq = ld_stream(vv + i);
+        R* px = reinterpret_cast<R*>(&xq);
+        R* pv = reinterpret_cast<R*>(&vq);
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) one(px[e], pv[e], full_warp);
+        st_stream(xv + i, xq);
+        if (KICK) st_stream(vv + i, vq);
     };
 
-    const long long stride = (long long)gridDim.x * THREADS * UNROLL;
-    for (long long base = (long long)blockIdx.x * THREADS * UNROLL + tid; base < nvec; base += stride) {
+    // full tiles: every lane of every warp has work, so warp-wide primitives may use the full mask
+    constexpr long long TILE = (long long)THREADS * UNROLL;
+    const long long n_tiles = nvec / TILE;
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const long long base = tile * TILE + tid;
         V xs[UNROLL], vs[UNROLL];
 #pragma unroll
-        for (int u = 0; u < UNROLL; ++u) {
-            long long i = base + (long long)u * THREADS;
-            if (i < nvec) { xs[u] = ld_stream(xv + i); vs[u] = ld_stream(vv + i); }
-        }
+        for (int u = 0; u < UNROLL; ++u) { xs[u] = ld_stream(xv + base + u * THREADS); vs[u] = ld_stream(vv + base + u * THREADS); }
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u) {
-            long long i = base + (long long)u * THREADS;
-            if (i < nvec) {
-                R* px = reinterpret_cast<R*>(&xs[u]);
-                R* pv = reinterpret_cast<R*>(&vs[u]);
+            R* px = reinterpret_cast<R*>(&xs[u]);
+            R* pv = reinterpret_cast<R*>(&vs[u]);
 #pragma unroll
-                for (int e = 0; e < VEC; ++e) one(px[e], pv[e]);
-                st_stream(xv + i, xs[u]);
-                if (KICK) st_stream(vv + i, vs[u]);
-            }
+            for (int e = 0; e < VEC; ++e) one(px[e], pv[e], std::true_type{});
+            st_stream(xv + base + u * THREADS, xs[u]);
+            if (KICK) st_stream(vv + base + u * THREADS, vs[u]);
         }
     }
-    // scalar tail (N not a multiple of the vector width)
+    // ragged remainder (< one tile of vectors) and the scalar tail (N not a multiple of the vector width)
+    if (blockIdx.x == (unsigned)(n_tiles % gridDim.x)) {
+        for (long long i = n_tiles * TILE + tid; i < nvec; i += THREADS) vec_pair(i, std::false_type{});
+    }
     if (blockIdx.x == 0) {
         long long i = nvec * VEC + tid;
         if (i < a.N) {
             R x = xe[i], v = ve[i];
-            one(x, v);
+            one(x, v, std::false_type{});
             xe[i] = x;
             if (KICK) ve[i] = v;
         }
@@ -289,10 +298,8 @@ __global__ void __launch_bounds__(THREADS) env_step_resident_kernel(const Reside
     if (a.n_steps == 0) {                                         // pic.py:76-77 on a fresh state
 #pragma unroll
         for (int j = 0; j < PPT; ++j) {
-            if (j * THREADS + tid < N) {
-                xs[j] = wrap_pos<R>(xs[j], pc, err);
-                deposit<R, EXACT_W>(xs[j], hist, pc, a.mc, err);
-            }
+            if (j * THREADS + tid < N)
+                particle_substage<R, false, false, EXACT_W, false>(xs[j], vs[j], hist, sm.E_s, (R)0, (R)0, pc, a.mc, true, err);
         }
         __syncthreads();
         dump_rho();
@@ -313,11 +320,10 @@ __global__ void __launch_bounds__(THREADS) env_step_resident_kernel(const Reside
 #pragma unroll
             for (int j = 0; j < PPT; ++j) {
                 if (j * THREADS + tid < N) {
-                    if (st > 0) kick<R, EXACT_W>(xs[j], vs[j], sm.E_s, dd, pc, M, err);
-                    xs[j] = drift<R>(xs[j], vs[j], cc, pc);
-                    R xw = wrap_pos<R>(xs[j], pc, err);
-                    if (fin) xs[j] = xw;                           // pic.py:139
-                    deposit<R, EXACT_W>(xw, hist, pc, a.mc, err);
+                    if (st == 0)
+                        particle_substage<R, false, true, EXACT_W, false>(xs[j], vs[j], hist, sm.E_s, cc, dd, pc, a.mc, false, err);
+                    else                                           // fin: state wrap of pic.py:139
+                        particle_substage<R, true, true, EXACT_W, false>(xs[j], vs[j], hist, sm.E_s, cc, dd, pc, a.mc, fin, err);
                 }
             }
             __syncthreads();

@@ -21,15 +21,22 @@ const void* resident_kernel_f64(int t, int p, int d, bool e) {
     return k;
 }
 
-static const int kPpt128[] = {40, 0};
-static const int kPpt256[] = {4, 8, 12, 16, 20, 24, 32, 40, 0};
-static const int kPpt512[] = {10, 20, 0};
-static const int kPpt1024[] = {5, 0};
-int resident_pick_ppt(int threads, long long n) {
-    const int* t = threads == 128 ? kPpt128 : threads == 256 ? kPpt256 : threads == 512 ? kPpt512
-                 : threads == 1024 ? kPpt1024 : nullptr;
-    if (!t) return 0;
-    for (; *t; ++t) if ((long long)threads * *t >= n) return *t;
-    return 0;
+// Compiled (threads, particles-per-thread) shapes of the resident kernel.  More threads per CTA win as long as the
+// per-thread particle state fits the register budget (1024 threads -> 64 registers -> at most 6 fp64 particles).
+struct Shape { int threads, ppt; };
+static const Shape kShapesF64[] = {{1024, 1}, {1024, 2}, {1024, 3}, {1024, 4}, {1024, 5}, {1024, 6}, {512, 8}, {512, 10},
+                                   {512, 12}, {512, 16}, {512, 20}, {256, 24}, {256, 32}, {256, 40}, {0, 0}};
+static const Shape kShapesF32[] = {{1024, 1}, {1024, 2}, {1024, 3}, {1024, 4}, {1024, 5}, {1024, 6}, {1024, 8}, {1024, 10},
+                                   {512, 12}, {512, 16}, {512, 20}, {0, 0}};
+bool resident_pick_shape(long long n, bool f32, int* threads, int* ppt) {
+    for (const Shape* s = f32 ? kShapesF32 : kShapesF64; s->threads; ++s)
+        if ((long long)s->threads * s->ppt >= n) { *threads = s->threads; *ppt = s->ppt; return true; }
+    return false;
+}
+long long resident_capacity(bool f32) {
+    long long best = 0;
+    for (const Shape* s = f32 ? kShapesF32 : kShapesF64; s->threads; ++s)
+        if ((long long)s->threads * s->ppt > best) best = (long long)s->threads * s->ppt;
+    return best;
 }
 }  // namespace pic

@@ -10,8 +10,9 @@ const void* stream_kernel_f32(int threads, int unroll, int mode, int dep, bool e
 const void* resident_kernel_f64(int threads, int ppt, int dep, bool exact_w);
 const void* resident_kernel_f32(int threads, int ppt, int dep, bool exact_w);
 
-// smallest compiled PPT with threads*ppt >= n for the given thread count; 0 when none fits
-int resident_pick_ppt(int threads, long long n);
+// default resident launch shape for n particles per env; false when n exceeds what one CTA keeps in registers
+bool resident_pick_shape(long long n, bool f32, int* threads, int* ppt);
+long long resident_capacity(bool f32);
 
 
 
