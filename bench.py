@@ -253,9 +253,17 @@ def run_gpu_arm(args):
     kick_ms = float(np.mean(stage_ms[1:4]))
     alg_bytes = 32.0 * N_local                          # read x,v + write x,v, float64 (DESIGN.md "Roofline")
     achieved = alg_bytes / (kick_ms * 1e-3) / 1e9
+    traffic, traffic_src = None, None
+    try:                                                # DRAM bytes of the same kernel from the committed ncu capture
+        with open(os.path.join(ROOT, "profiles", "traffic_r01.json")) as f:
+            tj = json.load(f)
+        traffic, traffic_src = tj["traffic_bytes_per_particle"] * N_local, tj["source"]
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "kernel": "push_stream_kernel<MODE_KICK> (stages 1-3 of 4)", "achieved": achieved,
                 "peak": hbm_peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / hbm_peak,
-                "traffic": None, "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": kick_ms,
+                "traffic": traffic, "traffic_source": traffic_src,
+                "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": kick_ms,
                 "stage_ms": [float(s) for s in stage_ms],
                 "step_frac_of_hbm": (120.0 * N_local / (float(stage_ms.sum()) * 1e-3) / 1e9) / hbm_peak}
     flags = eng.error_flags()
