@@ -349,54 +349,115 @@ struct ExtSrc {
 // Periodic 3-point Poisson + centred difference in closed form (DESIGN.md "Field solve"):
 //   b_j = n_j - n0,  S_j = sum_{i<=j} b_i,  D_j = dx^2 (S_j - mean S),  E_j = -(D_j + D_{j-1}) / (2 dx)
 // which is the reference's Thomas/Sherman-Morrison solve of laplacian @ phi = b followed by -grad @ phi
-// (src/env/util.py:99-100) without forming phi.  Block-cooperative; every thread must call it.
+// (src/env/util.py:99-100) without forming phi.
 //
-//   rho      : M fixed-point cell sums (global or shared memory), already including the wrap cell
+// Block-cooperative with TWO block barriers (A after the per-thread prefix sums, C before the result is used).
+// The first FIELD_THREADS (<= 256) threads own contiguous runs of cells; each warp publishes three numbers --
+// its sum of b, the sum of its local prefixes and its cell count -- from which every field thread derives its own
+// offset, the grand total and sum_j S_j without further communication (S_{j-1} of a thread's first cell is its
+// exclusive offset, so D_{j-1} never comes from a neighbour).  The other threads meanwhile run `idle_work` (the
+// resident kernel clears the histogram there).  Every thread must call this.
+//
+//   rho      : M fixed-point cell sums (functor; global or shared memory)
 //   E_s      : shared, M pairs (E_j + ext_j, E_{j+1 mod M} + ext_{j+1 mod M}) for the gather
-//   D_s      : shared scratch, M doubles
-//   red      : shared scratch, THREADS/32 + 1 doubles
+//   D_s      : shared scratch, M doubles;  red: shared scratch, field_scratch_doubles(THREADS) doubles
 //   ext      : external field source added to what particles see (util.py:102-103)
 //   n_out/E_out : nullptr or global outputs of the density (interpolate.py:18) / self-consistent field
-// Returns sum_j E_j^2 of the self-consistent field (all threads) when WANT_E2, else 0.
-template <typename R, int THREADS, bool WANT_E2, typename RhoLoad>
-__device__ __forceinline__ double block_field(RhoLoad rho, typename PairT<R>::type* E_s, double* D_s, double* red,
-                                              const MeshConst& mc,
-                                              const ExtSrc& ext, double* __restrict__ n_out,
-                                              double* __restrict__ E_out) {
-    const bool has_ext = ext.any();
-    const int M = mc.M, tid = threadIdx.x;
-    const int cpt = (M + THREADS - 1) / THREADS;
+//   x1, x2   : two per-thread values summed over the block on the way (kinetic sums)
+// Returns {sum_j E_j^2 (self-consistent field), sum x1, sum x2}; valid in warp 0 only.
+struct FieldTotals { double e2, s1, s2; };
+
+template <int THREADS> struct FieldShape {
+    static constexpr int FT = THREADS < 256 ? THREADS : 256;     // field threads
+    static constexpr int NWF = FT / 32, NW = THREADS / 32;
+};
+template <int THREADS>
+__host__ __device__ constexpr int field_scratch_doubles_t() { return 3 * FieldShape<THREADS>::NWF + 3 * FieldShape<THREADS>::NW; }
+__host__ __device__ constexpr int field_scratch_doubles(int threads) { return 3 * ((threads < 256 ? threads : 256) / 32) + 3 * (threads / 32); }
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+template <typename R, int THREADS, typename RhoLoad, typename IdleWork>
+__device__ __forceinline__ FieldTotals block_field(RhoLoad rho, typename PairT<R>::type* E_s, double* D_s, double* red,
+                                                   const MeshConst& mc, const ExtSrc& ext, double* __restrict__ n_out,
+                                                   double* __restrict__ E_out, double x1, double x2,
+                                                   IdleWork idle_work) {
+    constexpr int FT = FieldShape<THREADS>::FT, NWF = FieldShape<THREADS>::NWF, NW = FieldShape<THREADS>::NW;
+    const int M = mc.M, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const bool field_thread = tid < FT;
+    const int cpt = (M + FT - 1) / FT;
     const int j0 = tid * cpt, j1 = min(M, j0 + cpt);
-    double run = 0.0, sumS_local = 0.0;
-    for (int j = j0; j < j1; ++j) {
-        double nj = (double)(long long)rho(j) * mc.inv_fix * mc.scale;
-        if (n_out) n_out[j] = nj;
-        run += nj - mc.n0;
-        D_s[j] = run;                                 // local inclusive prefix
+    double* red2 = red + 3 * NWF;
+    const bool has_ext = ext.any();
+
+    double run = 0.0, excl = 0.0;
+    if (field_thread) {
+        double ls = 0.0;
+        for (int j = j0; j < j1; ++j) {
+            double nj = (double)(long long)rho(j) * mc.inv_fix * mc.scale;
+            if (n_out) n_out[j] = nj;
+            run += nj - mc.n0;
+            D_s[j] = run;                              // inclusive prefix inside this thread's run of cells
+            ls += run;
+        }
+        const double ncell = j1 > j0 ? (double)(j1 - j0) : 0.0;
+        double inc = run;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            double t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
+        }
+        excl = inc - run;
+        const double a = warp_sum(ls + ncell * excl);
+        const double c = warp_sum(ncell);
+        const double wt = __shfl_sync(0xffffffffu, inc, 31);
+        if (lane == 0) { red[3 * w] = wt; red[3 * w + 1] = a; red[3 * w + 2] = c; }
     }
-    const double off = block_excl_scan<THREADS>(run, red);
-    for (int j = j0; j < j1; ++j) {
-        double S = D_s[j] + off;
-        D_s[j] = S;
-        sumS_local += S;
-    }
-    const double meanS = block_sum<THREADS>(sumS_local, red) / (double)M;   // (syncs inside publish D_s)
-    const double dx2 = mc.dx * mc.dx, inv2dx = 1.0 / (2.0 * mc.dx);
+    __syncthreads();                                   // (A) warp triples published; all reads of rho are done
+
     double e2 = 0.0;
-    for (int j = j0; j < j1; ++j) {
-        const int jm = j == 0 ? M - 1 : j - 1;
-        double Dj = dx2 * (D_s[j] - meanS), Dm = dx2 * (D_s[jm] - meanS);
-        double E = -(Dj + Dm) * inv2dx;
-        if (E_out) E_out[j] = E;
-        if (WANT_E2) e2 += E * E;
-        double Et = has_ext ? E + ext.at(j) : E;
-        E_s[j].x = (R)Et;
-        E_s[jm].y = (R)Et;
+    if (field_thread) {
+        double total = 0.0, sumS = 0.0, myoff = 0.0;
+#pragma unroll
+        for (int k = 0; k < NWF; ++k) {
+            if (k == w) myoff = total;
+            sumS += red[3 * k + 1] + red[3 * k + 2] * total;
+            total += red[3 * k];
+        }
+        const double meanS = sumS / (double)M;
+        const double off = myoff + excl;
+        const double dx2 = mc.dx * mc.dx, inv2dx = 1.0 / (2.0 * mc.dx);
+        double prevS = j0 == 0 ? total : off;          // S_{j0-1}; periodic: S_{-1} = S_{M-1} = total
+        for (int j = j0; j < j1; ++j) {
+            const int jm = j == 0 ? M - 1 : j - 1;
+            const double S = D_s[j] + off;
+            const double E = -(dx2 * (S - meanS) + dx2 * (prevS - meanS)) * inv2dx;
+            prevS = S;
+            if (E_out) E_out[j] = E;
+            e2 += E * E;
+            const double Et = has_ext ? E + ext.at(j) : E;
+            E_s[j].x = (R)Et;
+            E_s[jm].y = (R)Et;
+        }
+    } else {
+        idle_work();
     }
-    double tot = 0.0;
-    if (WANT_E2) tot = block_sum<THREADS>(e2, red);
-    __syncthreads();
-    return tot;
+    if (FT == THREADS) idle_work();                    // no spare threads: everyone does it after its share
+    e2 = warp_sum(e2); x1 = warp_sum(x1); x2 = warp_sum(x2);
+    if (lane == 0) { red2[3 * w] = e2; red2[3 * w + 1] = x1; red2[3 * w + 2] = x2; }
+    __syncthreads();                                   // (C) gather table, idle work and partial sums complete
+
+    FieldTotals t{0.0, 0.0, 0.0};
+    if (w == 0) {
+        t.e2 = warp_sum(lane < NW ? red2[3 * lane] : 0.0);
+        t.s1 = warp_sum(lane < NW ? red2[3 * lane + 1] : 0.0);
+        t.s2 = warp_sum(lane < NW ? red2[3 * lane + 2] : 0.0);
+    }
+    return t;
 }
 
 // ------------------------------------------------------------------- push step

@@ -54,7 +54,7 @@ __host__ __device__ constexpr size_t smem_plan_bytes(int M, int threads, bool se
     return (size_t)M * 2 * sizeof(R)                 // gather pair table
          + (((size_t)M * 12 + 16 + 15) & ~(size_t)15)   // histogram
          + (separate_d ? (size_t)M * 8 : 0)          // D_s
-         + (size_t)(threads / 32 + 2) * 8;           // reduction scratch
+         + (size_t)(field_scratch_doubles(threads) + threads / 32 + 2) * 8;   // field / reduction scratch
 }
 
 template <typename R>
@@ -102,7 +102,7 @@ __global__ void __launch_bounds__(THREADS) push_stream_kernel(const StreamArgs a
     if (KICK) {                                         // D_s aliases the histogram: solve first, then clear
         const ExtSrc ext = stage_ext(a.act, env, M);
         GlobalRho rho{a.rho_in + (size_t)env * M};
-        block_field<R, THREADS, false>(rho, sm.E_s, sm.D_s, sm.red, a.mc, ext, nullptr, nullptr);
+        block_field<R, THREADS>(rho, sm.E_s, sm.D_s, sm.red, a.mc, ext, nullptr, nullptr, 0.0, 0.0, [] {});
     }
     hist.zero(tid, THREADS);
     __syncthreads();
@@ -205,23 +205,21 @@ __global__ void __launch_bounds__(THREADS) field_finalize_kernel(const FinalizeA
     SmemLayout<double> sm(smem_raw, M, false);
     GlobalRho rho{a.rho + (size_t)env * M};
     const ExtSrc none{nullptr, nullptr, nullptr, nullptr, 0};
-    double e2 = block_field<double, THREADS, true>(rho, sm.E_s, sm.D_s, sm.red, a.mc, none,
-                                                   a.n_out + (size_t)env * M, a.E_out + (size_t)env * M);
-    if (a.rho_zero) for (int j = tid; j < M; j += THREADS) a.rho_zero[(size_t)env * M + j] = 0ull;
     double s2 = 0.0, s1 = 0.0;
     if (a.partial) {
         const double* p = a.partial + (size_t)env * a.n_partial * 2;
         for (int i = tid; i < a.n_partial; i += THREADS) { s2 += p[2 * i]; s1 += p[2 * i + 1]; }
-        s2 = block_sum<THREADS>(s2, sm.red);
-        s1 = block_sum<THREADS>(s1, sm.red);
     }
+    const FieldTotals t = block_field<double, THREADS>(rho, sm.E_s, sm.D_s, sm.red, a.mc, none,
+                                                       a.n_out + (size_t)env * M, a.E_out + (size_t)env * M, s2, s1, [] {});
+    if (a.rho_zero) for (int j = tid; j < M; j += THREADS) a.rho_zero[(size_t)env * M + j] = 0ull;
     if (tid == 0) {
         double* d = a.diag + (size_t)env * DIAG_N;
-        d[DIAG_PE_MESH] = 0.5 * e2 * a.mc.dx;
-        d[DIAG_SUM_E2] = e2;
+        d[DIAG_PE_MESH] = 0.5 * t.e2 * a.mc.dx;
+        d[DIAG_SUM_E2] = t.e2;
         if (a.partial) {
-            a.vsum[env * 2] = s2; a.vsum[env * 2 + 1] = s1;
-            d[DIAG_KE] = 0.5 * s2; d[DIAG_SUM_V] = s1;
+            a.vsum[env * 2] = t.s1; a.vsum[env * 2 + 1] = t.s2;
+            d[DIAG_KE] = 0.5 * t.s1; d[DIAG_SUM_V] = t.s2;
         }
     }
 }
@@ -270,29 +268,35 @@ __global__ void __launch_bounds__(THREADS) env_step_resident_kernel(const Reside
     double* E_out = a.E_out + (size_t)env * M;
     const ExtSrc none{nullptr, nullptr, nullptr, nullptr, 0};
 
-    auto write_diag = [&](double e2, int step) {
-        double s2 = 0.0, s1 = 0.0;
+    auto kinetic = [&](double& s2, double& s1) {
+        s2 = 0.0; s1 = 0.0;
 #pragma unroll
         for (int j = 0; j < PPT; ++j) {       // padded particles carry v == 0
             s2 += (double)vs[j] * (double)vs[j]; s1 += (double)vs[j];
         }
-        s2 = block_sum<THREADS>(s2, sm.red);
-        s1 = block_sum<THREADS>(s1, sm.red);
+    };
+    auto write_diag = [&](const FieldTotals& t, int step) {      // totals are valid in warp 0
         if (tid == 0) {
             double rec[DIAG_N];
-            rec[DIAG_KE] = 0.5 * s2; rec[DIAG_PE_MESH] = 0.5 * e2 * a.mc.dx; rec[DIAG_SUM_V] = s1; rec[DIAG_SUM_E2] = e2;
+            rec[DIAG_KE] = 0.5 * t.s1; rec[DIAG_PE_MESH] = 0.5 * t.e2 * a.mc.dx; rec[DIAG_SUM_V] = t.s2; rec[DIAG_SUM_E2] = t.e2;
             double* d = a.diag + (size_t)env * DIAG_N;
 #pragma unroll
             for (int k = 0; k < DIAG_N; ++k) d[k] = rec[k];
             if (a.trace && step >= 0) {
-                double* t = a.trace + ((size_t)step * gridDim.x + env) * DIAG_N;
+                double* tr = a.trace + ((size_t)step * gridDim.x + env) * DIAG_N;
 #pragma unroll
-                for (int k = 0; k < DIAG_N; ++k) t[k] = rec[k];
+                for (int k = 0; k < DIAG_N; ++k) tr[k] = rec[k];
             }
         }
     };
     auto dump_rho = [&]() {
         if (a.rho_out) for (int j = tid; j < M; j += THREADS) a.rho_out[(size_t)env * M + j] = rho(j);
+    };
+    // the threads that do not take part in the field solve clear the histogram for the next sub-stage meanwhile
+    constexpr int FT = FieldShape<THREADS>::FT;
+    auto clear_hist = [&]() {
+        if (FT == THREADS) hist.zero(tid, THREADS);
+        else hist.zero(tid - FT, THREADS - FT);
     };
 
     if (a.n_steps == 0) {                                         // pic.py:76-77 on a fresh state
@@ -303,8 +307,9 @@ __global__ void __launch_bounds__(THREADS) env_step_resident_kernel(const Reside
         }
         __syncthreads();
         dump_rho();
-        double e2 = block_field<R, THREADS, true>(rho, sm.E_s, sm.D_s, sm.red, a.mc, none, n_out, E_out);
-        write_diag(e2, -1);
+        double s2, s1;
+        kinetic(s2, s1);
+        write_diag(block_field<R, THREADS>(rho, sm.E_s, sm.D_s, sm.red, a.mc, none, n_out, E_out, s2, s1, clear_hist), -1);
     }
 
     for (int step = 0; step < a.n_steps; ++step) {
@@ -328,15 +333,14 @@ __global__ void __launch_bounds__(THREADS) env_step_resident_kernel(const Reside
             }
             __syncthreads();
             if (!fin) {
-                block_field<R, THREADS, false>(rho, sm.E_s, sm.D_s, sm.red, a.mc, ext, nullptr, nullptr);
+                block_field<R, THREADS>(rho, sm.E_s, sm.D_s, sm.red, a.mc, ext, nullptr, nullptr, 0.0, 0.0, clear_hist);
             } else {
                 if (last) dump_rho();
-                double e2 = block_field<R, THREADS, true>(rho, sm.E_s, sm.D_s, sm.red, a.mc, none,
-                                                          last ? n_out : nullptr, last ? E_out : nullptr);
-                write_diag(e2, step);
+                double s2, s1;
+                kinetic(s2, s1);
+                write_diag(block_field<R, THREADS>(rho, sm.E_s, sm.D_s, sm.red, a.mc, none, last ? n_out : nullptr,
+                                                   last ? E_out : nullptr, s2, s1, clear_hist), step);
             }
-            hist.zero(tid, THREADS);
-            __syncthreads();
         }
     }
 
