@@ -445,3 +445,45 @@ def runner_initial_state(simcase: str, N=5000, L=50.0, vb=3.0, vth=1.0, a=0.2, A
             raise ValueError(simcase)
     v = perturb_velocity(x, v, A, n_mode, L)
     return x, v
+
+
+# --------------------------------------------------------------------------
+# float32 mode (no reference counterpart: the reference is float64 only)
+# --------------------------------------------------------------------------
+def step_f32(x, v, p: PicParams, E_ext: Optional[np.ndarray] = None):
+    """Restatement of the library's PIC_F32 mode for index parity: particle state, wrap, cell index, weights,
+    gather, kick and drift in float32 (same operation order as `step`), density accumulation and the mesh field in
+    float64, the gather table rounded to float32.  Returns dict(x, v, indx_l, E_mesh, n) with x, v float32."""
+    f = np.float32
+    cs, ds = yoshida_coefficients()
+    L, dx, dt = f(p.L), f(p.dx), f(p.dt)
+    inv_dx = f(1) / dx
+    q = np.asarray(x, dtype=f).copy()
+    pm = np.asarray(v, dtype=f).copy()
+    ext = None if E_ext is None else np.asarray(E_ext, dtype=np.float64).reshape(-1)
+
+    def cells(xq):
+        xw = np.mod(np.mod(xq, L), L).astype(f)
+        il = np.floor(xw / dx).astype(np.int64)
+        fl = il.astype(f)
+        wl = (((fl + f(1)) * dx - xw) * inv_dx).astype(f)
+        wr = ((xw - fl * dx) * inv_dx).astype(f)
+        return xw, il, wl, wr
+
+    def density(il, wr):
+        w = wr.astype(np.float64)
+        n = np.bincount(il, weights=1.0 - w, minlength=p.N_mesh) + np.bincount((il + 1) % p.N_mesh, weights=w,
+                                                                                minlength=p.N_mesh)
+        return n * (p.n0 * p.L / p.N / p.dx)
+
+    for c, d in zip(cs, ds):
+        if d != 0.0:
+            xw, il, wl, wr = cells(q)
+            E_mesh = field_prefix(density(il, wr), p.n0, p.L, p.N_mesh)
+            Et = (E_mesh + ext if ext is not None else E_mesh).astype(f)
+            Ep = (wl * Et[il] + wr * Et[(il + 1) % p.N_mesh]).astype(f)
+            pm = (pm + (f(d) * (-Ep)) * dt).astype(f)
+        q = (q + (f(c) * pm) * dt).astype(f)
+    xw, il, wl, wr = cells(q)
+    n = density(il, wr)
+    return dict(x=xw, v=pm, indx_l=il, n=n, E_mesh=field_prefix(n, p.n0, p.L, p.N_mesh))
