@@ -40,7 +40,9 @@ enum { PIC_DIAG_KE = 0,        /* 0.5*sum(v^2)            src/env/util.py:144   
        PIC_DIAG_PE_MESH = 1,   /* 0.5*sum(E_mesh^2)*dx    src/control/objective.py:31 (reward term) */
        PIC_DIAG_SUM_V = 2,     /* sum(v)                                                            */
        PIC_DIAG_SUM_E2 = 3,    /* sum(E_mesh^2)                                                     */
-       PIC_DIAG_N = 4 };
+       PIC_DIAG_REWARD = 4,    /* Reward.compute_reward of the transition into this state, reward.py:71-76 */
+       PIC_DIAG_INPUT_E = 5,   /* sum(a^2)*L/4 of the applied action, reward.py:52-54 (0 for mesh-vector control) */
+       PIC_DIAG_N = 6 };
 
 typedef struct pic_handle pic_handle;
 
@@ -109,6 +111,17 @@ int pic_step_coeffs(pic_handle* h, const double* coeffs, int32_t n_steps);
 /* Same two calls with DEVICE pointers (no copies, nothing synchronises). */
 int pic_step_mesh_device(pic_handle* h, const double* E_ext_dev, int32_t n_steps);
 int pic_step_coeffs_device(pic_handle* h, const double* coeffs_dev, int32_t n_steps);
+/* Device-side Reward (src/control/rl/reward.py:5-34,71-76): every step records
+ *   alpha * max(1 - PE_mesh(s_t)/r_pe_n, 0) + beta * max(1 - (sum a_t^2 L/4)/r_ie_n, 0)
+ * with s_t the state BEFORE the step (the trainers' convention, ddpg.py:425-455).  Defaults: alpha = beta = 1,
+ * r_pe_n = 1, r_ie_n = 10 L/4 (the reference's n_actions = 10). */
+int pic_set_reward(pic_handle* h, double alpha, double beta, double r_pe_n, double r_ie_n);
+/* Spectral read-out: first n_modes (<= 8) Fourier modes of the self-consistent mesh field with the normalisation of
+ * src/interpret/spectrum.py:17 (fft/N_mesh*2), k = 1..n_modes, layout [env][Re_1..Re_m, Im_1..Im_m].  The linear
+ * feedback law of run_feedback.py and the behaviour-cloning target of ddpg.py:429-431 are (-Re, +Im) of these. */
+int pic_enable_modes(pic_handle* h, int32_t n_modes);
+int pic_get_modes(pic_handle* h, double* modes);                          /* current state                    */
+int pic_get_mode_trace(pic_handle* h, double* modes, int32_t n_steps);    /* per step of the last pic_step_*  */
 int pic_sync(pic_handle* h);
 /* sticky numeric flags raised on the device (bit 0: cell index out of range, bit 1: non-finite position) */
 int pic_get_error_flags(pic_handle* h, uint32_t* flags);

@@ -12,7 +12,7 @@ PIC_OK = 0
 PIC_F64, PIC_F32 = 0, 1
 PIC_MODE_AUTO, PIC_MODE_RESIDENT, PIC_MODE_STREAMING = 0, 1, 2
 PIC_DEPOSIT_AUTO, PIC_DEPOSIT_CAS64, PIC_DEPOSIT_SPLIT32 = -1, 0, 1
-DIAG_KE, DIAG_PE_MESH, DIAG_SUM_V, DIAG_SUM_E2, DIAG_N = 0, 1, 2, 3, 4
+DIAG_KE, DIAG_PE_MESH, DIAG_SUM_V, DIAG_SUM_E2, DIAG_REWARD, DIAG_INPUT_E, DIAG_N = 0, 1, 2, 3, 4, 5, 6
 ERR_INDEX_RANGE, ERR_NONFINITE = 1, 2
 
 
@@ -56,6 +56,10 @@ SIGNATURES = {
     "pic_step_coeffs": (C.c_int, [_H, C.c_void_p, C.c_int32]),
     "pic_step_mesh_device": (C.c_int, [_H, C.c_void_p, C.c_int32]),
     "pic_step_coeffs_device": (C.c_int, [_H, C.c_void_p, C.c_int32]),
+    "pic_set_reward": (C.c_int, [_H, C.c_double, C.c_double, C.c_double, C.c_double]),
+    "pic_enable_modes": (C.c_int, [_H, C.c_int32]),
+    "pic_get_modes": (C.c_int, [_H, C.c_void_p]),
+    "pic_get_mode_trace": (C.c_int, [_H, C.c_void_p, C.c_int32]),
     "pic_sync": (C.c_int, [_H]),
     "pic_get_error_flags": (C.c_int, [_H, C.POINTER(C.c_uint32)]),
     "pic_get_device_views": (C.c_int, [_H, C.POINTER(PicDeviceViews)]),

@@ -47,17 +47,16 @@ class BatchedPIC:
             from .actuator import E_field
             act = E_field(L, N_mesh, max_mode)
             self.engine.set_actuator_basis(act.basis_cos, act.basis_sin)
-        # reward constants, src/control/rl/reward.py:32-33,71-76
+        # reward constants, src/control/rl/reward.py:32-33,71-76 -- the reward itself is computed on the device
         self.alpha, self.beta = alpha, beta
         self.r_pe_n = 1.0
         self.r_ie_n = float(n_actions) * L * 0.25
-        self._pe_prev = None
+        self.engine.set_reward(alpha, beta, self.r_pe_n, self.r_ie_n)
 
     # ---- state
     def set_state(self, x, v):
         """x, v: (n_envs_local, N) float64."""
         self.engine.set_state(x, v)
-        self._pe_prev = self.engine.get_diag()[:, L.DIAG_PE_MESH].copy()
 
     def reset_from_sampler(self, make_dist, A: float = 0.1, n_mode: int = 2, seed: Optional[int] = 42):
         """Fills every local env from a host sampler: env e (global index) is seeded with seed + e, sampled by
@@ -85,23 +84,22 @@ class BatchedPIC:
         reward for each transition (computed on the PRE-step state, ddpg.py:455)."""
         if actions is None:
             self.engine.step_mesh(None, n_steps)
-            a = None
         else:
             a = np.asarray(actions, dtype=np.float64)
             if a.ndim == 2:
                 a = np.broadcast_to(a, (n_steps,) + a.shape)
             self.engine.step_coeffs(np.ascontiguousarray(a), n_steps)
         tr = self.engine.get_trace(n_steps)
-        pe = tr[:, :, L.DIAG_PE_MESH]
-        pe_pre = np.concatenate([self._pe_prev[None, :], pe[:-1]], axis=0)
-        r = self.alpha * np.maximum(1.0 - pe_pre / self.r_pe_n, 0)
-        if a is not None:
-            ie = np.sum(a ** 2, axis=2) * self.L * 0.25                 # reward.py:52-54
-            r = r + self.beta * np.maximum(1.0 - ie / self.r_ie_n, 0)
-        else:
-            r = r + self.beta
-        self._pe_prev = pe[-1].copy()
-        return {"pe_mesh": pe, "ke": tr[:, :, L.DIAG_KE], "sum_v": tr[:, :, L.DIAG_SUM_V], "reward": r}
+        out = {"pe_mesh": tr[:, :, L.DIAG_PE_MESH], "ke": tr[:, :, L.DIAG_KE], "sum_v": tr[:, :, L.DIAG_SUM_V],
+               "reward": tr[:, :, L.DIAG_REWARD], "input_energy": tr[:, :, L.DIAG_INPUT_E]}
+        if self.engine.n_modes > 0:
+            out["modes"] = self.engine.get_mode_trace(n_steps)
+        return out
+
+    def enable_modes(self, n_modes: Optional[int] = None):
+        """Emit the first n_modes Fourier modes of E_mesh every step (default: max_mode), e.g. for the feedback law
+        a = (-Re E_k, +Im E_k) of run_feedback.py / the behaviour-cloning target of ddpg.py:429-431."""
+        self.engine.enable_modes(self.max_mode if n_modes is None else n_modes)
 
     def views(self):
         return self.engine.views()

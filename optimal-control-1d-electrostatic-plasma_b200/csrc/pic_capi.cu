@@ -79,6 +79,10 @@ struct pic_handle {
     unsigned long long* rho[4] = {nullptr, nullptr, nullptr, nullptr};   // W0, W1, W2, S
     double *n = nullptr, *E = nullptr, *diag = nullptr, *vsum = nullptr, *partial = nullptr;
     double *ext = nullptr, *coeffs = nullptr, *bcos = nullptr, *bsin = nullptr, *trace = nullptr;
+    double *tw_cos = nullptr, *tw_sin = nullptr, *modes = nullptr, *mode_trace = nullptr;   // spectral read-out
+    int n_modes = 0;
+    long long mode_trace_cap = 0;
+    RewardConst rw{1.0, 1.0, 1.0, 1.0, 1.0};
     double* stage64 = nullptr;                      // staging for f32 <-> f64 state conversion / cells
     size_t stage64_elems = 0;
     long long coeffs_cap = 0, trace_cap = 0;
@@ -122,12 +126,12 @@ const void* stream_kernel(const pic_handle* h, int mode) {
                   : stream_kernel_f64(h->threads, h->per_thread, mode, h->dep, h->exact_w);
 }
 const void* resident_kernel(const pic_handle* h) {
-    return h->f32 ? resident_kernel_f32(h->threads, h->per_thread, h->dep, h->exact_w)
-                  : resident_kernel_f64(h->threads, h->per_thread, h->dep, h->exact_w);
+    return h->f32 ? resident_kernel_f32(h->threads, h->dep, h->exact_w) : resident_kernel_f64(h->threads, h->dep, h->exact_w);
 }
 size_t smem_for(const pic_handle* h) {
-    return h->f32 ? smem_plan_bytes<float>(h->M, h->threads, h->resident)
-                  : smem_plan_bytes<double>(h->M, h->threads, h->resident);
+    if (h->resident)
+        return h->f32 ? resident_smem_bytes<float>(h->M, h->threads, h->N) : resident_smem_bytes<double>(h->M, h->threads, h->N);
+    return h->f32 ? smem_plan_bytes<float>(h->M, h->threads, false) : smem_plan_bytes<double>(h->M, h->threads, false);
 }
 
 int configure_launch(pic_handle* h) {
@@ -137,8 +141,7 @@ int configure_launch(pic_handle* h) {
                     std::to_string(h->smem) + " B needed, " + std::to_string(h->max_smem) + " B available)");
     if (h->resident) {
         const void* k = resident_kernel(h);
-        if (!k) return fail(h, PIC_EUNSUPPORTED, "no resident kernel variant for threads=" + std::to_string(h->threads) +
-                            " per_thread=" + std::to_string(h->per_thread));
+        if (!k) return fail(h, PIC_EUNSUPPORTED, "no resident kernel variant for threads=" + std::to_string(h->threads));
         CK(h, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
         h->grid_x = h->n_envs;
         return PIC_OK;
@@ -240,6 +243,8 @@ int run_stage(pic_handle* h, int stage, const double* ext, const double* coeffs,
         FinalizeArgs f{};
         f.mc = h->mc; f.rho = h->rho[3]; f.rho_zero = h->rho[2]; f.n_out = h->n; f.E_out = h->E; f.diag = h->diag;
         f.partial = h->partial; f.vsum = h->vsum; f.n_partial = h->grid_x;
+        f.rw = h->rw; f.coeffs = coeffs; f.two_m = 2 * h->m; f.step_done = trace_row != nullptr;
+        f.tw_cos = h->tw_cos; f.tw_sin = h->tw_sin; f.n_modes = h->n_modes; f.modes = h->n_modes > 0 ? h->modes : nullptr;
         void* args[] = {&f};
         CK(h, cudaLaunchKernel((const void*)&field_finalize_kernel<256>, dim3(h->n_envs), dim3(256), args,
                                smem_plan_bytes<double>(h->M, 256, false), h->stream));
@@ -284,6 +289,15 @@ int ensure_trace(pic_handle* h, int n_steps) {
         h->trace_cap = need;
     }
     h->trace_steps = n_steps;
+    if (h->n_modes > 0) {
+        long long need_m = (long long)n_steps * h->n_envs * 2 * h->n_modes;
+        if (need_m > h->mode_trace_cap) {
+            if (h->mode_trace) cudaFree(h->mode_trace);
+            h->mode_trace = nullptr; h->mode_trace_cap = 0;
+            CK(h, cudaMalloc(&h->mode_trace, sizeof(double) * need_m));
+            h->mode_trace_cap = need_m;
+        }
+    }
     return PIC_OK;
 }
 
@@ -295,9 +309,15 @@ int launch_resident(pic_handle* h, int n_steps, const double* ext, const double*
     for (int i = 0; i < 4; ++i) { a.c[i] = h->cs[i]; a.d[i] = h->ds[i]; }
     a.n_out = h->n; a.E_out = h->E; a.diag = h->diag; a.trace = n_steps > 0 ? h->trace : nullptr;
     a.rho_out = h->rho[3]; a.err = h->err;
+    a.rw = h->rw; a.tw_cos = h->tw_cos; a.tw_sin = h->tw_sin; a.n_modes = h->n_modes;
+    a.modes = h->n_modes > 0 ? h->modes : nullptr;
+    a.mode_trace = (h->n_modes > 0 && n_steps > 0) ? h->mode_trace : nullptr;
     void* args[] = {&a};
     CK(h, cudaLaunchKernel(resident_kernel(h), dim3(h->n_envs), dim3(h->threads), args, h->smem, h->stream));
     h->launches++;
+    if (a.mode_trace)            // the state's modes = the last row of the per-step record
+        CK(h, cudaMemcpyAsync(h->modes, h->mode_trace + (size_t)(n_steps - 1) * h->n_envs * 2 * h->n_modes,
+                              sizeof(double) * (size_t)h->n_envs * 2 * h->n_modes, cudaMemcpyDeviceToDevice, h->stream));
     return PIC_OK;
 }
 
@@ -312,7 +332,10 @@ int step_device(pic_handle* h, const double* ext, const double* coeffs, int n_st
     for (int s = 0; s < n_steps; ++s) {
         const double* cf = coeffs ? coeffs + (size_t)s * h->n_envs * 2 * h->m : nullptr;
         for (int st = 0; st < 4; ++st) if ((rc = run_stage(h, st, ext, cf, nullptr))) return rc;
-        if ((rc = run_stage(h, 4, nullptr, nullptr, h->trace + (size_t)s * h->n_envs * DIAG_N))) return rc;
+        if ((rc = run_stage(h, 4, nullptr, cf, h->trace + (size_t)s * h->n_envs * DIAG_N))) return rc;
+        if (h->n_modes > 0)
+            CK(h, cudaMemcpyAsync(h->mode_trace + (size_t)s * h->n_envs * 2 * h->n_modes, h->modes,
+                                  sizeof(double) * (size_t)h->n_envs * 2 * h->n_modes, cudaMemcpyDeviceToDevice, h->stream));
     }
     return PIC_OK;
 }
@@ -384,6 +407,7 @@ int pic_create(const pic_config* cfg, pic_handle** out) {
     h->m = cfg->max_mode > 0 ? cfg->max_mode : 0;
     h->ld = (h->N + 15) / 16 * 16;
     yoshida(h->cs, h->ds);
+    h->rw = RewardConst{1.0, 1.0, 1.0, 10.0 * cfg->L * 0.25, cfg->L};      // reward.py defaults: n_actions = 10
 
     MeshConst& mc = h->mc;
     mc.M = h->M; mc.L = cfg->L; mc.dx = cfg->L / cfg->n_mesh; mc.inv_dx = 1.0 / mc.dx; mc.n0 = cfg->n0; mc.dt = cfg->dt;
@@ -404,13 +428,19 @@ int pic_create(const pic_config* cfg, pic_handle** out) {
     h->dep = cfg->deposit == PIC_DEPOSIT_CAS64 ? DEP_CAS64 : DEP_SPLIT32;     // auto: native 32-bit atomics
     if (h->f32) h->dep = DEP_SPLIT32;
     int mode = cfg->mode;
-    if (mode == PIC_MODE_AUTO) mode = h->N <= resident_capacity(h->f32) ? PIC_MODE_RESIDENT : PIC_MODE_STREAMING;
+    // resident = the whole env (particles + mesh tables) fits the shared memory of one CTA
+    const size_t res512 = h->f32 ? resident_smem_bytes<float>(h->M, 512, h->N) : resident_smem_bytes<double>(h->M, 512, h->N);
+    const size_t res1024 = h->f32 ? resident_smem_bytes<float>(h->M, 1024, h->N) : resident_smem_bytes<double>(h->M, 1024, h->N);
+    if (mode == PIC_MODE_AUTO) mode = (long long)res1024 <= (long long)h->max_smem ? PIC_MODE_RESIDENT : PIC_MODE_STREAMING;
     h->resident = mode == PIC_MODE_RESIDENT;
     if (h->resident) {
-        if (!resident_pick_shape(h->N, h->f32, &h->threads, &h->per_thread)) {
+        if ((long long)res1024 > (long long)h->max_smem) {
             delete h;
-            return fail(nullptr, PIC_EUNSUPPORTED, "n_particles too large for resident mode");
+            return fail(nullptr, PIC_EUNSUPPORTED, "n_particles too large for resident mode (env does not fit in shared memory)");
         }
+        // two 512-thread CTAs per SM when two envs fit side by side (measured best), else one 1024-thread CTA
+        h->threads = 2 * (res512 + 1024) <= (size_t)h->max_smem + 1024 ? 512 : 1024;
+        h->per_thread = 0;
     } else {
         h->threads = 1024; h->per_thread = 2;       // measured best: 1024 threads x 2 vectors in flight, 1 CTA per SM
     }
@@ -445,7 +475,8 @@ int pic_destroy(pic_handle* h) {
     cudaStreamSynchronize(h->stream);
     if (h->own_comm && h->comm && nccl_api().destroy) nccl_api().destroy(h->comm);
     void* bufs[] = {h->x, h->v, h->rho[0], h->rho[1], h->rho[2], h->rho[3], h->n, h->E, h->diag, h->vsum, h->partial,
-                    h->ext, h->coeffs, h->bcos, h->bsin, h->trace, h->stage64, h->err};
+                    h->ext, h->coeffs, h->bcos, h->bsin, h->trace, h->stage64, h->err, h->tw_cos, h->tw_sin, h->modes,
+                    h->mode_trace};
     for (void* b : bufs) if (b) cudaFree(b);
     delete h;
     return PIC_OK;
@@ -462,12 +493,8 @@ int pic_set_tuning(pic_handle* h, int32_t threads, int32_t per_thread, int32_t c
     if (!h) return PIC_EINVAL;
     int t0 = h->threads, p0 = h->per_thread, c0 = h->ctas_per_sm;
     if (threads > 0) h->threads = threads;
-    if (per_thread > 0) h->per_thread = per_thread;
+    if (per_thread > 0 && !h->resident) h->per_thread = per_thread;
     if (ctas_per_sm >= 0) h->ctas_per_sm = ctas_per_sm;
-    if (h->resident && (long long)h->threads * h->per_thread < h->N) {
-        h->threads = t0; h->per_thread = p0; h->ctas_per_sm = c0;
-        return fail(h, PIC_EINVAL, "threads * per_thread must cover n_particles in resident mode");
-    }
     cudaStreamSynchronize(h->stream);
     int rc = configure_launch(h);
     if (rc) { h->threads = t0; h->per_thread = p0; h->ctas_per_sm = c0; configure_launch(h); }
@@ -667,6 +694,59 @@ int pic_step_coeffs(pic_handle* h, const double* coeffs, int32_t n_steps) {
     }
     CK(h, cudaMemcpyAsync(h->coeffs, coeffs, sizeof(double) * need, cudaMemcpyHostToDevice, h->stream));
     return step_device(h, nullptr, h->coeffs, n_steps);
+}
+
+int pic_set_reward(pic_handle* h, double alpha, double beta, double r_pe_n, double r_ie_n) {
+    if (!h) return PIC_EINVAL;
+    if (!(r_pe_n > 0) || !(r_ie_n > 0)) return fail(h, PIC_EINVAL, "reward normalisations must be positive");
+    h->rw.alpha = alpha; h->rw.beta = beta; h->rw.r_pe_n = r_pe_n; h->rw.r_ie_n = r_ie_n;
+    return PIC_OK;
+}
+
+int pic_enable_modes(pic_handle* h, int32_t n_modes) {
+    if (!h) return PIC_EINVAL;
+    if (n_modes < 0 || n_modes > MAX_MODES || n_modes >= h->M / 2)
+        return fail(h, PIC_EINVAL, "n_modes must be in 0.." + std::to_string(MAX_MODES) + " and below N_mesh/2");
+    CK(h, cudaSetDevice(h->device));
+    CK(h, cudaStreamSynchronize(h->stream));
+    for (double** b : {&h->tw_cos, &h->tw_sin, &h->modes}) { if (*b) cudaFree(*b); *b = nullptr; }
+    h->n_modes = n_modes;
+    if (n_modes == 0) return PIC_OK;
+    std::vector<double> c((size_t)h->M * n_modes), s((size_t)h->M * n_modes);
+    for (int j = 0; j < h->M; ++j)
+        for (int k = 0; k < n_modes; ++k) {
+            // exact argument reduction: (j * (k+1)) mod M keeps the angle in [0, 2 pi)
+            const long long jk = ((long long)j * (k + 1)) % h->M;
+            const double th = 2.0 * 3.14159265358979323846 * (double)jk / (double)h->M;
+            c[(size_t)j * n_modes + k] = cos(th); s[(size_t)j * n_modes + k] = sin(th);
+        }
+    size_t b = sizeof(double) * (size_t)h->M * n_modes;
+    CK(h, cudaMalloc(&h->tw_cos, b)); CK(h, cudaMalloc(&h->tw_sin, b));
+    CK(h, cudaMalloc(&h->modes, sizeof(double) * (size_t)h->n_envs * 2 * n_modes));
+    CK(h, cudaMemcpy(h->tw_cos, c.data(), b, cudaMemcpyHostToDevice));
+    CK(h, cudaMemcpy(h->tw_sin, s.data(), b, cudaMemcpyHostToDevice));
+    CK(h, cudaMemset(h->modes, 0, sizeof(double) * (size_t)h->n_envs * 2 * n_modes));
+    if (h->have_state) return init_fields(h);          // refresh so that the modes of the current state exist
+    return PIC_OK;
+}
+
+int pic_get_modes(pic_handle* h, double* modes) {
+    if (!h || !modes) return PIC_EINVAL;
+    if (h->n_modes < 1) return fail(h, PIC_ESTATE, "pic_enable_modes has not been called");
+    if (!h->have_state) return fail(h, PIC_ESTATE, "no state");
+    CK(h, cudaMemcpyAsync(modes, h->modes, sizeof(double) * (size_t)h->n_envs * 2 * h->n_modes, cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));
+    return PIC_OK;
+}
+
+int pic_get_mode_trace(pic_handle* h, double* out, int32_t n_steps) {
+    if (!h || !out) return PIC_EINVAL;
+    if (h->n_modes < 1) return fail(h, PIC_ESTATE, "pic_enable_modes has not been called");
+    if (n_steps < 1 || n_steps > h->trace_steps) return fail(h, PIC_EINVAL, "n_steps exceeds the last call's step count");
+    CK(h, cudaMemcpyAsync(out, h->mode_trace, sizeof(double) * (size_t)n_steps * h->n_envs * 2 * h->n_modes,
+                          cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));
+    return PIC_OK;
 }
 
 int pic_sync(pic_handle* h) {

@@ -25,7 +25,32 @@ constexpr int DIAG_KE = 0;        // 0.5 * sum v^2            (src/env/util.py:1
 constexpr int DIAG_PE_MESH = 1;   // 0.5 * sum E_mesh^2 * dx  (src/control/objective.py:31)
 constexpr int DIAG_SUM_V = 2;     // sum v (momentum)
 constexpr int DIAG_SUM_E2 = 3;    // sum E_mesh^2
-constexpr int DIAG_N = 4;
+constexpr int DIAG_REWARD = 4;    // reward of the transition that produced this state (src/control/rl/reward.py:71-76)
+constexpr int DIAG_INPUT_E = 5;   // sum(a^2) * L / 4 of the action applied (reward.py:52-54)
+constexpr int DIAG_N = 6;
+constexpr int MAX_MODES = 8;      // Fourier modes of E_mesh emitted per step (spectrum.py:17)
+
+// Reward.compute_reward (reward.py:71-76): alpha * max(1 - PE_mesh(s_t)/r_pe_n, 0) + beta * max(1 - IE(a_t)/r_ie_n, 0)
+struct RewardConst { double alpha, beta, r_pe_n, r_ie_n, L; };
+
+__device__ __forceinline__ double input_energy(const double* __restrict__ coeff, int two_m, double L) {
+    double s = 0.0;
+    for (int k = 0; k < two_m; ++k) s += coeff[k] * coeff[k];
+    return s * L * 0.25;
+}
+__device__ __forceinline__ double reward_of(const RewardConst& rc, double pe_pre, double ie) {
+    const double r_pe = fmax(1.0 - pe_pre / rc.r_pe_n, 0.0), r_ie = fmax(1.0 - ie / rc.r_ie_n, 0.0);
+    return r_pe * rc.alpha + r_ie * rc.beta;
+}
+
+// Optional spectral read-out of the self-consistent field: E_k = fft(E_mesh)[k] / N_mesh * 2 for k = 1..m
+// (src/interpret/spectrum.py:17; what run_feedback.py and the behaviour-cloning target of ddpg.py:429-431 use).
+struct ModeOut {
+    const double* tw_cos;   // [M][m] cos(2 pi j k / M)
+    const double* tw_sin;   // [M][m]
+    double* out;            // [2m]: Re_1..Re_m, Im_1..Im_m for this env, or nullptr
+    int m;
+};
 
 constexpr unsigned ERR_INDEX_RANGE = 1u;   // floor(x/dx) fell outside [0, N_mesh) (the reference would raise in np.bincount)
 constexpr unsigned ERR_NONFINITE = 2u;     // non-finite position reached the deposit
@@ -364,6 +389,7 @@ struct ExtSrc {
 //   ext      : external field source added to what particles see (util.py:102-103)
 //   n_out/E_out : nullptr or global outputs of the density (interpolate.py:18) / self-consistent field
 //   x1, x2   : two per-thread values summed over the block on the way (kinetic sums)
+//   modes    : optional Fourier read-out of the self-consistent field (written by warp 0 after barrier C)
 // Returns {sum_j E_j^2 (self-consistent field), sum x1, sum x2}; valid in warp 0 only.
 struct FieldTotals { double e2, s1, s2; };
 
@@ -372,8 +398,8 @@ template <int THREADS> struct FieldShape {
     static constexpr int NWF = FT / 32, NW = THREADS / 32;
 };
 template <int THREADS>
-__host__ __device__ constexpr int field_scratch_doubles_t() { return 3 * FieldShape<THREADS>::NWF + 3 * FieldShape<THREADS>::NW; }
-__host__ __device__ constexpr int field_scratch_doubles(int threads) { return 3 * ((threads < 256 ? threads : 256) / 32) + 3 * (threads / 32); }
+__host__ __device__ constexpr int field_scratch_doubles_t() { return (3 + 2 * MAX_MODES) * FieldShape<THREADS>::NWF + 3 * FieldShape<THREADS>::NW; }
+__host__ __device__ constexpr int field_scratch_doubles(int threads) { return (3 + 2 * MAX_MODES) * ((threads < 256 ? threads : 256) / 32) + 3 * (threads / 32); }
 
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
@@ -385,14 +411,16 @@ template <typename R, int THREADS, typename RhoLoad, typename IdleWork>
 __device__ __forceinline__ FieldTotals block_field(RhoLoad rho, typename PairT<R>::type* E_s, double* D_s, double* red,
                                                    const MeshConst& mc, const ExtSrc& ext, double* __restrict__ n_out,
                                                    double* __restrict__ E_out, double x1, double x2,
-                                                   IdleWork idle_work) {
+                                                   IdleWork idle_work, const ModeOut modes = ModeOut{nullptr, nullptr, nullptr, 0}) {
     constexpr int FT = FieldShape<THREADS>::FT, NWF = FieldShape<THREADS>::NWF, NW = FieldShape<THREADS>::NW;
     const int M = mc.M, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const bool field_thread = tid < FT;
     const int cpt = (M + FT - 1) / FT;
     const int j0 = tid * cpt, j1 = min(M, j0 + cpt);
     double* red2 = red + 3 * NWF;
+    double* red3 = red2 + 3 * NW;                       // [NWF][2 * MAX_MODES] mode partials
     const bool has_ext = ext.any();
+    const bool want_modes = modes.out != nullptr;
 
     double run = 0.0, excl = 0.0;
     if (field_thread) {
@@ -439,9 +467,21 @@ __device__ __forceinline__ FieldTotals block_field(RhoLoad rho, typename PairT<R
             prevS = S;
             if (E_out) E_out[j] = E;
             e2 += E * E;
+            if (want_modes) D_s[j] = E;                 // S_j is dead from here on; keep E_j for the read-out below
             const double Et = has_ext ? E + ext.at(j) : E;
             E_s[j].x = (R)Et;
             E_s[jm].y = (R)Et;
+        }
+        if (want_modes) {                               // cold: one mode at a time keeps the register footprint small
+            for (int k = 0; k < modes.m; ++k) {
+                double re = 0.0, im = 0.0;
+                for (int j = j0; j < j1; ++j) {
+                    re += D_s[j] * modes.tw_cos[j * modes.m + k];
+                    im -= D_s[j] * modes.tw_sin[j * modes.m + k];
+                }
+                re = warp_sum(re); im = warp_sum(im);
+                if (lane == 0) { red3[w * 2 * MAX_MODES + k] = re; red3[w * 2 * MAX_MODES + MAX_MODES + k] = im; }
+            }
         }
     } else {
         idle_work();
@@ -456,6 +496,14 @@ __device__ __forceinline__ FieldTotals block_field(RhoLoad rho, typename PairT<R
         t.e2 = warp_sum(lane < NW ? red2[3 * lane] : 0.0);
         t.s1 = warp_sum(lane < NW ? red2[3 * lane + 1] : 0.0);
         t.s2 = warp_sum(lane < NW ? red2[3 * lane + 2] : 0.0);
+        if (want_modes && lane < 2 * modes.m) {         // lane < m: Re_{lane+1}; m <= lane < 2m: Im_{lane-m+1}
+            const int k = lane < modes.m ? lane : lane - modes.m;
+            const int slot = lane < modes.m ? k : MAX_MODES + k;
+            double acc = 0.0;
+#pragma unroll
+            for (int ww = 0; ww < NWF; ++ww) acc += red3[ww * 2 * MAX_MODES + slot];
+            modes.out[lane] = acc / (double)M * 2.0;
+        }
     }
     return t;
 }

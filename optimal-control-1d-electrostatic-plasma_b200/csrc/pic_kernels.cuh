@@ -6,8 +6,8 @@
 //                        Poisson launch), gathers/kicks/drifts, and deposits into a shared-memory privatised
 //                        histogram that is flushed with 64-bit global reductions.
 //   env_step_resident_kernel
-//                        small-N / batched mode: one CTA per env, particles live in registers for the whole launch,
-//                        all four sub-stages (and any number of env steps) run inside one launch.
+//                        small-N / batched mode: one CTA per env, particles live in shared memory for the whole
+//                        launch, all four sub-stages (and any number of env steps) run inside one launch.
 //   field_finalize_kernel
 //                        state field after a streaming step: density, self-consistent E, energies.
 #pragma once
@@ -188,6 +188,12 @@ __global__ void __launch_bounds__(THREADS) push_stream_kernel(const StreamArgs a
 // ----------------------------------------------------------------- finalize
 struct FinalizeArgs {
     MeshConst mc;
+    RewardConst rw;
+    const double* coeffs;              // [n_envs][2m] action applied in this step, or nullptr
+    int two_m;
+    const double* tw_cos; const double* tw_sin; int n_modes;   // spectral read-out tables ([M][n_modes]) or nullptr
+    double* modes;                     // [n_envs][2 n_modes] or nullptr
+    int step_done;                     // 1: this finalize closes an env step (emit reward), 0: initial state
     const unsigned long long* rho;     // [n_envs][M] state density (fixed point)
     unsigned long long* rho_zero;      // [n_envs][M] or nullptr
     double* n_out;                     // [n_envs][M]
@@ -210,11 +216,19 @@ __global__ void __launch_bounds__(THREADS) field_finalize_kernel(const FinalizeA
         const double* p = a.partial + (size_t)env * a.n_partial * 2;
         for (int i = tid; i < a.n_partial; i += THREADS) { s2 += p[2 * i]; s1 += p[2 * i + 1]; }
     }
+    const ModeOut mo{a.tw_cos, a.tw_sin, a.modes ? a.modes + (size_t)env * 2 * a.n_modes : nullptr, a.n_modes};
     const FieldTotals t = block_field<double, THREADS>(rho, sm.E_s, sm.D_s, sm.red, a.mc, none,
-                                                       a.n_out + (size_t)env * M, a.E_out + (size_t)env * M, s2, s1, [] {});
+                                                       a.n_out + (size_t)env * M, a.E_out + (size_t)env * M, s2, s1, [] {}, mo);
     if (a.rho_zero) for (int j = tid; j < M; j += THREADS) a.rho_zero[(size_t)env * M + j] = 0ull;
     if (tid == 0) {
         double* d = a.diag + (size_t)env * DIAG_N;
+        if (a.step_done) {                             // reward of this transition: field energy of the PRE-step state
+            const double ie = a.coeffs ? input_energy(a.coeffs + (size_t)env * a.two_m, a.two_m, a.rw.L) : 0.0;
+            d[DIAG_REWARD] = reward_of(a.rw, d[DIAG_PE_MESH], ie);
+            d[DIAG_INPUT_E] = ie;
+        } else {
+            d[DIAG_REWARD] = 0.0; d[DIAG_INPUT_E] = 0.0;
+        }
         d[DIAG_PE_MESH] = 0.5 * t.e2 * a.mc.dx;
         d[DIAG_SUM_E2] = t.e2;
         if (a.partial) {
@@ -227,6 +241,10 @@ __global__ void __launch_bounds__(THREADS) field_finalize_kernel(const FinalizeA
 // ----------------------------------------------------------------- resident
 struct ResidentArgs {
     MeshConst mc;
+    RewardConst rw;
+    const double* tw_cos; const double* tw_sin; int n_modes;   // spectral read-out tables or nullptr
+    double* modes;                     // [n_envs][2 n_modes] after the last step, or nullptr
+    double* mode_trace;                // nullptr or [n_steps][n_envs][2 n_modes]
     void* x; void* v;                  // [n_envs][ld]
     long long N, ld;
     int n_steps;                       // 0 => init only (wrap + deposit + field)
@@ -242,24 +260,28 @@ struct ResidentArgs {
     unsigned* err;
 };
 
-template <typename R, int THREADS, int PPT, int DEP, bool EXACT_W>
+// One CTA per env; the particle state of the env lives in SHARED memory for the whole launch (any number of env
+// steps): a run-time loop over the particles (any N that fits), two conflict-free 8-byte loads and stores per
+// particle and sub-stage on top of the random gather / atomics.  (A register-resident variant was measured 1.4x
+// slower: 64 registers per thread at 1024 threads spill, and at 512 threads only one CTA fits per SM, so nothing
+// overlaps the barriers of the field solve.  With the state in shared memory two 512-thread CTAs share an SM.)
+template <typename R>
+__host__ __device__ constexpr size_t resident_smem_bytes(int M, int threads, long long n) {
+    return smem_plan_bytes<R>(M, threads, true) + (size_t)((n + 1) / 2 * 2) * 2 * sizeof(R);
+}
+
+template <typename R, int THREADS, int DEP, bool EXACT_W>
 __global__ void __launch_bounds__(THREADS) env_step_resident_kernel(const ResidentArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int tid = threadIdx.x, env = blockIdx.x, M = a.mc.M;
+    const int tid = threadIdx.x, env = blockIdx.x, M = a.mc.M, N = (int)a.N;
     SmemLayout<R> sm(smem_raw, M, true);
+    R* x_s = (R*)(smem_raw + smem_plan_bytes<R>(M, THREADS, true));
+    R* v_s = x_s + (N + 1) / 2 * 2;
     Hist<DEP> hist; hist.init(sm.hist, M);
     const PartConst<R> pc = make_part_const<R>(a.mc);
     R* xe = (R*)a.x + (size_t)env * a.ld;
     R* ve = (R*)a.v + (size_t)env * a.ld;
-    const int N = (int)a.N;
-
-    R xs[PPT], vs[PPT];
-#pragma unroll
-    for (int j = 0; j < PPT; ++j) {
-        int i = j * THREADS + tid;
-        xs[j] = i < N ? xe[i] : (R)0;
-        vs[j] = i < N ? ve[i] : (R)0;
-    }
+    for (int i = tid; i < N; i += THREADS) { x_s[i] = xe[i]; v_s[i] = ve[i]; }
     hist.zero(tid, THREADS);
     __syncthreads();
     unsigned err = 0;
@@ -267,18 +289,27 @@ __global__ void __launch_bounds__(THREADS) env_step_resident_kernel(const Reside
     double* n_out = a.n_out + (size_t)env * M;
     double* E_out = a.E_out + (size_t)env * M;
     const ExtSrc none{nullptr, nullptr, nullptr, nullptr, 0};
-
+    constexpr int FT = FieldShape<THREADS>::FT;
+    auto clear_hist = [&]() {
+        if (FT == THREADS) hist.zero(tid, THREADS);
+        else hist.zero(tid - FT, THREADS - FT);
+    };
     auto kinetic = [&](double& s2, double& s1) {
         s2 = 0.0; s1 = 0.0;
-#pragma unroll
-        for (int j = 0; j < PPT; ++j) {       // padded particles carry v == 0
-            s2 += (double)vs[j] * (double)vs[j]; s1 += (double)vs[j];
-        }
+        for (int i = tid; i < N; i += THREADS) { const double vj = (double)v_s[i]; s2 += vj * vj; s1 += vj; }
     };
-    auto write_diag = [&](const FieldTotals& t, int step) {      // totals are valid in warp 0
+    double pe_pre = 0.0;
+    if (tid == 0 && a.n_steps > 0) pe_pre = a.diag[(size_t)env * DIAG_N + DIAG_PE_MESH];
+    auto write_diag = [&](const FieldTotals& t, int step, const double* coeff) {
         if (tid == 0) {
             double rec[DIAG_N];
             rec[DIAG_KE] = 0.5 * t.s1; rec[DIAG_PE_MESH] = 0.5 * t.e2 * a.mc.dx; rec[DIAG_SUM_V] = t.s2; rec[DIAG_SUM_E2] = t.e2;
+            rec[DIAG_REWARD] = 0.0; rec[DIAG_INPUT_E] = 0.0;
+            if (step >= 0) {
+                rec[DIAG_INPUT_E] = coeff ? input_energy(coeff, 2 * a.act.m, a.rw.L) : 0.0;
+                rec[DIAG_REWARD] = reward_of(a.rw, pe_pre, rec[DIAG_INPUT_E]);
+                pe_pre = rec[DIAG_PE_MESH];
+            }
             double* d = a.diag + (size_t)env * DIAG_N;
 #pragma unroll
             for (int k = 0; k < DIAG_N; ++k) d[k] = rec[k];
@@ -292,24 +323,20 @@ __global__ void __launch_bounds__(THREADS) env_step_resident_kernel(const Reside
     auto dump_rho = [&]() {
         if (a.rho_out) for (int j = tid; j < M; j += THREADS) a.rho_out[(size_t)env * M + j] = rho(j);
     };
-    // the threads that do not take part in the field solve clear the histogram for the next sub-stage meanwhile
-    constexpr int FT = FieldShape<THREADS>::FT;
-    auto clear_hist = [&]() {
-        if (FT == THREADS) hist.zero(tid, THREADS);
-        else hist.zero(tid - FT, THREADS - FT);
-    };
 
-    if (a.n_steps == 0) {                                         // pic.py:76-77 on a fresh state
-#pragma unroll
-        for (int j = 0; j < PPT; ++j) {
-            if (j * THREADS + tid < N)
-                particle_substage<R, false, false, EXACT_W, false>(xs[j], vs[j], hist, sm.E_s, (R)0, (R)0, pc, a.mc, true, err);
+    if (a.n_steps == 0) {
+        for (int i = tid; i < N; i += THREADS) {
+            R x = x_s[i], v = v_s[i];
+            particle_substage<R, false, false, EXACT_W, false>(x, v, hist, sm.E_s, (R)0, (R)0, pc, a.mc, true, err);
+            x_s[i] = x;
         }
         __syncthreads();
         dump_rho();
         double s2, s1;
         kinetic(s2, s1);
-        write_diag(block_field<R, THREADS>(rho, sm.E_s, sm.D_s, sm.red, a.mc, none, n_out, E_out, s2, s1, clear_hist), -1);
+        const ModeOut mo{a.tw_cos, a.tw_sin, a.modes ? a.modes + (size_t)env * 2 * a.n_modes : nullptr, a.n_modes};
+        write_diag(block_field<R, THREADS>(rho, sm.E_s, sm.D_s, sm.red, a.mc, none, n_out, E_out, s2, s1, clear_hist, mo),
+                   -1, nullptr);
     }
 
     for (int step = 0; step < a.n_steps; ++step) {
@@ -318,18 +345,26 @@ __global__ void __launch_bounds__(THREADS) env_step_resident_kernel(const Reside
         if (act.ext) act.ext += (size_t)step * a.ext_step_stride;
         const ExtSrc ext = stage_ext(act, env, M);
         const bool last = step == a.n_steps - 1;
+        {                                                           // stage 0: drift only (integration.py:71)
+            const R cc = (R)a.c[0];
+#pragma unroll 2
+            for (int i = tid; i < N; i += THREADS) {
+                R x = x_s[i], v = v_s[i];
+                particle_substage<R, false, true, EXACT_W, false>(x, v, hist, sm.E_s, cc, (R)0, pc, a.mc, false, err);
+                x_s[i] = x;
+            }
+            __syncthreads();
+            block_field<R, THREADS>(rho, sm.E_s, sm.D_s, sm.red, a.mc, ext, nullptr, nullptr, 0.0, 0.0, clear_hist);
+        }
 #pragma unroll 1
-        for (int st = 0; st < 4; ++st) {
+        for (int st = 1; st < 4; ++st) {
             const R cc = (R)a.c[st], dd = (R)a.d[st];
             const bool fin = st == 3;
-#pragma unroll
-            for (int j = 0; j < PPT; ++j) {
-                if (j * THREADS + tid < N) {
-                    if (st == 0)
-                        particle_substage<R, false, true, EXACT_W, false>(xs[j], vs[j], hist, sm.E_s, cc, dd, pc, a.mc, false, err);
-                    else                                           // fin: state wrap of pic.py:139
-                        particle_substage<R, true, true, EXACT_W, false>(xs[j], vs[j], hist, sm.E_s, cc, dd, pc, a.mc, fin, err);
-                }
+#pragma unroll 2
+            for (int i = tid; i < N; i += THREADS) {
+                R x = x_s[i], v = v_s[i];
+                particle_substage<R, true, true, EXACT_W, false>(x, v, hist, sm.E_s, cc, dd, pc, a.mc, fin, err);
+                x_s[i] = x; v_s[i] = v;
             }
             __syncthreads();
             if (!fin) {
@@ -338,17 +373,18 @@ __global__ void __launch_bounds__(THREADS) env_step_resident_kernel(const Reside
                 if (last) dump_rho();
                 double s2, s1;
                 kinetic(s2, s1);
+                double* mout = nullptr;
+                if (a.n_modes > 0) {
+                    if (a.mode_trace) mout = a.mode_trace + ((size_t)step * gridDim.x + env) * 2 * a.n_modes;
+                    else if (last && a.modes) mout = a.modes + (size_t)env * 2 * a.n_modes;
+                }
+                const ModeOut mo{a.tw_cos, a.tw_sin, mout, a.n_modes};
                 write_diag(block_field<R, THREADS>(rho, sm.E_s, sm.D_s, sm.red, a.mc, none, last ? n_out : nullptr,
-                                                   last ? E_out : nullptr, s2, s1, clear_hist), step);
+                                                   last ? E_out : nullptr, s2, s1, clear_hist, mo), step, ext.coeff);
             }
         }
     }
-
-#pragma unroll
-    for (int j = 0; j < PPT; ++j) {
-        int i = j * THREADS + tid;
-        if (i < N) { xe[i] = xs[j]; ve[i] = vs[j]; }
-    }
+    for (int i = tid; i < N; i += THREADS) { xe[i] = x_s[i]; ve[i] = v_s[i]; }
     if (err) atomicOr(a.err, err);
 }
 

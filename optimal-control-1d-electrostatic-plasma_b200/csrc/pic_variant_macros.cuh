@@ -11,7 +11,7 @@
     PIC_S_CASE(R, T, U, pic::MODE_FINAL, DP, EX) PIC_S_CASE(R, T, U, pic::MODE_INIT, DP, EX)
 #define PIC_S_DEPS(R, T, U, EX) PIC_S_MODES(R, T, U, pic::DEP_CAS64, EX) PIC_S_MODES(R, T, U, pic::DEP_SPLIT32, EX)
 
-#define PIC_R_CASE(R, T, P, DP, EX) \
-    if (threads == T && ppt == P && dep == DP && exact_w == EX) \
-        return (const void*)&pic::env_step_resident_kernel<R, T, P, DP, EX>;
-#define PIC_R_DEPS(R, T, P, EX) PIC_R_CASE(R, T, P, pic::DEP_CAS64, EX) PIC_R_CASE(R, T, P, pic::DEP_SPLIT32, EX)
+#define PIC_R_CASE(R, T, DP, EX) \
+    if (threads == T && dep == DP && exact_w == EX) \
+        return (const void*)&pic::env_step_resident_kernel<R, T, DP, EX>;
+#define PIC_R_DEPS(R, T, EX) PIC_R_CASE(R, T, pic::DEP_CAS64, EX) PIC_R_CASE(R, T, pic::DEP_SPLIT32, EX)

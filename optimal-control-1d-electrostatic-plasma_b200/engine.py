@@ -49,6 +49,8 @@ class Engine:
         self.N, self.M, self.n_envs, self.m = int(n_particles), int(n_mesh), int(n_envs), int(max_mode)
         self.precision = "f32" if _PREC[precision] == L.PIC_F32 else "f64"
         self.device = int(device)
+        self.L = float(L_box)
+        self.n_modes = 0
 
     # ---- lifetime
     def close(self):
@@ -145,6 +147,27 @@ class Engine:
 
     def step_coeffs_device(self, dev_ptr, n_steps=1):
         self._ck(self._lib.pic_step_coeffs_device(self._h, C.c_void_p(dev_ptr), int(n_steps)))
+
+    def set_reward(self, alpha=1.0, beta=1.0, r_pe_n=1.0, r_ie_n=None, n_actions=10):
+        """Reward constants of src/control/rl/reward.py (r_ie_n defaults to n_actions * L / 4, reward.py:33)."""
+        if r_ie_n is None:
+            r_ie_n = float(n_actions) * self.L * 0.25
+        self._ck(self._lib.pic_set_reward(self._h, float(alpha), float(beta), float(r_pe_n), float(r_ie_n)))
+
+    def enable_modes(self, n_modes):
+        self._ck(self._lib.pic_enable_modes(self._h, int(n_modes)))
+        self.n_modes = int(n_modes)
+
+    def get_modes(self):
+        """(n_envs, 2m): Re_1..Re_m, Im_1..Im_m of fft(E_mesh)/N_mesh*2 (spectrum.py:17) for the current state."""
+        out = np.empty((self.n_envs, 2 * self.n_modes))
+        self._ck(self._lib.pic_get_modes(self._h, _ptr(out)))
+        return out
+
+    def get_mode_trace(self, n_steps):
+        out = np.empty((n_steps, self.n_envs, 2 * self.n_modes))
+        self._ck(self._lib.pic_get_mode_trace(self._h, _ptr(out), int(n_steps)))
+        return out
 
     def sync(self):
         self._ck(self._lib.pic_sync(self._h))

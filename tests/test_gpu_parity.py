@@ -28,8 +28,8 @@ def test_wrap_index_deposit_edge_cases(golden, cfg, LM):
     key = f"L{L:g}_M{M}"
     x = g[key + "_x"]
     N = x.shape[0]
-    if cfg["mode"] == "resident" and N > 10240:
-        pytest.skip("more particles than one CTA keeps in registers")
+    if cfg["mode"] == "resident" and M >= 4096:
+        pytest.skip("16310 particles + a 4096-cell mesh do not fit one CTA's shared memory")
     eng = _engine(N, M, L, 0.01, **cfg)
     eng.set_state(x[None], np.zeros((1, N)))
     xs, _ = eng.get_state()
@@ -154,8 +154,11 @@ def test_bitwise_reproducibility_across_kernels(golden):
     N, M, L, dt = int(g["N"]), int(g["N_mesh"]), float(g["L"]), float(g["dt"])
     outs = []
     variants = [dict(mode="resident", deposit="cas64"), dict(mode="resident", deposit="split32"),
-                dict(mode="streaming", deposit="cas64"), dict(mode="streaming", deposit="split32")]
-    tunings = [None, None, (512, 1, 1), (256, 4, 2)]
+                dict(mode="streaming", deposit="cas64"), dict(mode="streaming", deposit="split32"),
+                dict(mode="resident", deposit="split32"), dict(mode="resident", deposit="cas64"),
+                dict(mode="resident", deposit="split32")]
+    # (threads, unroll [streaming only], ctas per SM)
+    tunings = [None, None, (512, 1, 1), (256, 4, 2), (1024, 0, -1), (256, 0, -1), (512, 0, -1)]
     for cfg, tune in zip(variants, tunings):
         eng = _engine(N, M, L, dt, **cfg)
         if tune:
@@ -251,3 +254,32 @@ def test_pic_class_is_a_drop_in(golden):
     assert np.abs(sim.E_mesh[:, 0] - g["t10_E_mesh"]).max() < 1e-12
     with pytest.raises(NotImplementedError):
         PIC(N=100, N_mesh=10, interpol="TSC", init_dist=dist)
+
+
+@pytest.mark.parametrize("mode", ["resident", "streaming"])
+def test_device_reward_and_spectral_modes(golden, mode):
+    """Reward.compute_reward (reward.py:71-76) and the first Fourier modes of E_mesh
+    (spectrum.py:17: fft/N_mesh*2) come out of the step kernels."""
+    g = golden("bump_vb3_randctrl")
+    N, M, L, dt, m, steps = int(g["N"]), int(g["N_mesh"]), float(g["L"]), float(g["dt"]), 3, 60
+    eng = _engine(N, M, L, dt, mode=mode, max_mode=m)
+    eng.set_actuator_basis(g["basis_cos"], g["basis_sin"])
+    eng.enable_modes(m)
+    eng.set_state(g["t0_x"][None], g["t0_v"][None])
+    Ek0 = np.fft.fft(g["t0_E_mesh"]) / M * 2.0
+    m0 = eng.get_modes()[0]
+    assert np.abs(m0[:m] - Ek0[1:m + 1].real).max() < 1e-12 and np.abs(m0[m:] - Ek0[1:m + 1].imag).max() < 1e-12
+    eng.step_coeffs(g["coeffs"][:steps, None, :], steps)
+    tr = eng.get_trace(steps)[:, 0, :]
+    assert np.max(np.abs(tr[:, 4] - g["rewards"][:steps])) < 1e-9                       # reward on the PRE-step state
+    ie = np.sum(g["coeffs"][:steps] ** 2, axis=1) * L * 0.25
+    assert np.max(np.abs(tr[:, 5] - ie)) < 1e-12
+    mt = eng.get_mode_trace(steps)[:, 0, :]
+    _, E = eng.get_fields()
+    Ek = np.fft.fft(E[0]) / M * 2.0
+    assert np.abs(mt[-1, :m] - Ek[1:m + 1].real).max() < 1e-12 and np.abs(mt[-1, m:] - Ek[1:m + 1].imag).max() < 1e-12
+    assert np.array_equal(eng.get_modes()[0], mt[-1])
+    # mesh-vector control carries no coefficients: input-energy term is zero, reward = r_pe + beta
+    eng.step_mesh(g["E_ext"][0][None], 1)
+    d = eng.get_diag()[0]
+    assert d[5] == 0.0 and abs(d[4] - (max(1 - tr[-1, 1], 0) + 1.0)) < 1e-12

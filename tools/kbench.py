@@ -72,10 +72,9 @@ def main():
             idx = torch.argsort(torch.floor(x0 / (L / a.mesh)))
             orders.append(("sorted", x0[idx].contiguous(), v0[idx].contiguous()))
             del idx
-        shapes = [(256, 2, 0), (256, 1, 0), (256, 4, 0), (512, 1, 0), (512, 2, 0), (512, 4, 0), (1024, 1, 0), (1024, 2, 0),
-                  (256, 2, 2), (256, 2, 1), (512, 2, 1)]
+        shapes = [(512, 2, 0), (512, 4, 0), (768, 2, 0), (1024, 1, 0), (1024, 2, 0), (1024, 4, 0)]
         if a.quick:
-            shapes = [(256, 2, 0), (512, 2, 0), (1024, 1, 0)]
+            shapes = [(512, 2, 0), (1024, 1, 0), (1024, 2, 0)]
         for prec in a.precisions.split(","):
             for oname, xs, vs in orders:
                 for dep in ("cas64", "split32"):
@@ -85,7 +84,7 @@ def main():
                     else:
                         xin, vin = xs, vs
                     for (th, un, occ) in shapes:
-                        if prec == "f32" and (th, un) not in [(256, 1), (256, 2), (512, 2)]:
+                        if prec == "f32" and (th, un) not in [(512, 2), (1024, 1), (1024, 2)]:
                             continue
                         try:
                             eng.set_tuning(th, un, occ)
@@ -119,7 +118,7 @@ def main():
                 eng = pic_b200.Engine(N, M, L, 0.05, n_envs=B, mode="resident", deposit=dep, max_mode=3, precision=prec)
                 eng.set_actuator_basis(act.basis_cos, act.basis_sin)
                 cdev = torch.as_tensor(coeffs, device="cuda")
-                shapes = [(256, 20), (128, 40), (512, 10), (1024, 5)] if prec == "f64" else [(256, 20)]
+                shapes = [(256, 0), (512, 0), (1024, 0)]
                 for (th, ppt) in shapes:
                     try:
                         eng.set_tuning(th, ppt, -1)

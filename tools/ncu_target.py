@@ -26,8 +26,8 @@ if which == "stream":
     print("stream ok", eng.launch_info(), eng.get_diag())
 else:
     B = int(sys.argv[2]) if len(sys.argv) > 2 else 1184
-    th = int(sys.argv[3]) if len(sys.argv) > 3 else 1024
-    pt = int(sys.argv[4]) if len(sys.argv) > 4 else 5
+    th = int(sys.argv[3]) if len(sys.argv) > 3 else 512
+    pt = 0
     dep = sys.argv[5] if len(sys.argv) > 5 else "split32"
     rng = np.random.RandomState(0)
     x = rng.uniform(0, L, size=(B, 5000)); v = rng.normal(size=(B, 5000)) + 3.0 * (rng.uniform(size=(B, 5000)) < 0.1667)
