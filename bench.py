@@ -235,6 +235,29 @@ def run_gpu_arm(args):
         e2e_s = float(t[0])
     e2e_value = N * args.steps / e2e_s
 
+    # ---- for context: what a step costs when the caller insists on round-tripping the whole particle state through
+    #      host memory every step (pinned buffers, PCIe).  This is why the env state is device-resident.
+    roundtrip = None
+    if not args.no_roundtrip and world == 1:
+        Nr = 50_000_000
+        er = pic_b200.Engine(Nr, N_MESH, L_BOX, 2 / np.sqrt(Nr / L_BOX), mode="streaming", device=local)
+        er.sample_state("bump-on-tail", seed=1)
+        xh = torch.empty(Nr, dtype=torch.float64).pin_memory()
+        vh = torch.empty(Nr, dtype=torch.float64).pin_memory()
+        er.get_state_into(xh.data_ptr(), vh.data_ptr())
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(2):
+            er.set_state_ptr(xh.data_ptr(), vh.data_ptr())                          # H2D of x, v (+ field build)
+            er.step_mesh_ptr(ext_host.data_ptr(), 1)
+            er.get_state_into(xh.data_ptr(), vh.data_ptr())                         # D2H of x, v (synchronises)
+        dt_rt = (time.perf_counter() - t0) / 2
+        roundtrip = {"value": Nr / dt_rt, "unit": UNIT, "n_particles": Nr, "h2d_bytes_per_step": 16 * Nr + N_MESH * 8,
+                     "d2h_bytes_per_step": 16 * Nr, "s_per_step": dt_rt,
+                     "api": "pic_set_state(host x, v) + pic_step_mesh(host E_external) + pic_get_state(host x, v) every step"}
+        er.close()
+        del xh, vh
+
     # ---- roofline: the dominant kernel (kick + drift + deposit pass, stages 1-3) timed alone with CUDA events
     stage_ms = np.zeros(5)
     reps = max(2, min(args.steps, 10))
@@ -287,7 +310,6 @@ def run_gpu_arm(args):
         act = pic_b200.E_field(L_BOX, 250, 3)
         bp.set_actuator_basis(act.basis_cos, act.basis_sin)
         bp.sample_state("bump-on-tail", seed=7, n_global=5000)
-        bp.set_tuning(1024, 5, -1)
         T = 10
         coeffs = torch.rand(T, hi - lo, 6, dtype=torch.float64, device=dev) * 2 - 1
         for _ in range(10):
@@ -329,6 +351,7 @@ def run_gpu_arm(args):
             "roofline": roofline,
             "cpu_baseline": cpu,
             "batched": batched,
+            "e2e_state_roundtrip": roundtrip,
             "error_flags": int(flags),
             "energy_last": energies[-1] if energies else None,
         }
@@ -351,6 +374,7 @@ def main():
     ap.add_argument("--ctas", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-batched", action="store_true")
+    ap.add_argument("--no-roundtrip", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3                                   # timing rule: at least 3 warm-up steps

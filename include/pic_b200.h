@@ -122,6 +122,14 @@ int pic_set_reward(pic_handle* h, double alpha, double beta, double r_pe_n, doub
 int pic_enable_modes(pic_handle* h, int32_t n_modes);
 int pic_get_modes(pic_handle* h, double* modes);                          /* current state                    */
 int pic_get_mode_trace(pic_handle* h, double* modes, int32_t n_steps);    /* per step of the last pic_step_*  */
+/* Phase-space diagnostics of src/control/objective.py:8-18 (the KL cost of Reward.compute_kl_divergence,
+ * reward.py:43-46): 2-D histogram over x in [0, L] x v in [vmin, vmax] with nbins x nbins bins and np.histogram2d's
+ * edge rules; f = counts * n0/dx/dv/N; KL = sum(rel_entr(f, f_eq + 1e-12)) * dx * dv.  f_eq is supplied by the caller
+ * (estimate_f of the initial state, reward.py:18), host float64 [nbins][nbins]. */
+int pic_phase_hist_config(pic_handle* h, double vmin, double vmax, int32_t nbins);
+int pic_phase_hist(pic_handle* h, uint32_t* counts /* host [n_envs][nbins][nbins] or NULL */);
+int pic_set_feq(pic_handle* h, const double* feq);
+int pic_kl_divergence(pic_handle* h, double* kl /* host [n_envs] */);
 int pic_sync(pic_handle* h);
 /* sticky numeric flags raised on the device (bit 0: cell index out of range, bit 1: non-finite position) */
 int pic_get_error_flags(pic_handle* h, uint32_t* flags);

@@ -60,6 +60,10 @@ SIGNATURES = {
     "pic_enable_modes": (C.c_int, [_H, C.c_int32]),
     "pic_get_modes": (C.c_int, [_H, C.c_void_p]),
     "pic_get_mode_trace": (C.c_int, [_H, C.c_void_p, C.c_int32]),
+    "pic_phase_hist_config": (C.c_int, [_H, C.c_double, C.c_double, C.c_int32]),
+    "pic_phase_hist": (C.c_int, [_H, C.c_void_p]),
+    "pic_set_feq": (C.c_int, [_H, C.c_void_p]),
+    "pic_kl_divergence": (C.c_int, [_H, C.c_void_p]),
     "pic_sync": (C.c_int, [_H]),
     "pic_get_error_flags": (C.c_int, [_H, C.POINTER(C.c_uint32)]),
     "pic_get_device_views": (C.c_int, [_H, C.POINTER(PicDeviceViews)]),

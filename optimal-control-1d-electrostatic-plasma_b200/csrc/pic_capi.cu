@@ -83,6 +83,8 @@ struct pic_handle {
     int n_modes = 0;
     long long mode_trace_cap = 0;
     RewardConst rw{1.0, 1.0, 1.0, 1.0, 1.0};
+    unsigned* ph_counts = nullptr; double *ph_feq = nullptr, *ph_kl = nullptr;             // phase-space histogram
+    int ph_nb = 0; double ph_vmin = 0, ph_vmax = 0;
     double* stage64 = nullptr;                      // staging for f32 <-> f64 state conversion / cells
     size_t stage64_elems = 0;
     long long coeffs_cap = 0, trace_cap = 0;
@@ -235,6 +237,48 @@ __global__ void sample_kernel(R* __restrict__ x, R* __restrict__ v, long long N,
         x[(size_t)env * ld + i] = (R)xx;
         v[(size_t)env * ld + i] = (R)vv;
     }
+}
+
+// Phase-space histogram of src/control/objective.py:8-14: np.histogram2d(x, v, bins=[nb, nb], range=[[0, L],
+// [vmin, vmax]]).  Bin i of a coordinate is the largest i with edge(i) <= value, edges as np.linspace builds them
+// (i * step + start, last edge = stop exactly), the right-most edge belongs to the last bin, outliers are dropped.
+__device__ __forceinline__ double hist_edge(int i, int nb, double lo, double hi, double step) {
+    return i == nb ? hi : __dadd_rn(__dmul_rn((double)i, step), lo);
+}
+__device__ __forceinline__ int hist_bin(double val, int nb, double lo, double hi, double step, double inv_step) {
+    if (!(val >= lo && val <= hi)) return -1;
+    int i = (int)floor((val - lo) * inv_step);
+    i = i < 0 ? 0 : (i > nb - 1 ? nb - 1 : i);
+    while (i > 0 && val < hist_edge(i, nb, lo, hi, step)) --i;
+    while (i < nb - 1 && val >= hist_edge(i + 1, nb, lo, hi, step)) ++i;
+    return i;
+}
+template <typename R>
+__global__ void phase_hist_kernel(const R* __restrict__ x, const R* __restrict__ v, long long N, long long ld, int nb,
+                                  double L, double vmin, double vmax, unsigned* __restrict__ counts) {
+    const int env = blockIdx.y;
+    const double sx = L / nb, sv = (vmax - vmin) / nb;       // np.linspace: step = (stop - start) / div
+    const double isx = 1.0 / sx, isv = 1.0 / sv;
+    unsigned* c = counts + (size_t)env * nb * nb;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (long long)gridDim.x * blockDim.x) {
+        const int bx = hist_bin((double)x[(size_t)env * ld + i], nb, 0.0, L, sx, isx);
+        const int bv = hist_bin((double)v[(size_t)env * ld + i], nb, vmin, vmax, sv, isv);
+        if (bx >= 0 && bv >= 0) atomicAdd(&c[(size_t)bx * nb + bv], 1u);
+    }
+}
+// KL divergence of objective.py:16-18: sum(rel_entr(f, feq + 1e-12)) * dx * dv with f = counts * n0 / dx / dv / N
+__global__ void kl_kernel(const unsigned* __restrict__ counts, const double* __restrict__ feq, int nb, double scale,
+                          double dxdv, double* __restrict__ kl) {
+    __shared__ double red[33];
+    const int env = blockIdx.x;
+    const unsigned* c = counts + (size_t)env * nb * nb;
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < nb * nb; i += blockDim.x) {
+        const double a = (double)c[i] * scale, b = feq[i] + 1e-12;
+        if (a > 0.0) acc += a * log(a / b);
+    }
+    acc = block_sum<256>(acc, red);
+    if (threadIdx.x == 0) kl[env] = acc * dxdv;
 }
 
 // one streaming sub-stage: stage 0..3 = Yoshida stages, 4 = finalize, -1 = init deposit
@@ -476,7 +520,7 @@ int pic_destroy(pic_handle* h) {
     if (h->own_comm && h->comm && nccl_api().destroy) nccl_api().destroy(h->comm);
     void* bufs[] = {h->x, h->v, h->rho[0], h->rho[1], h->rho[2], h->rho[3], h->n, h->E, h->diag, h->vsum, h->partial,
                     h->ext, h->coeffs, h->bcos, h->bsin, h->trace, h->stage64, h->err, h->tw_cos, h->tw_sin, h->modes,
-                    h->mode_trace};
+                    h->mode_trace, h->ph_counts, h->ph_feq, h->ph_kl};
     for (void* b : bufs) if (b) cudaFree(b);
     delete h;
     return PIC_OK;
@@ -745,6 +789,77 @@ int pic_get_mode_trace(pic_handle* h, double* out, int32_t n_steps) {
     if (n_steps < 1 || n_steps > h->trace_steps) return fail(h, PIC_EINVAL, "n_steps exceeds the last call's step count");
     CK(h, cudaMemcpyAsync(out, h->mode_trace, sizeof(double) * (size_t)n_steps * h->n_envs * 2 * h->n_modes,
                           cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));
+    return PIC_OK;
+}
+
+static int phase_hist_run(pic_handle* h) {
+    const int nb = h->ph_nb;
+    CK(h, cudaMemsetAsync(h->ph_counts, 0, sizeof(unsigned) * (size_t)h->n_envs * nb * nb, h->stream));
+    long long gx = (h->N + 255) / 256;
+    dim3 grid((unsigned)(gx < 2048 ? gx : 2048), h->n_envs);
+    if (h->f32) phase_hist_kernel<float><<<grid, 256, 0, h->stream>>>((const float*)h->x, (const float*)h->v, h->N, h->ld, nb,
+                                                                      h->mc.L, h->ph_vmin, h->ph_vmax, h->ph_counts);
+    else phase_hist_kernel<double><<<grid, 256, 0, h->stream>>>((const double*)h->x, (const double*)h->v, h->N, h->ld, nb,
+                                                                h->mc.L, h->ph_vmin, h->ph_vmax, h->ph_counts);
+    h->launches++;
+    CK(h, cudaGetLastError());
+    return PIC_OK;
+}
+
+int pic_phase_hist_config(pic_handle* h, double vmin, double vmax, int32_t nbins) {
+    if (!h) return PIC_EINVAL;
+    if (nbins < 1 || nbins > 4096 || !(vmax > vmin)) return fail(h, PIC_EINVAL, "need 1 <= nbins <= 4096 and vmax > vmin");
+    CK(h, cudaSetDevice(h->device));
+    CK(h, cudaStreamSynchronize(h->stream));
+    if (h->ph_counts) cudaFree(h->ph_counts);
+    if (h->ph_feq) cudaFree(h->ph_feq);
+    if (h->ph_kl) cudaFree(h->ph_kl);
+    h->ph_counts = nullptr; h->ph_feq = nullptr; h->ph_kl = nullptr;
+    h->ph_nb = nbins; h->ph_vmin = vmin; h->ph_vmax = vmax;
+    CK(h, cudaMalloc(&h->ph_counts, sizeof(unsigned) * (size_t)h->n_envs * nbins * nbins));
+    CK(h, cudaMalloc(&h->ph_feq, sizeof(double) * (size_t)nbins * nbins));
+    CK(h, cudaMalloc(&h->ph_kl, sizeof(double) * (size_t)h->n_envs));
+    CK(h, cudaMemset(h->ph_feq, 0, sizeof(double) * (size_t)nbins * nbins));
+    return PIC_OK;
+}
+
+int pic_phase_hist(pic_handle* h, uint32_t* counts) {
+    if (!h) return PIC_EINVAL;
+    if (h->ph_nb < 1) return fail(h, PIC_ESTATE, "pic_phase_hist_config has not been called");
+    if (!h->have_state) return fail(h, PIC_ESTATE, "no state");
+    CK(h, cudaSetDevice(h->device));
+    int rc = phase_hist_run(h);
+    if (rc) return rc;
+    if (counts) {
+        CK(h, cudaMemcpyAsync(counts, h->ph_counts, sizeof(unsigned) * (size_t)h->n_envs * h->ph_nb * h->ph_nb,
+                              cudaMemcpyDeviceToHost, h->stream));
+        CK(h, cudaStreamSynchronize(h->stream));
+    }
+    return PIC_OK;
+}
+
+int pic_set_feq(pic_handle* h, const double* feq) {
+    if (!h || !feq) return PIC_EINVAL;
+    if (h->ph_nb < 1) return fail(h, PIC_ESTATE, "pic_phase_hist_config has not been called");
+    CK(h, cudaMemcpyAsync(h->ph_feq, feq, sizeof(double) * (size_t)h->ph_nb * h->ph_nb, cudaMemcpyHostToDevice, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));
+    return PIC_OK;
+}
+
+int pic_kl_divergence(pic_handle* h, double* kl) {
+    if (!h || !kl) return PIC_EINVAL;
+    if (h->ph_nb < 1) return fail(h, PIC_ESTATE, "pic_phase_hist_config has not been called");
+    if (!h->have_state) return fail(h, PIC_ESTATE, "no state");
+    CK(h, cudaSetDevice(h->device));
+    int rc = phase_hist_run(h);
+    if (rc) return rc;
+    const int nb = h->ph_nb;
+    const double dx = h->mc.L / nb, dv = (h->ph_vmax - h->ph_vmin) / nb;
+    const double scale = h->mc.n0 / dx / dv / (double)h->Ntotal;            // objective.py:13
+    kl_kernel<<<h->n_envs, 256, 0, h->stream>>>(h->ph_counts, h->ph_feq, nb, scale, dx * dv, h->ph_kl);
+    h->launches++;
+    CK(h, cudaMemcpyAsync(kl, h->ph_kl, sizeof(double) * (size_t)h->n_envs, cudaMemcpyDeviceToHost, h->stream));
     CK(h, cudaStreamSynchronize(h->stream));
     return PIC_OK;
 }

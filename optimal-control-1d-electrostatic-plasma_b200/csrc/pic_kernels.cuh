@@ -271,7 +271,7 @@ __host__ __device__ constexpr size_t resident_smem_bytes(int M, int threads, lon
 }
 
 template <typename R, int THREADS, int DEP, bool EXACT_W>
-__global__ void __launch_bounds__(THREADS) env_step_resident_kernel(const ResidentArgs a) {
+__global__ void __launch_bounds__(THREADS, THREADS <= 512 ? 1024 / THREADS : 1) env_step_resident_kernel(const ResidentArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x, env = blockIdx.x, M = a.mc.M, N = (int)a.N;
     SmemLayout<R> sm(smem_raw, M, true);

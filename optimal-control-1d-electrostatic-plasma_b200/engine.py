@@ -90,6 +90,10 @@ class Engine:
         self._ck(self._lib.pic_get_state(self._h, _ptr(x), _ptr(v)))
         return x, v
 
+    def set_state_ptr(self, x, v):
+        """x, v: addresses of host float64 buffers (e.g. pinned) of n_envs * N elements."""
+        self._ck(self._lib.pic_set_state(self._h, C.c_void_p(x), C.c_void_p(v)))
+
     def get_state_into(self, x, v):
         """Copies into caller-provided (e.g. pinned) float64 buffers."""
         self._ck(self._lib.pic_get_state(self._h, C.c_void_p(x), C.c_void_p(v)))
@@ -168,6 +172,33 @@ class Engine:
         out = np.empty((n_steps, self.n_envs, 2 * self.n_modes))
         self._ck(self._lib.pic_get_mode_trace(self._h, _ptr(out), int(n_steps)))
         return out
+
+    def phase_hist_config(self, vmin=-25.0, vmax=25.0, nbins=None):
+        """Configure the phase-space histogram (objective.py:8-14); nbins defaults to N_mesh as in Reward."""
+        self._nb = int(self.M if nbins is None else nbins)
+        self._ph = (float(vmin), float(vmax))
+        self._ck(self._lib.pic_phase_hist_config(self._h, float(vmin), float(vmax), self._nb))
+
+    def phase_hist(self):
+        """Raw counts (n_envs, nbins, nbins) uint32 == np.histogram2d(x, v, bins, range=[[0, L], [vmin, vmax]])[0]."""
+        c = np.empty((self.n_envs, self._nb, self._nb), dtype=np.uint32)
+        self._ck(self._lib.pic_phase_hist(self._h, _ptr(c)))
+        return c
+
+    def estimate_f(self, n0=1.0, n_total=None):
+        """estimate_f of objective.py:8-14 for the current state."""
+        dx, dv = self.L / self._nb, (self._ph[1] - self._ph[0]) / self._nb
+        return self.phase_hist().astype(np.float64) * (n0 / dx / dv / (self.N if n_total is None else n_total))
+
+    def set_feq(self, feq):
+        f = _f64(feq, (self._nb, self._nb))
+        self._ck(self._lib.pic_set_feq(self._h, _ptr(f)))
+
+    def kl_divergence(self):
+        """Reward.compute_kl_divergence (reward.py:43-46) of the current state of every env against f_eq."""
+        kl = np.empty(self.n_envs)
+        self._ck(self._lib.pic_kl_divergence(self._h, _ptr(kl)))
+        return kl
 
     def sync(self):
         self._ck(self._lib.pic_sync(self._h))

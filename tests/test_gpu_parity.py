@@ -283,3 +283,41 @@ def test_device_reward_and_spectral_modes(golden, mode):
     eng.step_mesh(g["E_ext"][0][None], 1)
     d = eng.get_diag()[0]
     assert d[5] == 0.0 and abs(d[4] - (max(1 - tr[-1, 1], 0) + 1.0)) < 1e-12
+
+
+def test_phase_space_histogram_and_kl(golden):
+    """estimate_f / estimate_KL_divergence (src/control/objective.py:8-18) on the device, checked
+    against np.histogram2d + scipy rel_entr on the same state (counts bit-exact, KL to 1e-12)."""
+    from scipy.special import rel_entr
+    g = golden("twostream_vb3")
+    N, M, L, dt = int(g["N"]), int(g["N_mesh"]), float(g["L"]), float(g["dt"])
+    vmin, vmax = -25.0, 25.0
+    eng = _engine(N, M, L, dt)
+    eng.phase_hist_config(vmin, vmax, M)
+
+    def ref_f(x, v):
+        d, _, _ = np.histogram2d(x, v, bins=[M, M], density=False, range=np.array([[0, L], [vmin, vmax]]))
+        return d
+
+    eng.set_state(g["t0_x"][None], g["t0_v"][None])
+    c0 = eng.phase_hist()[0]
+    assert np.array_equal(c0, ref_f(g["t0_x"], g["t0_v"]).astype(np.uint32))
+    dx, dv = L / M, (vmax - vmin) / M
+    feq = ref_f(g["raw_x_init"], g["raw_v_init"]) * (1.0 / dx / dv / N)        # Reward.__init__: estimate_f(init_state)
+    eng.set_feq(feq)
+    eng.step_mesh(None, 40)
+    x, v = eng.get_state()
+    f = ref_f(x[0], v[0]) * (1.0 / dx / dv / N)
+    assert np.array_equal(eng.phase_hist()[0], ref_f(x[0], v[0]).astype(np.uint32))
+    assert np.array_equal(eng.estimate_f()[0], f)
+    kl_ref = np.sum(rel_entr(f, feq + 1e-12)) * dx * dv
+    assert abs(eng.kl_divergence()[0] - kl_ref) < 1e-12 * max(1.0, abs(kl_ref))
+    # edge rules: values exactly on bin edges, on the right-most edge, and outliers
+    edges_v = np.linspace(vmin, vmax, M + 1)
+    xs = np.concatenate([np.linspace(0, L, M + 1)[:-1], np.nextafter(np.linspace(0, L, M + 1)[1:], 0), [0.0] * 6])
+    vs = np.concatenate([edges_v[:-1], edges_v[1:], [vmax, vmin, np.nextafter(vmax, 100), np.nextafter(vmin, -100), 30.0, -30.0]])
+    e2 = _engine(xs.shape[0], M, L, dt)
+    e2.phase_hist_config(vmin, vmax, M)
+    e2.set_state(xs[None], vs[None])
+    xx, vv = e2.get_state()
+    assert np.array_equal(e2.phase_hist()[0], ref_f(xx[0], vv[0]).astype(np.uint32))
