@@ -34,6 +34,7 @@ enum { PIC_OK = 0, PIC_EINVAL = -1, PIC_ENODEVICE = -2, PIC_ECUDA = -3, PIC_ENOM
 enum { PIC_F64 = 0, PIC_F32 = 1 };                       /* device precision of particles               */
 enum { PIC_MODE_AUTO = 0, PIC_MODE_RESIDENT = 1, PIC_MODE_STREAMING = 2 };
 enum { PIC_DEPOSIT_AUTO = -1, PIC_DEPOSIT_CAS64 = 0, PIC_DEPOSIT_SPLIT32 = 1 };
+enum { PIC_INTERP_CIC = 0, PIC_INTERP_TSC = 1 };         /* interpol of PIC.__init__: interpolate.py:4 / :22 */
 
 /* per-env diagnostics record (pic_get_diag / pic_get_trace), doubles */
 enum { PIC_DIAG_KE = 0,        /* 0.5*sum(v^2)            src/env/util.py:144                       */
@@ -64,6 +65,7 @@ typedef struct pic_config {
     int32_t device;             /* CUDA device ordinal                                                         */
     int32_t max_mode;           /* actuator modes m (src/control/actuator.py:5); 0 => mesh-vector actuation only */
     void*   stream;             /* cudaStream_t to enqueue on; NULL => the legacy default stream               */
+    int32_t interpolation;      /* PIC_INTERP_CIC | PIC_INTERP_TSC (float64 + split32 deposit only)            */
 } pic_config;
 
 /* --- lifetime ---------------------------------------------------------------------------------------------- */
@@ -95,9 +97,11 @@ int pic_get_density_fixed(pic_handle* h, uint64_t* rho, int32_t* fixed_bits);
 int pic_get_diag(pic_handle* h, double* diag);
 /* per-step records of the last pic_step_* call: [n_steps][n_envs][PIC_DIAG_N] */
 int pic_get_trace(pic_handle* h, double* trace, int32_t n_steps);
-/* cell index floor(x/dx), CIC weights and gathered field of the current state (pic.py:102-105,120);
- * [n_envs][n_particles] each, any pointer may be NULL */
-int pic_get_cells(pic_handle* h, int32_t* indx_l, double* weight_l, double* weight_r, double* E_particles);
+/* cell index floor(x/dx), weights and gathered field of the current state (pic.py:102-123); [n_envs][n_particles]
+ * each, any pointer may be NULL.  CIC: indx = indx_l, weight_m = 0.  TSC: indx = indx_m (indx_l/r = indx_m -+ 1 mod
+ * N_mesh) and the three weights of interpolate.py:30-32. */
+int pic_get_cells(pic_handle* h, int32_t* indx, double* weight_l, double* weight_r, double* E_particles,
+                  double* weight_m);
 
 /* --- the hot path -------------------------------------------------------------------------------------------- */
 /* PIC.update_state(E_external) (pic.py:131-146) n_steps times with the same external mesh field.

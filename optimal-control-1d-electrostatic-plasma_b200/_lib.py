@@ -12,6 +12,7 @@ PIC_OK = 0
 PIC_F64, PIC_F32 = 0, 1
 PIC_MODE_AUTO, PIC_MODE_RESIDENT, PIC_MODE_STREAMING = 0, 1, 2
 PIC_DEPOSIT_AUTO, PIC_DEPOSIT_CAS64, PIC_DEPOSIT_SPLIT32 = -1, 0, 1
+PIC_INTERP_CIC, PIC_INTERP_TSC = 0, 1
 DIAG_KE, DIAG_PE_MESH, DIAG_SUM_V, DIAG_SUM_E2, DIAG_REWARD, DIAG_INPUT_E, DIAG_N = 0, 1, 2, 3, 4, 5, 6
 ERR_INDEX_RANGE, ERR_NONFINITE = 1, 2
 
@@ -22,6 +23,7 @@ class PicConfig(C.Structure):
         ("n0", C.c_double), ("L", C.c_double), ("dt", C.c_double),
         ("precision", C.c_int32), ("mode", C.c_int32), ("deposit", C.c_int32), ("fixed_bits", C.c_int32),
         ("exact_weights", C.c_int32), ("device", C.c_int32), ("max_mode", C.c_int32), ("stream", C.c_void_p),
+        ("interpolation", C.c_int32),
     ]
 
 
@@ -50,7 +52,7 @@ SIGNATURES = {
     "pic_get_density_fixed": (C.c_int, [_H, C.c_void_p, C.POINTER(C.c_int32)]),
     "pic_get_diag": (C.c_int, [_H, C.c_void_p]),
     "pic_get_trace": (C.c_int, [_H, C.c_void_p, C.c_int32]),
-    "pic_get_cells": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "pic_get_cells": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "pic_step_mesh": (C.c_int, [_H, C.c_void_p, C.c_int32]),
     "pic_set_actuator_basis": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_int32]),
     "pic_step_coeffs": (C.c_int, [_H, C.c_void_p, C.c_int32]),

@@ -68,6 +68,7 @@ struct pic_handle {
     long long N = 0, ld = 0, Ntotal = 0;
     int M = 0, n_envs = 1, esize = 8, fixed_bits = 0, dep = DEP_CAS64;
     bool f32 = false, exact_w = false, resident = false;
+    int ip = IP_CIC;                                // interpolation: CIC | TSC
     double cs[4]{}, ds[4]{};
 
     // tuning
@@ -124,16 +125,20 @@ void yoshida(double cs[4], double ds[4]) {          // src/env/integration.py:62
 }
 
 const void* stream_kernel(const pic_handle* h, int mode) {
+    if (h->ip == IP_TSC) return stream_kernel_tsc(h->threads, h->per_thread, mode);
     return h->f32 ? stream_kernel_f32(h->threads, h->per_thread, mode, h->dep, h->exact_w)
                   : stream_kernel_f64(h->threads, h->per_thread, mode, h->dep, h->exact_w);
 }
 const void* resident_kernel(const pic_handle* h) {
+    if (h->ip == IP_TSC) return resident_kernel_tsc(h->threads);
     return h->f32 ? resident_kernel_f32(h->threads, h->dep, h->exact_w) : resident_kernel_f64(h->threads, h->dep, h->exact_w);
 }
 size_t smem_for(const pic_handle* h) {
     if (h->resident)
-        return h->f32 ? resident_smem_bytes<float>(h->M, h->threads, h->N) : resident_smem_bytes<double>(h->M, h->threads, h->N);
-    return h->f32 ? smem_plan_bytes<float>(h->M, h->threads, false) : smem_plan_bytes<double>(h->M, h->threads, false);
+        return h->f32 ? resident_smem_bytes<float>(h->M, h->threads, h->N, h->ip)
+                      : resident_smem_bytes<double>(h->M, h->threads, h->N, h->ip);
+    return h->f32 ? smem_plan_bytes<float>(h->M, h->threads, false, h->ip)
+                  : smem_plan_bytes<double>(h->M, h->threads, false, h->ip);
 }
 
 int configure_launch(pic_handle* h) {
@@ -190,22 +195,37 @@ __global__ void apply_vsum_kernel(const double* vsum, double* diag, double* trac
     }
 }
 
-template <typename R, bool EXACT_W>
+template <typename R, bool EXACT_W, int IP>
 __global__ void cells_kernel(const R* __restrict__ x, long long N, long long ld, MeshConst mc, int* il,
-                             double* wl, double* wr, const double* __restrict__ Emesh, double* Ep) {
+                             double* wl, double* wr, double* wm, const double* __restrict__ Emesh, double* Ep) {
     const PartConst<R> pc = make_part_const<R>(mc);
-    const int env = blockIdx.y;
+    const int env = blockIdx.y, M = mc.M;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (long long)gridDim.x * blockDim.x) {
-        R a, b; unsigned err = 0;
+        unsigned err = 0;
         R xw = wrap_pos<R>(x[(size_t)env * ld + i], pc, err);
-        Cell c = cell_weights<R, EXACT_W>(xw, pc, mc.M, a, b, err);
         size_t o = (size_t)env * N + i;
-        if (il) il[o] = c.il;
-        if (wl) wl[o] = (double)a;
-        if (wr) wr[o] = (double)b;
-        if (Ep) {                                      // pic.py:120
-            const double* E = Emesh + (size_t)env * mc.M;
-            Ep[o] = __dadd_rn(__dmul_rn((double)a, E[c.il]), __dmul_rn((double)b, E[c.ir == mc.M ? 0 : c.ir]));
+        const double* E = Emesh + (size_t)env * M;
+        if (IP == IP_TSC) {                            // interpolate.py:22-36, pic.py:123: il holds indx_m
+            R f;
+            int im = cell_index<R>(xw, pc, M, f, err);
+            R nr = RT<R>::sub(xw, RT<R>::mul(f, pc.dx));
+            R d = EXACT_W ? RT<R>::div(nr, pc.dx) : RT<R>::mul(nr, pc.inv_dx);
+            R a, b, c;
+            tsc_weights<R>(d, a, b, c);
+            if (il) il[o] = im;
+            if (wl) wl[o] = (double)a;
+            if (wm) wm[o] = (double)b;
+            if (wr) wr[o] = (double)c;
+            if (Ep) Ep[o] = __dadd_rn(__dadd_rn(__dmul_rn((double)a, E[im == 0 ? M - 1 : im - 1]), __dmul_rn((double)b, E[im])),
+                                      __dmul_rn((double)c, E[im == M - 1 ? 0 : im + 1]));
+        } else {
+            R a, b;
+            Cell c = cell_weights<R, EXACT_W>(xw, pc, M, a, b, err);
+            if (il) il[o] = c.il;
+            if (wl) wl[o] = (double)a;
+            if (wr) wr[o] = (double)b;
+            if (wm) wm[o] = 0.0;
+            if (Ep) Ep[o] = __dadd_rn(__dmul_rn((double)a, E[c.il]), __dmul_rn((double)b, E[c.ir == M ? 0 : c.ir]));   // pic.py:120
         }
     }
 }
@@ -448,6 +468,11 @@ int pic_create(const pic_config* cfg, pic_handle** out) {
     h->M = cfg->n_mesh; h->n_envs = cfg->n_envs;
     h->f32 = cfg->precision == PIC_F32; h->esize = h->f32 ? 4 : 8;
     h->exact_w = cfg->exact_weights != 0;
+    h->ip = cfg->interpolation == PIC_INTERP_TSC ? IP_TSC : IP_CIC;
+    if (h->ip == IP_TSC && (cfg->precision == PIC_F32 || cfg->deposit == PIC_DEPOSIT_CAS64 || h->exact_w)) {
+        delete h;
+        return fail(nullptr, PIC_EUNSUPPORTED, "TSC interpolation is built for float64 with the split32 deposit only");
+    }
     h->m = cfg->max_mode > 0 ? cfg->max_mode : 0;
     h->ld = (h->N + 15) / 16 * 16;
     yoshida(h->cs, h->ds);
@@ -473,8 +498,8 @@ int pic_create(const pic_config* cfg, pic_handle** out) {
     if (h->f32) h->dep = DEP_SPLIT32;
     int mode = cfg->mode;
     // resident = the whole env (particles + mesh tables) fits the shared memory of one CTA
-    const size_t res512 = h->f32 ? resident_smem_bytes<float>(h->M, 512, h->N) : resident_smem_bytes<double>(h->M, 512, h->N);
-    const size_t res1024 = h->f32 ? resident_smem_bytes<float>(h->M, 1024, h->N) : resident_smem_bytes<double>(h->M, 1024, h->N);
+    const size_t res512 = h->f32 ? resident_smem_bytes<float>(h->M, 512, h->N, h->ip) : resident_smem_bytes<double>(h->M, 512, h->N, h->ip);
+    const size_t res1024 = h->f32 ? resident_smem_bytes<float>(h->M, 1024, h->N, h->ip) : resident_smem_bytes<double>(h->M, 1024, h->N, h->ip);
     if (mode == PIC_MODE_AUTO) mode = (long long)res1024 <= (long long)h->max_smem ? PIC_MODE_RESIDENT : PIC_MODE_STREAMING;
     h->resident = mode == PIC_MODE_RESIDENT;
     if (h->resident) {
@@ -670,25 +695,27 @@ int pic_get_trace(pic_handle* h, double* trace, int32_t n_steps) {
     return PIC_OK;
 }
 
-int pic_get_cells(pic_handle* h, int32_t* il, double* wl, double* wr, double* Ep) {
+int pic_get_cells(pic_handle* h, int32_t* il, double* wl, double* wr, double* Ep, double* wm) {
     if (!h) return PIC_EINVAL;
     if (!h->have_state) return fail(h, PIC_ESTATE, "no state");
     size_t n = (size_t)h->N * h->n_envs;
-    int rc = ensure_stage64(h, 4 * n);          // [wl | wr | Ep | il(int32)]
+    int rc = ensure_stage64(h, 5 * n);          // [wl | wr | Ep | wm | il(int32)]
     if (rc) return rc;
-    double* dwl = h->stage64; double* dwr = h->stage64 + n; double* dE = h->stage64 + 2 * n;
-    int* dil = (int*)(h->stage64 + 3 * n);
+    double* dwl = h->stage64; double* dwr = h->stage64 + n; double* dE = h->stage64 + 2 * n; double* dwm = h->stage64 + 3 * n;
+    int* dil = (int*)(h->stage64 + 4 * n);
     long long gx = (h->N + 255) / 256;
     dim3 grid((unsigned)(gx < 4096 ? gx : 4096), h->n_envs);
-#define PIC_CELLS(R, EX) cells_kernel<R, EX><<<grid, 256, 0, h->stream>>>((const R*)h->x, h->N, h->ld, h->mc, dil, dwl, dwr, h->E, dE)
-    if (h->f32) { if (h->exact_w) PIC_CELLS(float, true); else PIC_CELLS(float, false); }
-    else        { if (h->exact_w) PIC_CELLS(double, true); else PIC_CELLS(double, false); }
+#define PIC_CELLS(R, EX, IP) cells_kernel<R, EX, IP><<<grid, 256, 0, h->stream>>>((const R*)h->x, h->N, h->ld, h->mc, dil, dwl, dwr, dwm, h->E, dE)
+    if (h->ip == IP_TSC) PIC_CELLS(double, false, IP_TSC);
+    else if (h->f32) { if (h->exact_w) PIC_CELLS(float, true, IP_CIC); else PIC_CELLS(float, false, IP_CIC); }
+    else             { if (h->exact_w) PIC_CELLS(double, true, IP_CIC); else PIC_CELLS(double, false, IP_CIC); }
 #undef PIC_CELLS
     h->launches++;
     if (il) CK(h, cudaMemcpyAsync(il, dil, sizeof(int) * n, cudaMemcpyDeviceToHost, h->stream));
     if (wl) CK(h, cudaMemcpyAsync(wl, dwl, sizeof(double) * n, cudaMemcpyDeviceToHost, h->stream));
     if (wr) CK(h, cudaMemcpyAsync(wr, dwr, sizeof(double) * n, cudaMemcpyDeviceToHost, h->stream));
     if (Ep) CK(h, cudaMemcpyAsync(Ep, dE, sizeof(double) * n, cudaMemcpyDeviceToHost, h->stream));
+    if (wm) CK(h, cudaMemcpyAsync(wm, dwm, sizeof(double) * n, cudaMemcpyDeviceToHost, h->stream));
     CK(h, cudaStreamSynchronize(h->stream));
     return PIC_OK;
 }

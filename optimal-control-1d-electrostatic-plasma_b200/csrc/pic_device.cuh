@@ -293,6 +293,40 @@ template <> struct Hist<DEP_SPLIT32> {
     }
 };
 
+// TSC (3-point) deposit, src/env/interpolate.py:22-44: a particle in cell m gives W_l to cell m-1, W_r to cell m+1 and
+// 2^k - W_l - W_r to its own cell (the reference's three weights sum to one; the middle one may be negative, which
+// the modular integer arithmetic handles).  Same single-cell trick as the CIC split deposit: the particle only
+// touches cell m -- cnt[m] += 1, A[m] += W_l, B[m] += W_r (two 64-bit sums in 32-bit words) -- and
+//   density[j] = cnt[j] 2^k - A[j] - B[j] + A[j+1] + B[j-1].
+constexpr int IP_CIC = 0;
+constexpr int IP_TSC = 1;
+
+struct HistTSC {
+    unsigned* w;                          // cnt | alo | ahi | blo | bhi, M words each
+    unsigned base_a;
+    int M;
+    static __host__ __device__ constexpr size_t bytes(int M) { return (size_t)M * 20 + 16; }
+    __device__ __forceinline__ void init(void* base, int M_) { M = M_; w = (unsigned*)base; base_a = (unsigned)__cvta_generic_to_shared(w); }
+    __device__ __forceinline__ void zero(int tid, int nthreads) { for (int j = tid; j < 5 * M; j += nthreads) w[j] = 0u; }
+    __device__ __forceinline__ void add64(unsigned lo_addr, unsigned hi_addr, unsigned long long S) {
+        const unsigned wl = (unsigned)S, wh = (unsigned)(S >> 32);
+        const unsigned old = atom_shared_u32(lo_addr, wl);
+        red_shared_u32(hi_addr, wh + ((old + wl) < old ? 1u : 0u));
+    }
+    __device__ __forceinline__ void deposit_group(int il, unsigned long long SA, unsigned long long SB, unsigned count) {
+        const unsigned off = base_a + 4u * (unsigned)il, st = 4u * (unsigned)M;
+        red_shared_u32(off, count);
+        add64(off + st, off + 2 * st, SA);
+        add64(off + 3 * st, off + 4 * st, SB);
+    }
+    __device__ __forceinline__ unsigned long long A(int j) const { return ((unsigned long long)w[2 * M + j] << 32) | w[M + j]; }
+    __device__ __forceinline__ unsigned long long B(int j) const { return ((unsigned long long)w[4 * M + j] << 32) | w[3 * M + j]; }
+    __device__ __forceinline__ unsigned long long get(int j, long long one) const {
+        const int jp = j == M - 1 ? 0 : j + 1, jm = j == 0 ? M - 1 : j - 1;
+        return (unsigned long long)w[j] * (unsigned long long)one - A(j) - B(j) + A(jp) + B(jm);
+    }
+};
+
 // ------------------------------------------------------------ block primitives
 template <int THREADS>
 __device__ __forceinline__ double block_sum(double v, double* scratch /* THREADS/32 + 1 doubles */) {
@@ -312,34 +346,6 @@ __device__ __forceinline__ double block_sum(double v, double* scratch /* THREADS
     }
     __syncthreads();
     return scratch[NW];
-}
-
-// exclusive prefix over the per-thread totals, plus nothing else; returns the exclusive offset of this thread
-template <int THREADS>
-__device__ __forceinline__ double block_excl_scan(double v, double* scratch /* THREADS/32 + 1 */) {
-    constexpr int NW = THREADS / 32;
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    double inc = v;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        double t = __shfl_up_sync(0xffffffffu, inc, o);
-        if (lane >= o) inc += t;
-    }
-    __syncthreads();
-    if (lane == 31) scratch[w] = inc;
-    __syncthreads();
-    if (w == 0) {
-        double s = lane < NW ? scratch[lane] : 0.0;
-        double si = s;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            double t = __shfl_up_sync(0xffffffffu, si, o);
-            if (lane >= o) si += t;
-        }
-        if (lane < NW) scratch[lane] = si - s;      // exclusive warp offsets
-    }
-    __syncthreads();
-    return scratch[w] + (inc - v);
 }
 
 // E_ext on the mesh from Fourier coefficients: basis_cos @ a + basis_sin @ b on the actuator's own node table
@@ -510,37 +516,17 @@ __device__ __forceinline__ FieldTotals block_field(RhoLoad rho, typename PairT<R
 
 // ------------------------------------------------------------------- push step
 // One Yoshida sub-stage for one particle (integration.py:22-47 with f = [v; -E], pic.py:125-129):
-//   kick  : v <- v + (d * (-E_p)) * dt     E_p = w_l E[i_l] + w_r E[i_r] at the CURRENT (wrapped) position
+//   kick  : v <- v + (d * (-E_p)) * dt     E_p gathered at the CURRENT (wrapped) position
 //   drift : x <- x + (c * v) * dt          x itself is carried unwrapped between sub-stages
-template <typename R, bool EXACT_W>
-__device__ __forceinline__ void kick(R x, R& v, const typename PairT<R>::type* __restrict__ E_s, R d,
-                                     const PartConst<R>& c, int M, unsigned& err) {
-    R wl, wr;
-    R xw = wrap_pos<R>(x, c, err);
-    Cell k = cell_weights<R, EXACT_W>(xw, c, M, wl, wr, err);
-    const typename PairT<R>::type e = E_s[k.il];
-    R Ep = RT<R>::add(RT<R>::mul(wl, e.x), RT<R>::mul(wr, e.y));
-    v = RT<R>::add(v, RT<R>::mul(RT<R>::mul(d, -Ep), c.dt));
-}
-
 template <typename R>
 __device__ __forceinline__ R drift(R x, R v, R cc, const PartConst<R>& c) {
     return RT<R>::add(x, RT<R>::mul(RT<R>::mul(cc, v), c.dt));
 }
 
-// CIC deposit in fixed point.  The right weight is rounded to k fractional bits, W_r = llrint(w_r 2^k), and the left
+// CIC deposit in fixed point: the right weight is rounded to k fractional bits, W_r = llrint(w_r 2^k), and the left
 // cell receives 2^k - W_r, so every particle deposits exactly 2^k: total charge is conserved to the bit and the sum
 // over cells is independent of summation order.  (The reference's w_l differs from 1 - w_r by at most one rounding
-// of 1.0, i.e. 1.1e-16 -- four orders below the stated density tolerance.)
-template <typename R, bool EXACT_W, typename H>
-__device__ __forceinline__ void deposit(R xw, H& hist, const PartConst<R>& c, const MeshConst& mc, unsigned& err) {
-    R f;
-    int il = cell_index<R>(xw, c, mc.M, f, err);
-    R nr = RT<R>::sub(xw, RT<R>::mul(f, c.dx));
-    R wr = EXACT_W ? RT<R>::div(nr, c.dx) : RT<R>::mul(nr, c.inv_dx);
-    long long Wr = fix_weight((double)wr, mc.fix_scale);
-    hist.deposit(il, Wr, mc.fix_one);
-}
+// of 1.0, i.e. 1.1e-16 -- four orders below the stated density tolerance.)  See deposit_weights below.
 
 // ---------------------------------------------------------------- fast path
 // The functions above are the reference semantics with every rare case handled in place (far wrap, positions within
@@ -563,8 +549,54 @@ __device__ __forceinline__ bool fast_cell(R xw, const PartConst<R>& c, int M, in
     return !(RT<R>::abs(diff) > c.idx_thr) | ((unsigned)il >= (unsigned)M);
 }
 
-template <typename R, bool KICK, bool MOVE, bool EXACT_W>
-__device__ __forceinline__ bool particle_fast(R x, R v, R& xn, R& vn, int& il_dep, long long& Wr_dep,
+// the three TSC weights from the in-cell distance d = (x - m dx)/dx, formulas followed literally (interpolate.py:28-32)
+template <typename R>
+__device__ __forceinline__ void tsc_weights(R d, R& wl, R& wm, R& wr) {
+    const R t = RT<R>::sub((R)1.5, d), u = RT<R>::sub(d, (R)1), q = RT<R>::sub(d, (R)0.5);
+    wl = RT<R>::mul((R)0.5, RT<R>::mul(t, t));
+    wm = RT<R>::sub((R)0.75, RT<R>::mul(u, u));
+    wr = RT<R>::mul((R)0.5, RT<R>::mul(q, q));
+}
+
+// gathered field at a particle of cell il (already inside the mesh) with in-cell numerators, util.py:106 / :110
+template <typename R, int IP, bool EXACT_W>
+__device__ __forceinline__ R gather_field(R x, int il, R f, const typename PairT<R>::type* __restrict__ E_s,
+                                          const PartConst<R>& c, int M) {
+    R nr = RT<R>::sub(x, RT<R>::mul(f, c.dx));
+    R wr = EXACT_W ? RT<R>::div(nr, c.dx) : RT<R>::mul(nr, c.inv_dx);
+    if (IP == IP_TSC) {
+        R wl, wm, wrr;
+        tsc_weights<R>(wr, wl, wm, wrr);
+        const typename PairT<R>::type e0 = E_s[il == 0 ? M - 1 : il - 1], e1 = E_s[il];   // (E_{m-1},E_m), (E_m,E_{m+1})
+        return RT<R>::add(RT<R>::add(RT<R>::mul(wl, e0.x), RT<R>::mul(wm, e1.x)), RT<R>::mul(wrr, e1.y));
+    }
+    R fr = RT<R>::add(f, (R)1);
+    R nl = RT<R>::sub(RT<R>::mul(fr, c.dx), x);
+    R wl = EXACT_W ? RT<R>::div(nl, c.dx) : RT<R>::mul(nl, c.inv_dx);
+    const typename PairT<R>::type e = E_s[il];
+    return RT<R>::add(RT<R>::mul(wl, e.x), RT<R>::mul(wr, e.y));
+}
+
+// fixed-point deposit weights of a particle at wrapped position xw in cell with floor f:
+// CIC: Wa = W_r (Wb unused);  TSC: Wa = W_l, Wb = W_r
+template <typename R, int IP, bool EXACT_W>
+__device__ __forceinline__ void deposit_weights(R xw, R f, const PartConst<R>& c, const MeshConst& mc, long long& Wa,
+                                                long long& Wb) {
+    R nr = RT<R>::sub(xw, RT<R>::mul(f, c.dx));
+    R wr = EXACT_W ? RT<R>::div(nr, c.dx) : RT<R>::mul(nr, c.inv_dx);
+    if (IP == IP_TSC) {
+        R wl, wm, wrr;
+        tsc_weights<R>(wr, wl, wm, wrr);
+        Wa = fix_weight((double)wl, mc.fix_scale);
+        Wb = fix_weight((double)wrr, mc.fix_scale);
+    } else {
+        Wa = fix_weight((double)wr, mc.fix_scale);
+        Wb = 0;
+    }
+}
+
+template <typename R, int IP, bool KICK, bool MOVE, bool EXACT_W>
+__device__ __forceinline__ bool particle_fast(R x, R v, R& xn, R& vn, int& il_dep, long long& Wa, long long& Wb,
                                               const typename PairT<R>::type* __restrict__ E_s, R cc, R dd,
                                               const PartConst<R>& c, const MeshConst& mc) {
     bool slow = false;
@@ -573,75 +605,83 @@ __device__ __forceinline__ bool particle_fast(R x, R v, R& xn, R& vn, int& il_de
         int il; R f;
         slow = fast_cell<R>(x, c, mc.M, il, f);
         il = (unsigned)il < (unsigned)mc.M ? il : 0;            // keep the gather address legal on the slow path
-        R fr = RT<R>::add(f, (R)1);
-        R nl = RT<R>::sub(RT<R>::mul(fr, c.dx), x);
-        R nr = RT<R>::sub(x, RT<R>::mul(f, c.dx));
-        R wl = EXACT_W ? RT<R>::div(nl, c.dx) : RT<R>::mul(nl, c.inv_dx);
-        R wr = EXACT_W ? RT<R>::div(nr, c.dx) : RT<R>::mul(nr, c.inv_dx);
-        const typename PairT<R>::type e = E_s[il];
-        R Ep = RT<R>::add(RT<R>::mul(wl, e.x), RT<R>::mul(wr, e.y));
+        R Ep = gather_field<R, IP, EXACT_W>(x, il, f, E_s, c, mc.M);
         vn = RT<R>::add(v, RT<R>::mul(RT<R>::mul(dd, -Ep), c.dt));
     }
     xn = MOVE ? RT<R>::add(x, RT<R>::mul(RT<R>::mul(cc, vn), c.dt)) : x;
     R f2;
     slow |= fast_cell<R>(xn, c, mc.M, il_dep, f2);
-    R nr2 = RT<R>::sub(xn, RT<R>::mul(f2, c.dx));
-    R wr2 = EXACT_W ? RT<R>::div(nr2, c.dx) : RT<R>::mul(nr2, c.inv_dx);
-    Wr_dep = fix_weight((double)wr2, mc.fix_scale);
+    deposit_weights<R, IP, EXACT_W>(xn, f2, c, mc, Wa, Wb);
     return slow;
 }
 
 // Reference semantics, every case handled (cold block; reached by ~1e-5 .. 1e-2 of the particles).
 // wrap_state: the position written back is the wrapped one (pic.py:139 / util.py:51), else the unwrapped drift.
-template <typename R, bool KICK, bool MOVE, bool EXACT_W>
-__device__ __forceinline__ void particle_careful(R& x, R& v, int& il_dep, long long& Wr_dep,
+template <typename R, int IP, bool KICK, bool MOVE, bool EXACT_W>
+__device__ __forceinline__ void particle_careful(R& x, R& v, int& il_dep, long long& Wa, long long& Wb,
                                                  const typename PairT<R>::type* __restrict__ E_s, R cc, R dd,
                                                  const PartConst<R>& c, const MeshConst& mc, bool wrap_state,
                                                  unsigned& err) {
-    if (KICK) kick<R, EXACT_W>(x, v, E_s, dd, c, mc.M, err);
+    if (KICK) {
+        R xk = wrap_pos<R>(x, c, err), fk;
+        int ik = cell_index<R>(xk, c, mc.M, fk, err);
+        R Ep = gather_field<R, IP, EXACT_W>(xk, ik, fk, E_s, c, mc.M);
+        v = RT<R>::add(v, RT<R>::mul(RT<R>::mul(dd, -Ep), c.dt));
+    }
     if (MOVE) x = drift<R>(x, v, cc, c);
     R xw = wrap_pos<R>(x, c, err);
     R f;
     il_dep = cell_index<R>(xw, c, mc.M, f, err);
-    R nr = RT<R>::sub(xw, RT<R>::mul(f, c.dx));
-    R wr = EXACT_W ? RT<R>::div(nr, c.dx) : RT<R>::mul(nr, c.inv_dx);
-    Wr_dep = fix_weight((double)wr, mc.fix_scale);
+    deposit_weights<R, IP, EXACT_W>(xw, f, c, mc, Wa, Wb);
     if (wrap_state) x = xw;
 }
 
+// 64-bit sum over the full warp of values below 2^51 (two 25/26-bit halves, each REDUX sum stays below 2^31)
+__device__ __forceinline__ unsigned long long warp_sum_u51(unsigned long long W) {
+    const unsigned a = __reduce_add_sync(0xffffffffu, (unsigned)(W & 0x1FFFFFFu));
+    const unsigned b = __reduce_add_sync(0xffffffffu, (unsigned)(W >> 25));
+    return (unsigned long long)a + ((unsigned long long)b << 25);
+}
+
 // Deposit of one particle per lane, all 32 lanes of the warp calling together.  When every lane hits the same
-// cell (cell-sorted particles) the warp sums its weights with two REDUX instructions and one lane issues the
+// cell (cell-sorted particles) the warp sums its weights with REDUX instructions and one lane issues the
 // atomics -- instead of 32 serialised same-address atomics.  Integer sums: grouping never changes the result.
-template <typename H>
-__device__ __forceinline__ void deposit_full_warp(H& hist, int il, long long Wr, long long one) {
-    constexpr unsigned FULL = 0xffffffffu;
-    const int il0 = __shfl_sync(FULL, il, 0);
-    if (__all_sync(FULL, il == il0)) {
-        const unsigned long long W = (unsigned long long)Wr;           // 0 <= Wr <= 2^50: two 25-bit halves,
-        const unsigned a = __reduce_add_sync(FULL, (unsigned)(W & 0x1FFFFFFu));   // 32 of them sum below 2^30
-        const unsigned b = __reduce_add_sync(FULL, (unsigned)(W >> 25));
-        if ((threadIdx.x & 31) == 0)
-            hist.deposit_group(il, (unsigned long long)a + ((unsigned long long)b << 25), 32u, one);
+template <int IP, typename H>
+__device__ __forceinline__ void deposit_one(H& hist, int il, long long Wa, long long Wb, long long one) {
+    if constexpr (IP == IP_TSC) hist.deposit_group(il, (unsigned long long)Wa, (unsigned long long)Wb, 1u);
+    else hist.deposit(il, Wa, one);
+}
+template <int IP, typename H>
+__device__ __forceinline__ void deposit_full_warp(H& hist, int il, long long Wa, long long Wb, long long one) {
+    const int il0 = __shfl_sync(0xffffffffu, il, 0);
+    if (__all_sync(0xffffffffu, il == il0)) {
+        const unsigned long long SA = warp_sum_u51((unsigned long long)Wa);
+        unsigned long long SB = 0;
+        if constexpr (IP == IP_TSC) SB = warp_sum_u51((unsigned long long)Wb);
+        if ((threadIdx.x & 31) == 0) {
+            if constexpr (IP == IP_TSC) hist.deposit_group(il, SA, SB, 32u);
+            else hist.deposit_group(il, SA, 32u, one);
+        }
     } else {
-        hist.deposit(il, Wr, one);
+        deposit_one<IP>(hist, il, Wa, Wb, one);
     }
 }
 
 // One sub-stage for one particle: fast path, careful fallback, deposit.  x, v are updated in place.
 // FULL_WARP: the caller guarantees that all 32 lanes of the warp execute this call (enables the aggregated deposit).
-template <typename R, bool KICK, bool MOVE, bool EXACT_W, bool FULL_WARP, typename H>
+template <typename R, int IP, bool KICK, bool MOVE, bool EXACT_W, bool FULL_WARP, typename H>
 __device__ __forceinline__ void particle_substage(R& x, R& v, H& hist, const typename PairT<R>::type* __restrict__ E_s,
                                                   R cc, R dd, const PartConst<R>& c, const MeshConst& mc,
                                                   bool wrap_state, unsigned& err) {
-    R xn, vn; int il; long long Wr;
-    const bool slow = particle_fast<R, KICK, MOVE, EXACT_W>(x, v, xn, vn, il, Wr, E_s, cc, dd, c, mc);
+    R xn, vn; int il; long long Wa, Wb;
+    const bool slow = particle_fast<R, IP, KICK, MOVE, EXACT_W>(x, v, xn, vn, il, Wa, Wb, E_s, cc, dd, c, mc);
     if (__builtin_expect(slow, 0)) {
-        particle_careful<R, KICK, MOVE, EXACT_W>(x, v, il, Wr, E_s, cc, dd, c, mc, wrap_state, err);
+        particle_careful<R, IP, KICK, MOVE, EXACT_W>(x, v, il, Wa, Wb, E_s, cc, dd, c, mc, wrap_state, err);
     } else {
         x = xn; v = vn;                                   // inside [0, L): wrapped == unwrapped
     }
-    if (FULL_WARP) deposit_full_warp(hist, il, Wr, mc.fix_one);
-    else hist.deposit(il, Wr, mc.fix_one);
+    if (FULL_WARP) deposit_full_warp<IP>(hist, il, Wa, Wb, mc.fix_one);
+    else deposit_one<IP>(hist, il, Wa, Wb, mc.fix_one);
 }
 
 // streaming loads / stores (no reuse: keep the particle stream out of L1, evict-first in L2)

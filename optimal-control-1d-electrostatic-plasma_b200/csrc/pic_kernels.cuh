@@ -47,12 +47,14 @@ struct StreamArgs {
 // Shared-memory plan of one CTA.  SEPARATE_D: the prefix-sum scratch gets its own region (needed when the density
 // is read from the shared histogram itself, i.e. the resident kernel); otherwise it aliases the histogram, which is
 // idle while the field is rebuilt from the global density.
-constexpr size_t hist_region_bytes(int M) { return (size_t)M * 12 + 16; }      // max over deposit flavours, 8-aligned
+__host__ __device__ constexpr size_t hist_region_bytes(int M, int ip) {      // max over deposit flavours, 16-aligned
+    return (((size_t)M * (ip == IP_TSC ? 20 : 12) + 16 + 15) & ~(size_t)15);
+}
 
 template <typename R>
-__host__ __device__ constexpr size_t smem_plan_bytes(int M, int threads, bool separate_d) {
+__host__ __device__ constexpr size_t smem_plan_bytes(int M, int threads, bool separate_d, int ip = IP_CIC) {
     return (size_t)M * 2 * sizeof(R)                 // gather pair table
-         + (((size_t)M * 12 + 16 + 15) & ~(size_t)15)   // histogram
+         + hist_region_bytes(M, ip)                  // histogram
          + (separate_d ? (size_t)M * 8 : 0)          // D_s
          + (size_t)(field_scratch_doubles(threads) + threads / 32 + 2) * 8;   // field / reduction scratch
 }
@@ -60,9 +62,9 @@ __host__ __device__ constexpr size_t smem_plan_bytes(int M, int threads, bool se
 template <typename R>
 struct SmemLayout {
     void* hist; typename PairT<R>::type* E_s; double* D_s; double* red;
-    __device__ __forceinline__ SmemLayout(unsigned char* base, int M, bool separate_d) {
+    __device__ __forceinline__ SmemLayout(unsigned char* base, int M, bool separate_d, int ip = IP_CIC) {
         E_s = (typename PairT<R>::type*)base;   base += (size_t)M * 2 * sizeof(R);
-        hist = base;                            base += (((size_t)M * 12 + 16 + 15) & ~(size_t)15);
+        hist = base;                            base += hist_region_bytes(M, ip);
         D_s = separate_d ? (double*)base : (double*)hist;
         if (separate_d) base += (size_t)M * 8;
         red = (double*)base;
@@ -87,7 +89,10 @@ __device__ __forceinline__ ExtSrc stage_ext(const ActuatorArgs& act, int env, in
     return e;
 }
 
-template <typename R, int THREADS, int UNROLL, int MODE, int DEP, bool EXACT_W>
+template <int DEP, int IP> struct HistSel { using type = Hist<DEP>; };
+template <int DEP> struct HistSel<DEP, IP_TSC> { using type = HistTSC; };
+
+template <typename R, int THREADS, int UNROLL, int MODE, int DEP, bool EXACT_W, int IP = IP_CIC>
 __global__ void __launch_bounds__(THREADS) push_stream_kernel(const StreamArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     using V = typename RT<R>::vec;
@@ -95,8 +100,8 @@ __global__ void __launch_bounds__(THREADS) push_stream_kernel(const StreamArgs a
     constexpr bool KICK = (MODE == MODE_KICK || MODE == MODE_FINAL);
     constexpr bool SUMS = (MODE == MODE_FINAL || MODE == MODE_INIT);
     const int tid = threadIdx.x, env = blockIdx.y, M = a.mc.M;
-    SmemLayout<R> sm(smem_raw, M, false);
-    Hist<DEP> hist; hist.init(sm.hist, M);
+    SmemLayout<R> sm(smem_raw, M, false, IP);
+    typename HistSel<DEP, IP>::type hist; hist.init(sm.hist, M);
     const PartConst<R> pc = make_part_const<R>(a.mc);
 
     if (KICK) {                                         // D_s aliases the histogram: solve first, then clear
@@ -121,7 +126,7 @@ __global__ void __launch_bounds__(THREADS) push_stream_kernel(const StreamArgs a
     double s2 = 0.0, s1 = 0.0;
 
     auto one = [&](R& x, R& v, auto full_warp) {
-        particle_substage<R, KICK, MODE != MODE_INIT, EXACT_W, decltype(full_warp)::value>(
+        particle_substage<R, IP, KICK, MODE != MODE_INIT, EXACT_W, decltype(full_warp)::value>(
             x, v, hist, sm.E_s, cc, dd, pc, a.mc, SUMS, err);
         if (SUMS) { s2 += (double)v * (double)v; s1 += (double)v; }
     };
@@ -266,18 +271,19 @@ struct ResidentArgs {
 // slower: 64 registers per thread at 1024 threads spill, and at 512 threads only one CTA fits per SM, so nothing
 // overlaps the barriers of the field solve.  With the state in shared memory two 512-thread CTAs share an SM.)
 template <typename R>
-__host__ __device__ constexpr size_t resident_smem_bytes(int M, int threads, long long n) {
-    return smem_plan_bytes<R>(M, threads, true) + (size_t)((n + 1) / 2 * 2) * 2 * sizeof(R);
+__host__ __device__ constexpr size_t resident_smem_bytes(int M, int threads, long long n, int ip = IP_CIC) {
+    return smem_plan_bytes<R>(M, threads, true, ip) + (size_t)((n + 1) / 2 * 2) * 2 * sizeof(R);
 }
 
-template <typename R, int THREADS, int DEP, bool EXACT_W>
+template <typename R, int THREADS, int DEP, bool EXACT_W, int IP = IP_CIC>
 __global__ void __launch_bounds__(THREADS, THREADS <= 512 ? 1024 / THREADS : 1) env_step_resident_kernel(const ResidentArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x, env = blockIdx.x, M = a.mc.M, N = (int)a.N;
-    SmemLayout<R> sm(smem_raw, M, true);
-    R* x_s = (R*)(smem_raw + smem_plan_bytes<R>(M, THREADS, true));
+    SmemLayout<R> sm(smem_raw, M, true, IP);
+    R* x_s = (R*)(smem_raw + smem_plan_bytes<R>(M, THREADS, true, IP));
     R* v_s = x_s + (N + 1) / 2 * 2;
-    Hist<DEP> hist; hist.init(sm.hist, M);
+    using H = typename HistSel<DEP, IP>::type;
+    H hist; hist.init(sm.hist, M);
     const PartConst<R> pc = make_part_const<R>(a.mc);
     R* xe = (R*)a.x + (size_t)env * a.ld;
     R* ve = (R*)a.v + (size_t)env * a.ld;
@@ -285,7 +291,7 @@ __global__ void __launch_bounds__(THREADS, THREADS <= 512 ? 1024 / THREADS : 1) 
     hist.zero(tid, THREADS);
     __syncthreads();
     unsigned err = 0;
-    SharedRho<Hist<DEP>> rho{&hist, a.mc.fix_one};
+    SharedRho<H> rho{&hist, a.mc.fix_one};
     double* n_out = a.n_out + (size_t)env * M;
     double* E_out = a.E_out + (size_t)env * M;
     const ExtSrc none{nullptr, nullptr, nullptr, nullptr, 0};
@@ -327,7 +333,7 @@ __global__ void __launch_bounds__(THREADS, THREADS <= 512 ? 1024 / THREADS : 1) 
     if (a.n_steps == 0) {
         for (int i = tid; i < N; i += THREADS) {
             R x = x_s[i], v = v_s[i];
-            particle_substage<R, false, false, EXACT_W, false>(x, v, hist, sm.E_s, (R)0, (R)0, pc, a.mc, true, err);
+            particle_substage<R, IP, false, false, EXACT_W, false>(x, v, hist, sm.E_s, (R)0, (R)0, pc, a.mc, true, err);
             x_s[i] = x;
         }
         __syncthreads();
@@ -350,7 +356,7 @@ __global__ void __launch_bounds__(THREADS, THREADS <= 512 ? 1024 / THREADS : 1) 
 #pragma unroll 2
             for (int i = tid; i < N; i += THREADS) {
                 R x = x_s[i], v = v_s[i];
-                particle_substage<R, false, true, EXACT_W, false>(x, v, hist, sm.E_s, cc, (R)0, pc, a.mc, false, err);
+                particle_substage<R, IP, false, true, EXACT_W, false>(x, v, hist, sm.E_s, cc, (R)0, pc, a.mc, false, err);
                 x_s[i] = x;
             }
             __syncthreads();
@@ -363,7 +369,7 @@ __global__ void __launch_bounds__(THREADS, THREADS <= 512 ? 1024 / THREADS : 1) 
 #pragma unroll 2
             for (int i = tid; i < N; i += THREADS) {
                 R x = x_s[i], v = v_s[i];
-                particle_substage<R, true, true, EXACT_W, false>(x, v, hist, sm.E_s, cc, dd, pc, a.mc, fin, err);
+                particle_substage<R, IP, true, true, EXACT_W, false>(x, v, hist, sm.E_s, cc, dd, pc, a.mc, fin, err);
                 x_s[i] = x; v_s[i] = v;
             }
             __syncthreads();

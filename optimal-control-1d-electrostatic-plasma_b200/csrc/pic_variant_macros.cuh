@@ -15,3 +15,12 @@
     if (threads == T && dep == DP && exact_w == EX) \
         return (const void*)&pic::env_step_resident_kernel<R, T, DP, EX>;
 #define PIC_R_DEPS(R, T, EX) PIC_R_CASE(R, T, pic::DEP_CAS64, EX) PIC_R_CASE(R, T, pic::DEP_SPLIT32, EX)
+
+// TSC interpolation: split32 deposit, float64, the default launch shapes only
+#define PIC_S_TSC(T, U, MD) \
+    if (threads == T && unroll == U && mode == MD) \
+        return (const void*)&pic::push_stream_kernel<double, T, U, MD, pic::DEP_SPLIT32, false, pic::IP_TSC>;
+#define PIC_S_TSC_MODES(T, U) PIC_S_TSC(T, U, pic::MODE_DRIFT) PIC_S_TSC(T, U, pic::MODE_KICK) \
+    PIC_S_TSC(T, U, pic::MODE_FINAL) PIC_S_TSC(T, U, pic::MODE_INIT)
+#define PIC_R_TSC(T) \
+    if (threads == T) return (const void*)&pic::env_step_resident_kernel<double, T, pic::DEP_SPLIT32, false, pic::IP_TSC>;

@@ -9,5 +9,7 @@ const void* stream_kernel_f64(int threads, int unroll, int mode, int dep, bool e
 const void* stream_kernel_f32(int threads, int unroll, int mode, int dep, bool exact_w);
 const void* resident_kernel_f64(int threads, int dep, bool exact_w);
 const void* resident_kernel_f32(int threads, int dep, bool exact_w);
+const void* stream_kernel_tsc(int threads, int unroll, int mode);     // TSC: float64, split32, default shapes
+const void* resident_kernel_tsc(int threads);
 
 }  // namespace pic

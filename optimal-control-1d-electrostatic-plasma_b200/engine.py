@@ -35,12 +35,15 @@ class DeviceArray:
 
 class Engine:
     def __init__(self, n_particles, n_mesh, L_box, dt, n0=1.0, n_envs=1, n_particles_total=0, precision="f64",
-                 mode="auto", deposit="auto", fixed_bits=0, exact_weights=False, device=0, max_mode=0, stream=None):
+                 mode="auto", deposit="auto", fixed_bits=0, exact_weights=False, device=0, max_mode=0, stream=None,
+                 interpol="CIC"):
         self._lib = L.load()
         self._h = C.c_void_p()
         cfg = L.PicConfig(int(n_particles), int(n_particles_total), int(n_mesh), int(n_envs), float(n0), float(L_box),
                           float(dt), _PREC[precision], _MODE[mode], _DEP[deposit], int(fixed_bits),
-                          int(bool(exact_weights)), int(device), int(max_mode), C.c_void_p(stream or 0))
+                          int(bool(exact_weights)), int(device), int(max_mode), C.c_void_p(stream or 0),
+                          {"CIC": L.PIC_INTERP_CIC, "TSC": L.PIC_INTERP_TSC}[interpol])
+        self.interpol = interpol
         rc = self._lib.pic_create(C.byref(cfg), C.byref(self._h))
         if rc != 0:
             msg = self._lib.pic_last_error(None)
@@ -119,13 +122,15 @@ class Engine:
         self._ck(self._lib.pic_get_trace(self._h, _ptr(t), n_steps))
         return t
 
-    def get_cells(self, want_weights=True, want_E=True):
+    def get_cells(self, want_weights=True, want_E=True, want_wm=False):
+        """(indx, weight_l, weight_r, E[, weight_m]); indx = indx_l for CIC, indx_m for TSC."""
         il = np.empty((self.n_envs, self.N), dtype=np.int32)
         wl = np.empty((self.n_envs, self.N)) if want_weights else None
         wr = np.empty((self.n_envs, self.N)) if want_weights else None
         E = np.empty((self.n_envs, self.N)) if want_E else None
-        self._ck(self._lib.pic_get_cells(self._h, _ptr(il), _ptr(wl), _ptr(wr), _ptr(E)))
-        return il, wl, wr, E
+        wm = np.empty((self.n_envs, self.N)) if want_wm else None
+        self._ck(self._lib.pic_get_cells(self._h, _ptr(il), _ptr(wl), _ptr(wr), _ptr(E), _ptr(wm)))
+        return (il, wl, wr, E, wm) if want_wm else (il, wl, wr, E)
 
     # ---- hot path
     def step_mesh(self, E_ext=None, n_steps=1):

@@ -19,9 +19,8 @@ class PIC:
                  tmin: float = 0.0, tmax: float = 50.0, gamma: float = 5.0, A: float = 0.1, n_mode: int = 4,
                  interpol: str = "CIC", init_dist=None, *, device: int = 0, precision: str = "f64",
                  mode: str = "auto", deposit: str = "auto", exact_weights: bool = False, max_mode: int = 0):
-        if interpol != "CIC":
-            raise NotImplementedError("interpol=%r: only the CIC deposit (src/env/interpolate.py:4) is on the device "
-                                      "path; TSC is listed as 'next' in DESIGN.md" % (interpol,))
+        if interpol not in ("CIC", "TSC"):
+            raise ValueError("interpol must be 'CIC' or 'TSC' (src/env/interpolate.py), got %r" % (interpol,))
         self.N = N
         self.N_mesh = N_mesh
         self.n0 = n0
@@ -49,7 +48,7 @@ class PIC:
             o = self._opts
             self._eng = Engine(self.N, self.N_mesh, self.L, self.dt, n0=self.n0, n_envs=1, precision=o["precision"],
                                mode=o["mode"], deposit=o["deposit"], exact_weights=o["exact_weights"],
-                               device=o["device"], max_mode=o["max_mode"])
+                               device=o["device"], max_mode=o["max_mode"], interpol=self.interpol)
         return self._eng
 
     @property
@@ -167,14 +166,24 @@ class PIC:
 
     def _cells(self):
         if "cells" not in self._cache:
-            il, wl, wr, E = self._engine().get_cells()
+            il, wl, wr, E, wm = self._engine().get_cells(want_wm=True)
             self._cache["cells"] = (il[0].astype(np.int64).reshape(-1, 1), wl[0].reshape(-1, 1), wr[0].reshape(-1, 1),
-                                    E[0].reshape(-1, 1))
+                                    E[0].reshape(-1, 1), wm[0].reshape(-1, 1))
         return self._cache["cells"]
 
     @property
     def indx_l(self):
+        if self.interpol == "TSC":                       # interpolate.py:34
+            return np.mod(self._cells()[0] - 1, self.N_mesh)
         return self._cells()[0]
+
+    @property
+    def indx_m(self):
+        return self._cells()[0] if self.interpol == "TSC" else None
+
+    @property
+    def weight_m(self):
+        return self._cells()[4] if self.interpol == "TSC" else None
 
     @property
     def indx_r(self):
@@ -191,9 +200,6 @@ class PIC:
     @property
     def E(self):
         return self._cells()[3]
-
-    indx_m = None
-    weight_m = None
 
     def update_params(self, **kwargs):                                 # pic.py:79-82
         for key in kwargs.keys():

@@ -122,9 +122,11 @@ def tsc(x: np.ndarray, n0: float, L: float, N: int, N_mesh: int, dx: float):
     return n, indx_l, indx_m, indx_r, weight_l, weight_m, weight_r
 
 
-def compute_n(x: np.ndarray, dx, N_mesh, n0, L, N):
-    """src/env/util.py:48-62 -- wraps ``x`` IN PLACE, then CIC."""
+def compute_n(x: np.ndarray, dx, N_mesh, n0, L, N, interpol: str = "CIC"):
+    """src/env/util.py:48-70 -- wraps ``x`` IN PLACE, then CIC (5-tuple) or TSC (7-tuple)."""
     x[:] = np.mod(x, L)
+    if interpol == "TSC":
+        return tsc(x, n0, L, N, N_mesh, dx)
     return cic(x, n0, L, N, N_mesh, dx)
 
 
@@ -240,6 +242,7 @@ class PicParams:
     L: float
     dt: float                 # already CFL-clipped (clip_dt)
     gamma: float = 5.0
+    interpol: str = "CIC"     # "CIC" | "TSC" (src/env/interpolate.py:4 / :22)
 
     @property
     def dx(self) -> float:
@@ -257,6 +260,12 @@ def accel(x, p: PicParams, E_ext: Optional[np.ndarray], faithful: bool):
     src/env/util.py:73-116 (gamma is hard-coded 5.0 there, util.py:99).
     Does not modify ``x`` (the reference wraps a scratch copy)."""
     xs = x.copy()
+    if p.interpol == "TSC":
+        n, il, im, ir, wl, wm, wr = compute_n(xs, p.dx, p.N_mesh, p.n0, p.L, p.N, "TSC")
+        E_mesh = _field(n, p, faithful, 5.0)
+        if E_ext is not None:
+            E_mesh = E_mesh + E_ext
+        return (-1) * (wl * E_mesh[il] + wm * E_mesh[im] + wr * E_mesh[ir]), im          # util.py:110
     n, il, ir, wl, wr = compute_n(xs, p.dx, p.N_mesh, p.n0, p.L, p.N)
     E_mesh = _field(n, p, faithful, 5.0)
     if E_ext is not None:
@@ -293,6 +302,15 @@ def step(x: np.ndarray, v: np.ndarray, p: PicParams, E_ext: Optional[np.ndarray]
             accel(q, p, E_ext, True)
         q = q + c * pm * dt                                # integration.py:42
     xf = np.mod(q, p.L)                                    # pic.py:139
+    if p.interpol == "TSC":
+        n, il, im, ir, wl, wm, wr = compute_n(xf, p.dx, p.N_mesh, p.n0, p.L, p.N, "TSC")
+        E_mesh = _field(n, p, faithful, p.gamma)
+        E = wl * E_mesh[il] + wm * E_mesh[im] + wr * E_mesh[ir]          # pic.py:123
+        out = dict(x=xf, v=pm, n=n, E_mesh=E_mesh, E=E, indx_l=il, indx_m=im, indx_r=ir, weight_l=wl, weight_m=wm,
+                   weight_r=wr)
+        if return_stage_indices:
+            out["stage_indx_l"] = stage_idx
+        return out
     n, il, ir, wl, wr = compute_n(xf, p.dx, p.N_mesh, p.n0, p.L, p.N)   # pic.py:145 (wraps xf again in place)
     E_mesh = _field(n, p, faithful, p.gamma)               # pic.py:116-117
     E = gather(E_mesh, il, ir, wl, wr)                     # pic.py:120
@@ -325,7 +343,7 @@ def mesh_field_of_state(x, p: PicParams, faithful: bool = False):
     compute_electric_energy / estimate_electric_energy recompute:
     src/env/util.py:128, src/control/objective.py:24)."""
     xs = np.asarray(x, dtype=np.float64).reshape(-1).copy()
-    n, *_ = compute_n(xs, p.dx, p.N_mesh, p.n0, p.L, p.N)
+    n, *_ = compute_n(xs, p.dx, p.N_mesh, p.n0, p.L, p.N, p.interpol)
     return _field(n, p, faithful, 5.0)
 
 

@@ -50,6 +50,9 @@ def snap(sim, tag, out, light=False):
     out[f"{tag}_E_mesh"] = sim.E_mesh[:, 0].copy()
     out[f"{tag}_E"] = sim.E[:, 0].copy()
     out[f"{tag}_indx_l"] = sim.indx_l[:, 0].astype(np.int32)
+    if sim.interpol == "TSC":
+        out[f"{tag}_indx_m"] = sim.indx_m[:, 0].astype(np.int32)
+        out[f"{tag}_weight_m"] = sim.weight_m[:, 0].copy()
 
 
 def run_case(name, simcase, steps, checkpoints, control=None, light=False, **kw):
@@ -142,6 +145,16 @@ def deposit_edge_cases():
 
 
 if __name__ == "__main__":
+    # TSC interpolation (run_wo_oc.py --interpol TSC)
+    if os.environ.get("GOLDEN_ONLY", "") in ("", "tsc"):
+        run_case("bump_vb3_tsc", "bump-on-tail", 40, {1, 40}, interpol="TSC")
+        rs3 = np.random.RandomState(77)
+        seq3 = rs3.uniform(-1.0, 1.0, size=(20, 6))
+        run_case("twostream_tsc_ctrl", "two-stream", 20, {1, 20}, interpol="TSC",
+                 control={"max_mode": 3, "fn": lambda t: seq3[t]})
+        if os.environ.get("GOLDEN_ONLY", "") == "tsc":
+            sys.exit(0)
+
     run_case("bump_vb3", "bump-on-tail", 500, {1, 10, 500})
     run_case("twostream_vb3", "two-stream", 500, {1, 10, 500})
     run_case("bump_vb5", "bump-on-tail", 500, {500}, vb=5.0)

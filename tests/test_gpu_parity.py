@@ -252,8 +252,8 @@ def test_pic_class_is_a_drop_in(golden):
     assert np.abs(sim.x[:, 0] - g["t10_x"]).max() < 1e-12
     assert np.array_equal(sim.indx_l[:, 0], g["t10_indx_l"].astype(np.int64))
     assert np.abs(sim.E_mesh[:, 0] - g["t10_E_mesh"]).max() < 1e-12
-    with pytest.raises(NotImplementedError):
-        PIC(N=100, N_mesh=10, interpol="TSC", init_dist=dist)
+    with pytest.raises(ValueError):
+        PIC(N=100, N_mesh=10, interpol="NGP", init_dist=dist)
 
 
 @pytest.mark.parametrize("mode", ["resident", "streaming"])
@@ -321,3 +321,55 @@ def test_phase_space_histogram_and_kl(golden):
     e2.set_state(xs[None], vs[None])
     xx, vv = e2.get_state()
     assert np.array_equal(e2.phase_hist()[0], ref_f(xx[0], vv[0]).astype(np.uint32))
+
+
+@pytest.mark.parametrize("mode", ["resident", "streaming"])
+@pytest.mark.parametrize("name,steps,ctrl", [("bump_vb3_tsc", 40, False), ("twostream_tsc_ctrl", 20, True)])
+def test_tsc_interpolation(golden, mode, name, steps, ctrl):
+    """interpol="TSC" (src/env/interpolate.py:22-44, gather util.py:110) against the reference."""
+    g = golden(name)
+    N, M, L, dt = int(g["N"]), int(g["N_mesh"]), float(g["L"]), float(g["dt"])
+    eng = _engine(N, M, L, dt, mode=mode, max_mode=3, interpol="TSC")
+    eng.set_state(g["t0_x"][None], g["t0_v"][None])
+    n, E = eng.get_fields()
+    assert np.abs(n[0] - g["t0_n"]).max() < 1e-12 and np.abs(E[0] - g["t0_E_mesh"]).max() < 1e-12
+    if ctrl:
+        eng.set_actuator_basis(g["basis_cos"], g["basis_sin"])
+        eng.step_coeffs(g["coeffs"][:1, None, :], 1)
+    else:
+        eng.step_mesh(None, 1)
+    x, v = eng.get_state()
+    assert np.abs(x[0] - g["t1_x"]).max() < 1e-12 and np.abs(v[0] - g["t1_v"]).max() < 1e-12
+    im, wl, wr, Ep, wm = eng.get_cells(want_wm=True)
+    assert np.array_equal(im[0], g["t1_indx_m"])
+    assert np.abs(wm[0] - g["t1_weight_m"]).max() < 1e-13
+    assert np.abs(Ep[0] - g["t1_E"]).max() < 1e-12 * max(1.0, np.abs(g["t1_E"]).max())
+    if ctrl:
+        eng.step_coeffs(g["coeffs"][1:steps, None, :], steps - 1)
+    else:
+        eng.step_mesh(None, steps - 1)
+    x, v = eng.get_state()
+    assert np.abs(x[0] - g[f"t{steps}_x"]).max() < 1e-10 and np.abs(v[0] - g[f"t{steps}_v"]).max() < 1e-10
+    im, *_ = eng.get_cells(False, False)
+    assert np.array_equal(im[0], g[f"t{steps}_indx_m"])
+    d = eng.get_diag()[0]
+    assert abs(d[0] + d[1] * N / L - g["H"][steps]) < 1e-11 * g["H"][steps]
+    assert abs(d[1] * N / L - g["PE"][steps]) < 1e-10 * g["PE"][steps]
+    rho, k = eng.get_density_fixed()
+    assert sum(int(r) for r in rho.ravel()) == N * (1 << k)
+    assert eng.error_flags() == 0
+
+
+def test_tsc_through_pic_class(golden):
+    from pic_b200 import PIC
+    from pic_b200.dist import BumpOnTail
+    g = golden("bump_vb3_tsc")
+    np.random.seed(42)
+    dist = BumpOnTail(a=0.2, v0=3.0, sigma=1.0, n_samples=5000, L=50.0)
+    sim = PIC(N=5000, N_mesh=250, n0=1.0, L=50.0, dt=0.1, tmin=0.0, tmax=50.0, gamma=5.0, A=0.1, n_mode=2,
+              interpol="TSC", init_dist=dist)
+    for t in range(1, 6):
+        sim.update_state(None)
+        assert abs(sim.get_energy() - g["H"][t]) < 1e-12 * g["H"][t]
+    assert sim.indx_m.shape == (5000, 1) and sim.weight_m.shape == (5000, 1)
+    assert np.array_equal(sim.indx_l, np.mod(sim.indx_m - 1, 250))

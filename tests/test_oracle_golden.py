@@ -144,3 +144,26 @@ def test_prefix_field_equals_dense_field():
         _, Ed = O.field_dense(n, 1.0, L, M)
         Ep = O.field_prefix(n, 1.0, L, M)
         assert np.abs(Ed - Ep).max() < 1e-10 * max(1.0, np.abs(Ed).max())
+
+
+@pytest.mark.parametrize("name,steps,ctrl", [("bump_vb3_tsc", 40, False), ("twostream_tsc_ctrl", 20, True)])
+def test_tsc_interpolation(golden, name, steps, ctrl):
+    """interpol="TSC" (src/env/interpolate.py:22-44, run_wo_oc.py --interpol TSC)."""
+    g = golden(name)
+    p = params(g)
+    p.interpol = "TSC"
+    bc, bs = O.actuator_basis(p.L, p.N_mesh, 3)
+    for faithful, tol in ((True, 0.0), (False, 1e-11)):
+        x, v = g["t0_x"].copy(), g["t0_v"].copy()
+        for t in range(1, steps + 1):
+            e = None
+            if ctrl:
+                c = g["coeffs"][t - 1]
+                e = O.actuator_field(bc, bs, c[:3], c[3:])
+            o = O.step(x, v, p, e, faithful=faithful)
+            x, v = o["x"], o["v"]
+            if f"t{t}_x" in g.files:
+                assert np.abs(x - g[f"t{t}_x"]).max() <= tol and np.abs(v - g[f"t{t}_v"]).max() <= tol
+                assert np.array_equal(o["indx_m"], g[f"t{t}_indx_m"])
+                assert np.abs(o["E_mesh"] - g[f"t{t}_E_mesh"]).max() <= max(tol, 0.0) * 10 + (0 if faithful else 1e-12)
+        assert abs(O.hamiltonian(x, v, p, faithful=faithful) - g["H"][steps]) <= (0 if faithful else 1e-9 * g["H"][steps])
