@@ -373,3 +373,27 @@ def test_tsc_through_pic_class(golden):
         assert abs(sim.get_energy() - g["H"][t]) < 1e-12 * g["H"][t]
     assert sim.indx_m.shape == (5000, 1) and sim.weight_m.shape == (5000, 1)
     assert np.array_equal(sim.indx_l, np.mod(sim.indx_m - 1, 250))
+
+
+def test_zero_copy_views_for_the_policy():
+    """`views()` aliases the device buffers through __cuda_array_interface__: torch sees the particle arrays in
+    `get_state()` order without a copy (obs layout [env][x(0..N-1)], [env][v(0..N-1)])."""
+    import torch
+    from pic_b200 import BatchedPIC
+    from pic_b200.dist import TwoStream
+    B, N = 3, 5000
+    bp = BatchedPIC(B, N=N, N_mesh=250, L=50.0, dt=0.05, max_mode=3)
+    bp.reset_from_sampler(lambda: TwoStream(v0=3.0, sigma=1.0, n_samples=N, L=50.0), seed=1)
+    bp.step(np.zeros((B, 6)), n_steps=2)
+    vw = bp.views()
+    xt = torch.as_tensor(vw["x"], device="cuda")
+    vt = torch.as_tensor(vw["v"], device="cuda")
+    assert xt.shape == (B, N) and xt.dtype == torch.float64 and xt.stride(0) == vw["ld"]
+    st = bp.get_state()
+    assert np.array_equal(xt.cpu().numpy(), st[:, :N]) and np.array_equal(vt.cpu().numpy(), st[:, N:])
+    ptr0 = xt.data_ptr()
+    bp.step(np.zeros((B, 6)), n_steps=1)
+    assert torch.as_tensor(bp.views()["x"], device="cuda").data_ptr() == ptr0          # same buffer, updated in place
+    assert np.array_equal(xt.cpu().numpy(), bp.get_state()[:, :N])
+    d = torch.as_tensor(vw["diag"], device="cuda")
+    assert d.shape == (B, 6) and float(d[0, 1]) == bp.engine.get_diag()[0, 1]

@@ -49,3 +49,31 @@ def test_invariants_at_scale():
     assert eng.error_flags() == 0
     rho, k = eng.get_density_fixed()
     assert sum(int(r) for r in rho.ravel()) == N * (1 << k)
+
+
+def test_full_size_1e9_invariants():
+    """BASELINE config 5 at its full size (1e9 particles, 4096 cells) through size-independent properties: every
+    particle deposits exactly 2^k (integer density sums to N 2^k), sum(n) dx = n0 L, momentum is conserved without
+    control and the Hamiltonian drifts by < 1e-7 relative over 5 env steps."""
+    import torch
+    from pic_b200 import Engine
+    if torch.cuda.get_device_properties(0).total_memory < 60e9:
+        pytest.skip("needs > 60 GB of device memory")
+    N, M, L = 1_000_000_000, 4096, 50.0
+    dt = 2 / np.sqrt(N / L)
+    eng = Engine(N, M, L, dt, mode="streaming")
+    eng.sample_state("bump-on-tail", seed=42)
+    d0 = eng.get_diag()[0]
+    rho, k = eng.get_density_fixed()
+    assert k == 41 and sum(int(r) for r in rho.ravel()) == N * (1 << k)
+    n, E = eng.get_fields()
+    assert abs(n.sum() * (L / M) - L) < 1e-9 and abs(n.mean() - 1.0) < 1e-12
+    eng.step_mesh(None, 5)
+    tr = eng.get_trace(5)[:, 0, :]
+    H0 = d0[0] + d0[1] * N / L
+    assert np.max(np.abs(tr[:, 0] + tr[:, 1] * N / L - H0)) / H0 < 1e-7
+    assert np.max(np.abs(tr[:, 2] - d0[2])) < 1e-6 * np.sqrt(N)
+    rho, k = eng.get_density_fixed()
+    assert sum(int(r) for r in rho.ravel()) == N * (1 << k)
+    assert eng.error_flags() == 0
+    eng.close()
