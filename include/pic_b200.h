@@ -161,8 +161,10 @@ int pic_comm_init(pic_handle* h, void* nccl_comm, int32_t rank, int32_t world_si
 int pic_nccl_unique_id(char* out128);
 int pic_comm_init_rank(pic_handle* h, const char* id128, int32_t rank, int32_t world_size);
 /* Alternative used when the collective is driven from the host side (e.g. torch.distributed): run sub-stage
- * `stage` (0..3, or 4 = finalize, -1 = init deposit) only and leave the local density in the buffer returned by
- * pic_stage_density (device pointer, [n_envs][n_mesh] uint64) for the caller to all-reduce in place. */
+ * `stage` (1..3, 4 = finalize, -1 = init deposit; 0 is a no-op because the drift-only stage 0 of a step is executed
+ * ahead of time by stage 3 / init of the state it starts from) and leave the local density in the buffer returned
+ * by pic_stage_density for the caller to all-reduce in place: [n_envs][n_mesh] uint64 for stages 1 and 2,
+ * 2 x [n_envs][n_mesh] (state density followed by the next step's stage-0 density) for stages 3 and -1. */
 int pic_run_stage(pic_handle* h, int32_t stage);
 int pic_stage_density(pic_handle* h, int32_t stage, uint64_t** rho_dev);
 int pic_set_stage_actuation(pic_handle* h, const double* E_ext_dev, const double* coeffs_dev);

@@ -77,7 +77,9 @@ struct pic_handle {
 
     // device buffers
     void *x = nullptr, *v = nullptr;
-    unsigned long long* rho[4] = {nullptr, nullptr, nullptr, nullptr};   // W0, W1, W2, S
+    void* xp = nullptr;                             // streaming: x1 = state + c0 v dt of the NEXT step (stage 0 done ahead)
+    unsigned long long* rho_block = nullptr;        // one allocation [S][W0][W1][W2], each n_envs * M
+    unsigned long long* rho[4] = {nullptr, nullptr, nullptr, nullptr};   // W0, W1, W2, S (S and W0 are adjacent)
     double *n = nullptr, *E = nullptr, *diag = nullptr, *vsum = nullptr, *partial = nullptr;
     double *ext = nullptr, *coeffs = nullptr, *bcos = nullptr, *bsin = nullptr, *trace = nullptr;
     double *tw_cos = nullptr, *tw_sin = nullptr, *modes = nullptr, *mode_trace = nullptr;   // spectral read-out
@@ -137,8 +139,8 @@ size_t smem_for(const pic_handle* h) {
     if (h->resident)
         return h->f32 ? resident_smem_bytes<float>(h->M, h->threads, h->N, h->ip)
                       : resident_smem_bytes<double>(h->M, h->threads, h->N, h->ip);
-    return h->f32 ? smem_plan_bytes<float>(h->M, h->threads, false, h->ip)
-                  : smem_plan_bytes<double>(h->M, h->threads, false, h->ip);
+    return h->f32 ? smem_plan_bytes<float>(h->M, h->threads, false, h->ip, true)      // two histograms in the
+                  : smem_plan_bytes<double>(h->M, h->threads, false, h->ip, true);    // stage-3 / init kernels
 }
 
 int configure_launch(pic_handle* h) {
@@ -154,7 +156,7 @@ int configure_launch(pic_handle* h) {
         return PIC_OK;
     }
     int occ_min = 1 << 30;
-    for (int mode = 0; mode < 4; ++mode) {
+    for (int mode = MODE_KICK; mode <= MODE_INIT; ++mode) {
         const void* k = stream_kernel(h, mode);
         if (!k) return fail(h, PIC_EUNSUPPORTED, "no streaming kernel variant for threads=" + std::to_string(h->threads) +
                             " unroll=" + std::to_string(h->per_thread));
@@ -323,25 +325,30 @@ int run_stage(pic_handle* h, int stage, const double* ext, const double* coeffs,
         }
         return PIC_OK;
     }
+    if (stage == 0) return PIC_OK;      // stage 0 (pure drift) was executed ahead of time by the previous stage 3 / init
     StreamArgs a{};
     a.mc = h->mc; a.x = h->x; a.v = h->v; a.N = h->N; a.ld = h->ld;
     a.act.ext = ext; a.act.coeffs = coeffs; a.act.bcos = h->bcos; a.act.bsin = h->bsin; a.act.m = h->m;
-    a.partial = h->partial; a.err = h->err;
-    int mode, out;
+    a.partial = h->partial; a.err = h->err; a.c_next = h->cs[0];
+    const size_t sz = (size_t)h->M * h->n_envs;
+    int mode;
+    unsigned long long* reduce = nullptr; size_t reduce_count = sz;
     switch (stage) {
-        case -1: mode = MODE_INIT; a.rho_out = h->rho[3]; out = 3; a.c = 0; a.d = 0; break;
-        case 0: mode = MODE_DRIFT; a.rho_out = h->rho[0]; a.rho_zero = h->rho[3]; out = 0; break;
-        case 1: mode = MODE_KICK; a.rho_in = h->rho[0]; a.rho_out = h->rho[1]; out = 1; break;
-        case 2: mode = MODE_KICK; a.rho_in = h->rho[1]; a.rho_out = h->rho[2]; a.rho_zero = h->rho[0]; out = 2; break;
-        case 3: mode = MODE_FINAL; a.rho_in = h->rho[2]; a.rho_out = h->rho[3]; a.rho_zero = h->rho[1]; out = 3; break;
+        case -1: mode = MODE_INIT; a.rho_out = h->rho[3]; a.rho_next = h->rho[0]; a.x_next = h->xp; a.c = 0; a.d = 0;
+                 reduce = h->rho[3]; reduce_count = 2 * sz; break;
+        case 1: mode = MODE_KICK; a.x_in = h->xp; a.rho_in = h->rho[0]; a.rho_out = h->rho[1]; a.rho_zero = h->rho[3];
+                reduce = h->rho[1]; break;
+        case 2: mode = MODE_KICK; a.rho_in = h->rho[1]; a.rho_out = h->rho[2]; a.rho_zero = h->rho[0]; reduce = h->rho[2]; break;
+        case 3: mode = MODE_FINAL; a.rho_in = h->rho[2]; a.rho_out = h->rho[3]; a.rho_next = h->rho[0]; a.x_next = h->xp;
+                a.rho_zero = h->rho[1]; reduce = h->rho[3]; reduce_count = 2 * sz; break;
         default: return fail(h, PIC_EINVAL, "stage must be -1..4");
     }
-    if (stage >= 0) { a.c = h->cs[stage]; a.d = h->ds[stage]; }
-    if (stage == -1) CK(h, cudaMemsetAsync(h->rho[3], 0, sizeof(unsigned long long) * (size_t)h->M * h->n_envs, h->stream));
+    if (stage >= 1) { a.c = h->cs[stage]; a.d = h->ds[stage]; }
+    if (stage == -1) CK(h, cudaMemsetAsync(h->rho_block, 0, sizeof(unsigned long long) * 4 * sz, h->stream));
     void* args[] = {&a};
     CK(h, cudaLaunchKernel(stream_kernel(h, mode), dim3(h->grid_x, h->n_envs), dim3(h->threads), args, h->smem, h->stream));
     h->launches++;
-    return allreduce_u64(h, h->rho[out], (size_t)h->M * h->n_envs);
+    return allreduce_u64(h, reduce, reduce_count);     // S and W0 are adjacent: one all-reduce covers both
 }
 
 int ensure_trace(pic_handle* h, int n_steps) {
@@ -395,7 +402,7 @@ int step_device(pic_handle* h, const double* ext, const double* coeffs, int n_st
     if (h->resident) return launch_resident(h, n_steps, ext, coeffs);
     for (int s = 0; s < n_steps; ++s) {
         const double* cf = coeffs ? coeffs + (size_t)s * h->n_envs * 2 * h->m : nullptr;
-        for (int st = 0; st < 4; ++st) if ((rc = run_stage(h, st, ext, cf, nullptr))) return rc;
+        for (int st = 1; st < 4; ++st) if ((rc = run_stage(h, st, ext, cf, nullptr))) return rc;
         if ((rc = run_stage(h, 4, nullptr, cf, h->trace + (size_t)s * h->n_envs * DIAG_N))) return rc;
         if (h->n_modes > 0)
             CK(h, cudaMemcpyAsync(h->mode_trace + (size_t)s * h->n_envs * 2 * h->n_modes, h->modes,
@@ -516,7 +523,11 @@ int pic_create(const pic_config* cfg, pic_handle** out) {
 
     size_t pbytes = (size_t)h->ld * h->n_envs * h->esize, mbytes = sizeof(double) * (size_t)h->M * h->n_envs;
     bool okm = cudaMalloc(&h->x, pbytes) == cudaSuccess && cudaMalloc(&h->v, pbytes) == cudaSuccess;
-    for (int i = 0; i < 4 && okm; ++i) okm = cudaMalloc(&h->rho[i], mbytes) == cudaSuccess;
+    okm = okm && cudaMalloc(&h->rho_block, 4 * mbytes) == cudaSuccess;
+    if (okm) {
+        const size_t sz = (size_t)h->M * h->n_envs;
+        h->rho[3] = h->rho_block; h->rho[0] = h->rho_block + sz; h->rho[1] = h->rho_block + 2 * sz; h->rho[2] = h->rho_block + 3 * sz;
+    }
     okm = okm && cudaMalloc(&h->n, mbytes) == cudaSuccess && cudaMalloc(&h->E, mbytes) == cudaSuccess &&
           cudaMalloc(&h->ext, mbytes) == cudaSuccess &&
           cudaMalloc(&h->diag, sizeof(double) * DIAG_N * h->n_envs) == cudaSuccess &&
@@ -526,9 +537,13 @@ int pic_create(const pic_config* cfg, pic_handle** out) {
         okm = cudaMalloc(&h->bcos, sizeof(double) * (size_t)h->M * h->m) == cudaSuccess &&
               cudaMalloc(&h->bsin, sizeof(double) * (size_t)h->M * h->m) == cudaSuccess;
     if (!okm) { std::string e = cudaGetErrorString(cudaGetLastError()); pic_destroy(h); return fail(nullptr, PIC_ENOMEM, "cudaMalloc: " + e); }
+    if (okm && !h->resident) {
+        if (cudaMalloc(&h->xp, pbytes) != cudaSuccess) { pic_destroy(h); return fail(nullptr, PIC_ENOMEM, "cudaMalloc of the stage-0 buffer"); }
+        cudaMemsetAsync(h->xp, 0, pbytes, h->stream);
+    }
     cudaMemsetAsync(h->x, 0, pbytes, h->stream);
     cudaMemsetAsync(h->v, 0, pbytes, h->stream);
-    for (int i = 0; i < 4; ++i) cudaMemsetAsync(h->rho[i], 0, mbytes, h->stream);
+    cudaMemsetAsync(h->rho_block, 0, 4 * mbytes, h->stream);
     cudaMemsetAsync(h->diag, 0, sizeof(double) * DIAG_N * h->n_envs, h->stream);
     cudaMemsetAsync(h->vsum, 0, sizeof(double) * 2 * h->n_envs, h->stream);
     cudaMemsetAsync(h->err, 0, sizeof(unsigned), h->stream);
@@ -543,7 +558,7 @@ int pic_destroy(pic_handle* h) {
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
     if (h->own_comm && h->comm && nccl_api().destroy) nccl_api().destroy(h->comm);
-    void* bufs[] = {h->x, h->v, h->rho[0], h->rho[1], h->rho[2], h->rho[3], h->n, h->E, h->diag, h->vsum, h->partial,
+    void* bufs[] = {h->x, h->v, h->xp, h->rho_block, h->n, h->E, h->diag, h->vsum, h->partial,
                     h->ext, h->coeffs, h->bcos, h->bsin, h->trace, h->stage64, h->err, h->tw_cos, h->tw_sin, h->modes,
                     h->mode_trace, h->ph_counts, h->ph_feq, h->ph_kl};
     for (void* b : bufs) if (b) cudaFree(b);
@@ -962,7 +977,7 @@ int pic_run_stage(pic_handle* h, int32_t stage) {
 
 int pic_stage_density(pic_handle* h, int32_t stage, uint64_t** rho_dev) {
     if (!h || !rho_dev) return PIC_EINVAL;
-    int idx = stage == -1 ? 3 : stage;
+    int idx = stage == -1 ? 3 : stage;          // -1 and 3: [S][W0], 2 * n_envs * n_mesh values (state + next stage 0)
     if (idx < 0 || idx > 3) return fail(h, PIC_EINVAL, "stage must be -1..3");
     *rho_dev = (uint64_t*)h->rho[idx];
     return PIC_OK;

@@ -684,6 +684,28 @@ __device__ __forceinline__ void particle_substage(R& x, R& v, H& hist, const typ
     else deposit_one<IP>(hist, il, Wa, Wb, mc.fix_one);
 }
 
+// Stage 0 of the NEXT env step, done while the particle is still in registers: the first Yoshida sub-stage has d = 0
+// (integration.py:71), i.e. it is a pure drift x1 = x + (c0 v) dt of the state the current step just produced and
+// depends on nothing else -- not on the next action, not on any field.  Doing it here (and depositing x1 into a
+// second histogram) removes one whole pass over the particles from every env step: 104 instead of 120 bytes per
+// particle-step.  x1 is returned UNWRAPPED, exactly as the reference carries positions between sub-stages.
+template <typename R, int IP, bool EXACT_W, bool FULL_WARP, typename H>
+__device__ __forceinline__ R next_stage0(R x_state, R v, H& hist_next, R c0, const PartConst<R>& c, const MeshConst& mc,
+                                         unsigned& err) {
+    const R x1 = RT<R>::add(x_state, RT<R>::mul(RT<R>::mul(c0, v), c.dt));
+    int il; R f; long long Wa, Wb;
+    const bool slow = fast_cell<R>(x1, c, mc.M, il, f);
+    deposit_weights<R, IP, EXACT_W>(x1, f, c, mc, Wa, Wb);
+    if (__builtin_expect(slow, 0)) {
+        const R xw = wrap_pos<R>(x1, c, err);
+        il = cell_index<R>(xw, c, mc.M, f, err);
+        deposit_weights<R, IP, EXACT_W>(xw, f, c, mc, Wa, Wb);
+    }
+    if (FULL_WARP) deposit_full_warp<IP>(hist_next, il, Wa, Wb, mc.fix_one);
+    else deposit_one<IP>(hist_next, il, Wa, Wb, mc.fix_one);
+    return x1;
+}
+
 // streaming loads / stores (no reuse: keep the particle stream out of L1, evict-first in L2)
 template <typename V> __device__ __forceinline__ V ld_stream(const V* p) { return __ldcs(p); }
 template <typename V> __device__ __forceinline__ void st_stream(V* p, const V& v) { __stcs(p, v); }

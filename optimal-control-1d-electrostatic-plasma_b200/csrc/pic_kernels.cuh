@@ -17,10 +17,12 @@
 
 namespace pic {
 
-constexpr int MODE_DRIFT = 0;   // stage 0: d == 0, drift only                 (integration.py:71)
+// Sub-stages of the streaming mode.  Stage 0 of every step (d == 0, a pure drift, integration.py:71) is executed
+// ahead of time by the kernel that produces the state it starts from (MODE_FINAL / MODE_INIT, see next_stage0), so an
+// env step is three passes over the particles: KICK, KICK, FINAL.
 constexpr int MODE_KICK = 1;    // stages 1,2: kick + drift                    (integration.py:72-73)
-constexpr int MODE_FINAL = 2;   // stage 3: kick + drift + state wrap (pic.py:139) + kinetic sums
-constexpr int MODE_INIT = 3;    // no motion: wrap in place + deposit          (pic.py:76 / util.py:51)
+constexpr int MODE_FINAL = 2;   // stage 3: kick + drift + state wrap (pic.py:139) + kinetic sums, then stage 0 of the next step
+constexpr int MODE_INIT = 3;    // no motion: wrap in place + deposit (pic.py:76 / util.py:51), then stage 0 of the next step
 
 struct ActuatorArgs {
     const double* ext;       // mesh mode: [n_envs][M] (device) or nullptr
@@ -32,14 +34,18 @@ struct ActuatorArgs {
 
 struct StreamArgs {
     MeshConst mc;
-    void* x;                           // [n_envs][ld] particle positions (R)
+    void* x;                           // [n_envs][ld] particle positions (R): read (unless x_in) and written
     void* v;                           // [n_envs][ld] particle velocities (R)
+    const void* x_in;                  // nullptr, or where this sub-stage reads its positions (stage 1: the drifted x1)
+    void* x_next;                      // MODE_FINAL / MODE_INIT: receives x1 = state + c0 v dt of the next step
     long long N, ld;
     const unsigned long long* rho_in;  // [n_envs][M] density of the previous sub-stage (MODE_KICK / MODE_FINAL)
     unsigned long long* rho_out;       // [n_envs][M] must be zero on entry
+    unsigned long long* rho_next;      // MODE_FINAL / MODE_INIT: density of x1 (must be zero on entry)
     unsigned long long* rho_zero;      // [n_envs][M] or nullptr: cleared for a later sub-stage
     ActuatorArgs act;
     double c, d;
+    double c_next;                     // c0 of the Yoshida scheme
     double* partial;                   // [n_envs][gridDim.x][2] per-CTA sum v^2, sum v (MODE_FINAL / MODE_INIT)
     unsigned* err;
 };
@@ -52,19 +58,22 @@ __host__ __device__ constexpr size_t hist_region_bytes(int M, int ip) {      // 
 }
 
 template <typename R>
-__host__ __device__ constexpr size_t smem_plan_bytes(int M, int threads, bool separate_d, int ip = IP_CIC) {
+__host__ __device__ constexpr size_t smem_plan_bytes(int M, int threads, bool separate_d, int ip = IP_CIC,
+                                                     bool second_hist = false) {
     return (size_t)M * 2 * sizeof(R)                 // gather pair table
-         + hist_region_bytes(M, ip)                  // histogram
+         + hist_region_bytes(M, ip) * (second_hist ? 2 : 1)   // histogram(s)
          + (separate_d ? (size_t)M * 8 : 0)          // D_s
          + (size_t)(field_scratch_doubles(threads) + threads / 32 + 2) * 8;   // field / reduction scratch
 }
 
 template <typename R>
 struct SmemLayout {
-    void* hist; typename PairT<R>::type* E_s; double* D_s; double* red;
-    __device__ __forceinline__ SmemLayout(unsigned char* base, int M, bool separate_d, int ip = IP_CIC) {
+    void* hist; void* hist2; typename PairT<R>::type* E_s; double* D_s; double* red;
+    __device__ __forceinline__ SmemLayout(unsigned char* base, int M, bool separate_d, int ip = IP_CIC,
+                                          bool second_hist = false) {
         E_s = (typename PairT<R>::type*)base;   base += (size_t)M * 2 * sizeof(R);
         hist = base;                            base += hist_region_bytes(M, ip);
+        hist2 = base;                           if (second_hist) base += hist_region_bytes(M, ip);
         D_s = separate_d ? (double*)base : (double*)hist;
         if (separate_d) base += (size_t)M * 8;
         red = (double*)base;
@@ -97,11 +106,14 @@ __global__ void __launch_bounds__(THREADS) push_stream_kernel(const StreamArgs a
     extern __shared__ __align__(16) unsigned char smem_raw[];
     using V = typename RT<R>::vec;
     constexpr int VEC = RT<R>::VEC;
+    static_assert(MODE == MODE_KICK || MODE == MODE_FINAL || MODE == MODE_INIT, "unknown sub-stage");
     constexpr bool KICK = (MODE == MODE_KICK || MODE == MODE_FINAL);
-    constexpr bool SUMS = (MODE == MODE_FINAL || MODE == MODE_INIT);
+    constexpr bool SUMS = (MODE == MODE_FINAL || MODE == MODE_INIT);      // these also run stage 0 of the next step
     const int tid = threadIdx.x, env = blockIdx.y, M = a.mc.M;
-    SmemLayout<R> sm(smem_raw, M, false, IP);
-    typename HistSel<DEP, IP>::type hist; hist.init(sm.hist, M);
+    SmemLayout<R> sm(smem_raw, M, false, IP, SUMS);
+    using H = typename HistSel<DEP, IP>::type;
+    H hist; hist.init(sm.hist, M);
+    H hist_next; hist_next.init(sm.hist2, M);
     const PartConst<R> pc = make_part_const<R>(a.mc);
 
     if (KICK) {                                         // D_s aliases the histogram: solve first, then clear
@@ -110,6 +122,7 @@ __global__ void __launch_bounds__(THREADS) push_stream_kernel(const StreamArgs a
         block_field<R, THREADS>(rho, sm.E_s, sm.D_s, sm.red, a.mc, ext, nullptr, nullptr, 0.0, 0.0, [] {});
     }
     hist.zero(tid, THREADS);
+    if (SUMS) hist_next.zero(tid, THREADS);
     __syncthreads();
     if (a.rho_zero) {
         unsigned long long* z = a.rho_zero + (size_t)env * M;
@@ -118,26 +131,36 @@ __global__ void __launch_bounds__(THREADS) push_stream_kernel(const StreamArgs a
 
     R* xe = (R*)a.x + (size_t)env * a.ld;
     R* ve = (R*)a.v + (size_t)env * a.ld;
+    const R* xie = a.x_in ? (const R*)a.x_in + (size_t)env * a.ld : xe;
+    R* xne = SUMS ? (R*)a.x_next + (size_t)env * a.ld : nullptr;
     V* xv = (V*)xe;
     V* vv = (V*)ve;
+    const V* xiv = (const V*)xie;
+    V* xnv = (V*)xne;
     const long long nvec = a.N / VEC;
-    const R cc = (R)a.c, dd = (R)a.d;
+    const R cc = (R)a.c, dd = (R)a.d, c0 = (R)a.c_next;
     unsigned err = 0;
     double s2 = 0.0, s1 = 0.0;
 
-    auto one = [&](R& x, R& v, auto full_warp) {
-        particle_substage<R, IP, KICK, MODE != MODE_INIT, EXACT_W, decltype(full_warp)::value>(
-            x, v, hist, sm.E_s, cc, dd, pc, a.mc, SUMS, err);
-        if (SUMS) { s2 += (double)v * (double)v; s1 += (double)v; }
+    // x, v: updated in place; xn: x1 of the next step (MODE_FINAL / MODE_INIT only)
+    auto one = [&](R& x, R& v, R& xn, auto full_warp) {
+        constexpr bool FW = decltype(full_warp)::value;
+        particle_substage<R, IP, KICK, MODE != MODE_INIT, EXACT_W, FW>(x, v, hist, sm.E_s, cc, dd, pc, a.mc, SUMS, err);
+        if (SUMS) {
+            s2 += (double)v * (double)v; s1 += (double)v;
+            xn = next_stage0<R, IP, EXACT_W, FW>(x, v, hist_next, c0, pc, a.mc, err);
+        }
     };
     auto vec_pair = [&](long long i, auto full_warp) {      // one 16-byte vector of x and of v
-        V xq = ld_stream(xv + i), vq = ld_stream(vv + i);
+        V xq = ld_stream(xiv + i), vq = ld_stream(vv + i), xnq;
         R* px = reinterpret_cast<R*>(&xq);
         R* pv = reinterpret_cast<R*>(&vq);
+        R* pn = reinterpret_cast<R*>(&xnq);
 #pragma unroll
-        for (int e = 0; e < VEC; ++e) one(px[e], pv[e], full_warp);
+        for (int e = 0; e < VEC; ++e) one(px[e], pv[e], pn[e], full_warp);
         st_stream(xv + i, xq);
         if (KICK) st_stream(vv + i, vq);
+        if (SUMS) st_stream(xnv + i, xnq);
     };
 
     // full tiles: every lane of every warp has work, so warp-wide primitives may use the full mask
@@ -147,15 +170,18 @@ __global__ void __launch_bounds__(THREADS) push_stream_kernel(const StreamArgs a
         const long long base = tile * TILE + tid;
         V xs[UNROLL], vs[UNROLL];
 #pragma unroll
-        for (int u = 0; u < UNROLL; ++u) { xs[u] = ld_stream(xv + base + u * THREADS); vs[u] = ld_stream(vv + base + u * THREADS); }
+        for (int u = 0; u < UNROLL; ++u) { xs[u] = ld_stream(xiv + base + u * THREADS); vs[u] = ld_stream(vv + base + u * THREADS); }
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u) {
+            V xnq;
             R* px = reinterpret_cast<R*>(&xs[u]);
             R* pv = reinterpret_cast<R*>(&vs[u]);
+            R* pn = reinterpret_cast<R*>(&xnq);
 #pragma unroll
-            for (int e = 0; e < VEC; ++e) one(px[e], pv[e], std::true_type{});
+            for (int e = 0; e < VEC; ++e) one(px[e], pv[e], pn[e], std::true_type{});
             st_stream(xv + base + u * THREADS, xs[u]);
             if (KICK) st_stream(vv + base + u * THREADS, vs[u]);
+            if (SUMS) st_stream(xnv + base + u * THREADS, xnq);
         }
     }
     // ragged remainder (< one tile of vectors) and the scalar tail (N not a multiple of the vector width)
@@ -165,10 +191,11 @@ __global__ void __launch_bounds__(THREADS) push_stream_kernel(const StreamArgs a
     if (blockIdx.x == 0) {
         long long i = nvec * VEC + tid;
         if (i < a.N) {
-            R x = xe[i], v = ve[i];
-            one(x, v, std::false_type{});
+            R x = xie[i], v = ve[i], xn = (R)0;
+            one(x, v, xn, std::false_type{});
             xe[i] = x;
             if (KICK) ve[i] = v;
+            if (SUMS) xne[i] = xn;
         }
     }
     __syncthreads();
@@ -180,6 +207,11 @@ __global__ void __launch_bounds__(THREADS) push_stream_kernel(const StreamArgs a
         if (val) atomicAdd(out + j, val);
     }
     if (SUMS) {
+        unsigned long long* outn = a.rho_next + (size_t)env * M;
+        for (int j = tid; j < M; j += THREADS) {
+            unsigned long long val = hist_next.get(j, a.mc.fix_one);
+            if (val) atomicAdd(outn + j, val);
+        }
         double t2 = block_sum<THREADS>(s2, sm.red);
         double t1 = block_sum<THREADS>(s1, sm.red);
         if (tid == 0) {

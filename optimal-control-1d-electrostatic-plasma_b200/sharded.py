@@ -102,10 +102,11 @@ class ShardedPIC:
 
     # ---- collective="torch": sub-stages driven from here
     def _rho_tensor(self, stage):
+        """int64 view of the density a sub-stage left behind; stages 3 and -1 leave two (state + next stage 0)."""
         import torch
         ptr = self.engine.stage_density_ptr(stage)
-        return torch.as_tensor(DeviceArray(ptr, (self.N_mesh,), "<i8", None, self.engine),
-                               device="cuda:%d" % self.engine.device)
+        n = self.N_mesh * (2 if stage in (3, -1) else 1)
+        return torch.as_tensor(DeviceArray(ptr, (n,), "<i8", None, self.engine), device="cuda:%d" % self.engine.device)
 
     def _set_state_staged(self, x, v):
         import torch
@@ -130,7 +131,7 @@ class ShardedPIC:
             self.engine.set_stage_actuation(self._ext_dev.data_ptr(), None)
         else:
             self.engine.set_stage_actuation(None, None)
-        for st in range(4):
+        for st in (1, 2, 3):                 # stage 0 of this step was done by the previous stage 3 / init
             self.engine.run_stage(st)
             allreduce_fixed_density(self._rho_tensor(st), self.group)
         self.engine.run_stage(4)

@@ -2,7 +2,7 @@
 
 Times every streaming sub-stage kernel (CUDA events on the launching stream) for a grid of launch shapes and
 deposit flavours, and the resident batched kernel for its shapes.  Prints achieved algorithmic GB/s
-(24 B/particle for stage 0, 32 B for stages 1-3) and writes gpurun_out/kbench.json.
+(32 B/particle for stages 1-2, 40 B for stage 3 which also runs stage 0 of the next step) and writes gpurun_out/kbench.json.
 """
 import argparse
 import json
@@ -17,16 +17,16 @@ import pic_b200  # noqa: E402
 
 
 def time_stages(eng, reps):
-    ev = [[(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(5)]
+    ev = [[(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(4)]
           for _ in range(reps)]
-    for st in range(5):
+    for st in (1, 2, 3, 4):
         eng.run_stage(st)           # warm-up step
     torch.cuda.synchronize()
     for r in range(reps):
-        for st in range(5):
-            ev[r][st][0].record()
+        for k, st in enumerate((1, 2, 3, 4)):
+            ev[r][k][0].record()
             eng.run_stage(st)
-            ev[r][st][1].record()
+            ev[r][k][1].record()
     torch.cuda.synchronize()
     t = np.array([[a.elapsed_time(b) for a, b in row] for row in ev])   # ms
     return t.mean(axis=0), t.min(axis=0)
@@ -94,8 +94,8 @@ def main():
                         eng.set_state_device(xin.data_ptr(), vin.data_ptr())
                         mean, best = time_stages(eng, a.reps)
                         esz = 4 if prec == "f32" else 8
-                        bytes_ = np.array([3, 4, 4, 4]) * esz * N
-                        gbs = bytes_ / (mean[:4] * 1e-3) / 1e9
+                        bytes_ = np.array([4, 4, 5]) * esz * N          # kick, kick, final + next stage 0
+                        gbs = bytes_ / (mean[:3] * 1e-3) / 1e9
                         info = eng.launch_info()
                         rec = dict(prec=prec, order=oname, dep=dep, threads=th, unroll=un, occ_req=occ, grid=info["grid_x"],
                                    ms=mean.tolist(), ms_min=best.tolist(), gbs=gbs.tolist(),
