@@ -312,7 +312,7 @@ def run_gpu_arm(args):
                              device=local)
         act = pic_b200.E_field(L_BOX, 250, 3)
         bp.set_actuator_basis(act.basis_cos, act.basis_sin)
-        bp.sample_state("bump-on-tail", seed=7, n_global=5000)
+        bp.sample_state("bump-on-tail", seed=7, n_global=5000, env_offset=lo)
         T = 10
         coeffs = torch.rand(T, hi - lo, 6, dtype=torch.float64, device=dev) * 2 - 1
         for _ in range(10):

@@ -84,9 +84,10 @@ int pic_set_state(pic_handle* h, const double* x, const double* v);
 int pic_set_state_device(pic_handle* h, const void* x_dev, const void* v_dev);   /* device precision, same layout */
 /* Device-side replacement of the host samplers (src/env/dist.py) + perturbation (pic.py:68) + pic_set_state's
  * field build: kind 0 = bump-on-tail(a, v0, sigma), 1 = two-stream(v0, sigma).  Philox, counter = global particle
- * index, so shards of one env (global_offset, n_global) draw disjoint pieces of the same population. */
+ * index, so shards of one env (global_offset, n_global) draw disjoint pieces of the same population; env_offset is
+ * the global index of this handle's first env (env-sharded batches draw the same envs as the unsharded batch). */
 int pic_sample_state(pic_handle* h, int32_t kind, double a, double v0, double sigma, double A, int32_t n_mode,
-                     uint64_t seed, int64_t global_offset, int64_t n_global);
+                     uint64_t seed, int64_t global_offset, int64_t n_global, int64_t env_offset);
 /* PIC.get_state / .x / .v (pic.py:165-167): copies to host float64 and synchronises. */
 int pic_get_state(pic_handle* h, double* x, double* v);
 /* .n, .E_mesh (pic.py:101,117): [n_envs][n_mesh] each; either pointer may be NULL. */

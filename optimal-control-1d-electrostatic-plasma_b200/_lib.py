@@ -46,7 +46,7 @@ SIGNATURES = {
     "pic_set_state": (C.c_int, [_H, C.c_void_p, C.c_void_p]),
     "pic_set_state_device": (C.c_int, [_H, C.c_void_p, C.c_void_p]),
     "pic_sample_state": (C.c_int, [_H, C.c_int32, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int32,
-                                   C.c_uint64, C.c_int64, C.c_int64]),
+                                   C.c_uint64, C.c_int64, C.c_int64, C.c_int64]),
     "pic_get_state": (C.c_int, [_H, C.c_void_p, C.c_void_p]),
     "pic_get_fields": (C.c_int, [_H, C.c_void_p, C.c_void_p]),
     "pic_get_density_fixed": (C.c_int, [_H, C.c_void_p, C.POINTER(C.c_int32)]),
@@ -93,6 +93,8 @@ def load(build_if_missing=True):
     if _lib is not None:
         return _lib
     path = _build.LIB
+    if os.environ.get("PIC_LIB_PATH"):                 # experiments: a differently built library, used as is
+        path, build_if_missing = os.environ["PIC_LIB_PATH"], False
     if build_if_missing and (_build.needs_build() if os.path.isdir(_build.CSRC) else not os.path.exists(path)):
         try:
             _build.build_library(verbose=False)

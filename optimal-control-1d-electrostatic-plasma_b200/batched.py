@@ -72,6 +72,22 @@ class BatchedPIC:
         self.set_state(xs, vs)
         return xs, vs
 
+    def reset(self, kind: str = "bump-on-tail", a: float = 0.2, v0: float = 3.0, sigma: float = 1.0, A: float = 0.1,
+              n_mode: int = 2, seed: int = 42):
+        """`PIC.reinit()` for every env at once, entirely on the device: env e (global index) draws its own Philox
+        stream of the reference's distribution (src/env/dist.py) followed by the perturbation of pic.py:68."""
+        self.engine.sample_state(kind, a=a, v0=v0, sigma=sigma, A=A, n_mode=n_mode, seed=seed, n_global=self.N,
+                                 env_offset=self.env_lo)
+        return self.observe()
+
+    def observe(self):
+        """Zero-copy observation for a device-side policy: dict of torch CUDA tensors aliasing the env state --
+        x, v of shape (n_envs_local, N) in `get_state()` order, plus the per-env diagnostics (n_envs_local, 6)."""
+        import torch
+        vw = self.engine.views()
+        dev = "cuda:%d" % self.engine.device
+        return {k: torch.as_tensor(vw[k], device=dev) for k in ("x", "v", "diag", "E_mesh", "n")}
+
     def get_state(self):
         """(n_envs_local, 2N): row e is `PIC.get_state()` of env e flattened (x then v)."""
         x, v = self.engine.get_state()

@@ -237,17 +237,17 @@ __global__ void cells_kernel(const R* __restrict__ x, long long N, long long ld,
 // reference's proposal range |v| <= 10, x uniform on [0, L)), same deterministic split of the particle index range
 // between the populations, followed by the velocity perturbation of src/env/pic.py:68.  Statistical, not bitwise,
 // parity with the host sampler.  Particle i of env e uses Philox subsequence (e * n_global + global index), so the
-// result does not depend on the launch shape or on how particles are sharded over ranks.
+// result does not depend on the launch shape or on how particles (or envs: env_offset) are sharded over ranks.
 template <typename R>
 __global__ void sample_kernel(R* __restrict__ x, R* __restrict__ v, long long N, long long ld, long long offset,
                               long long n_global, int kind, double a, double v0, double sigma, double A, int n_mode,
-                              double L, unsigned long long seed) {
+                              double L, unsigned long long seed, long long env_offset) {
     const int env = blockIdx.y;
     const long long n_first = kind == 0 ? (long long)((double)n_global * (1.0 / (1.0 + a))) : n_global / 2;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (long long)gridDim.x * blockDim.x) {
         const long long g = offset + i;
         curandStatePhilox4_32_10_t st;
-        curand_init(seed, (unsigned long long)env * (unsigned long long)n_global + (unsigned long long)g, 0, &st);
+        curand_init(seed, (unsigned long long)(env_offset + env) * (unsigned long long)n_global + (unsigned long long)g, 0, &st);
         double mean, sd;
         if (kind == 0) { mean = g < n_first ? 0.0 : v0; sd = g < n_first ? 1.0 : sigma; }   // bump-on-tail
         else           { mean = g < n_first ? v0 : -v0; sd = sigma; }                      // two-stream
@@ -634,7 +634,7 @@ int pic_set_state(pic_handle* h, const double* x, const double* v) {
 }
 
 int pic_sample_state(pic_handle* h, int32_t kind, double a, double v0, double sigma, double A, int32_t n_mode,
-                     uint64_t seed, int64_t global_offset, int64_t n_global) {
+                     uint64_t seed, int64_t global_offset, int64_t n_global, int64_t env_offset) {
     if (!h) return PIC_EINVAL;
     if (kind != 0 && kind != 1) return fail(h, PIC_EINVAL, "kind: 0 = bump-on-tail, 1 = two-stream");
     if (n_global <= 0) n_global = h->Ntotal;
@@ -642,9 +642,9 @@ int pic_sample_state(pic_handle* h, int32_t kind, double a, double v0, double si
     long long gx = (h->N + 255) / 256;
     dim3 grid((unsigned)(gx < 65535 ? gx : 65535), h->n_envs);
     if (h->f32) sample_kernel<float><<<grid, 256, 0, h->stream>>>((float*)h->x, (float*)h->v, h->N, h->ld, global_offset,
-                                                                  n_global, kind, a, v0, sigma, A, n_mode, h->mc.L, seed);
+                                                                  n_global, kind, a, v0, sigma, A, n_mode, h->mc.L, seed, env_offset);
     else sample_kernel<double><<<grid, 256, 0, h->stream>>>((double*)h->x, (double*)h->v, h->N, h->ld, global_offset,
-                                                            n_global, kind, a, v0, sigma, A, n_mode, h->mc.L, seed);
+                                                            n_global, kind, a, v0, sigma, A, n_mode, h->mc.L, seed, env_offset);
     h->launches++;
     CK(h, cudaGetLastError());
     return init_fields(h);

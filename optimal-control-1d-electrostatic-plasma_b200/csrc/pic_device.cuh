@@ -707,7 +707,33 @@ __device__ __forceinline__ R next_stage0(R x_state, R v, H& hist_next, R c0, con
 }
 
 // streaming loads / stores (no reuse: keep the particle stream out of L1, evict-first in L2)
-template <typename V> __device__ __forceinline__ V ld_stream(const V* p) { return __ldcs(p); }
-template <typename V> __device__ __forceinline__ void st_stream(V* p, const V& v) { __stcs(p, v); }
+#ifndef PIC_LD_FLAVOR
+#define PIC_LD_FLAVOR 0
+#endif
+#ifndef PIC_ST_FLAVOR
+#define PIC_ST_FLAVOR 0
+#endif
+template <typename V> __device__ __forceinline__ V ld_stream(const V* p) {
+#if PIC_LD_FLAVOR == 0
+    return __ldcs(p);
+#elif PIC_LD_FLAVOR == 1
+    return *p;
+#elif PIC_LD_FLAVOR == 2
+    return __ldcg(p);
+#else
+    return __ldg(p);
+#endif
+}
+template <typename V> __device__ __forceinline__ void st_stream(V* p, const V& v) {
+#if PIC_ST_FLAVOR == 0
+    __stcs(p, v);
+#elif PIC_ST_FLAVOR == 1
+    *p = v;
+#elif PIC_ST_FLAVOR == 2
+    __stcg(p, v);
+#else
+    __stwt(p, v);
+#endif
+}
 
 }  // namespace pic

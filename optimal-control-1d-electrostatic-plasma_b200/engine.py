@@ -81,11 +81,11 @@ class Engine:
         self._ck(self._lib.pic_set_state_device(self._h, C.c_void_p(x_ptr), C.c_void_p(v_ptr)))
 
     def sample_state(self, kind="bump-on-tail", a=0.2, v0=3.0, sigma=1.0, A=0.1, n_mode=2, seed=42, global_offset=0,
-                     n_global=0):
+                     n_global=0, env_offset=0):
         """Device-side sampler + perturbation + field build (no host particles)."""
         k = {"bump-on-tail": 0, "two-stream": 1}[kind]
         self._ck(self._lib.pic_sample_state(self._h, k, float(a), float(v0), float(sigma), float(A), int(n_mode),
-                                            int(seed), int(global_offset), int(n_global)))
+                                            int(seed), int(global_offset), int(n_global), int(env_offset)))
 
     def get_state(self, want_x=True, want_v=True):
         x = np.empty((self.n_envs, self.N)) if want_x else None
