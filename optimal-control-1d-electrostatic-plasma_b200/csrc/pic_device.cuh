@@ -73,10 +73,13 @@ template <> struct RT<double> {
     static __device__ __forceinline__ double fromint(int a) { return __int2double_rn(a); }
     // round-to-nearest-even integer of q (|q| < 2^31) on the fp64 add pipe: adding 2^52+2^51 leaves rint(q) in the
     // low mantissa word.  No F2I / FRND (those run at a fraction of the DADD rate).
-    static __device__ __forceinline__ double rint_magic(double q, int& i) {
+    // `ok` is false unless 0 <= rint(q) < 2^32 (the high word of the sum is then exactly the magic's): rejects
+    // negative, huge and non-finite q with one integer compare.
+    static __device__ __forceinline__ double rint_magic(double q, int& i, bool& ok) {
         const double MAGIC = 6755399441055744.0;
         double t = __dadd_rn(q, MAGIC);
         i = __double2loint(t);
+        ok = __double2hiint(t) == 0x43380000;
         return __dsub_rn(t, MAGIC);
     }
 };
@@ -94,10 +97,11 @@ template <> struct RT<float> {
     static __device__ __forceinline__ float abs(float a) { return fabsf(a); }
     static __device__ __forceinline__ int toint(float a) { return __float2int_rd(a); }
     static __device__ __forceinline__ float fromint(int a) { return __int2float_rn(a); }
-    static __device__ __forceinline__ float rint_magic(float q, int& i) {       // |q| < 2^22
+    static __device__ __forceinline__ float rint_magic(float q, int& i, bool& ok) {       // ok: 0 <= rint(q) < 2^22
         const float MAGIC = 12582912.0f;
         float t = __fadd_rn(q, MAGIC);
         i = __float_as_int(t) - __float_as_int(MAGIC);
+        ok = (__float_as_int(t) >> 22) == (0x4B400000 >> 22);
         return __fsub_rn(t, MAGIC);
     }
 };
@@ -184,11 +188,11 @@ struct Cell {
 template <typename R>
 __device__ __forceinline__ int cell_index(R xw, const PartConst<R>& c, int M, R& f, unsigned& err) {
     R q = RT<R>::mul(xw, c.inv_dx);
-    int il;
-    R r = RT<R>::rint_magic(q, il);
+    int il; bool ok;
+    R r = RT<R>::rint_magic(q, il, ok);
     R diff = RT<R>::sub(q, r);
     if (diff < (R)0) { r = RT<R>::sub(r, (R)1); il -= 1; }
-    if (RT<R>::abs(diff) <= c.idx_thr) {                 // rare: exact quotient
+    if (!ok || RT<R>::abs(diff) <= c.idx_thr) {          // rare: exact quotient
         r = floor_div_exact<R>(xw, c.dx);
         il = RT<R>::toint(r);
     }
@@ -540,13 +544,13 @@ __device__ __forceinline__ R drift(R x, R v, R cc, const PartConst<R>& c) {
 template <typename R>
 __device__ __forceinline__ bool fast_cell(R xw, const PartConst<R>& c, int M, int& il, R& f) {
     R q = RT<R>::mul(xw, c.inv_dx);
-    int i;
-    R r = RT<R>::rint_magic(q, i);
+    int i; bool ok;
+    R r = RT<R>::rint_magic(q, i, ok);
     R diff = RT<R>::sub(q, r);
     const bool neg = diff < (R)0;
     f = neg ? RT<R>::sub(r, (R)1) : r;
     il = neg ? i - 1 : i;
-    return !(RT<R>::abs(diff) > c.idx_thr) | ((unsigned)il >= (unsigned)M);
+    return !ok | !(RT<R>::abs(diff) > c.idx_thr) | ((unsigned)il >= (unsigned)M);
 }
 
 // the three TSC weights from the in-cell distance d = (x - m dx)/dx, formulas followed literally (interpolate.py:28-32)
