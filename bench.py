@@ -173,7 +173,7 @@ def run_gpu_arm(args):
     hbm_peak, peak_src = measured_peaks()
 
     sim = pic_b200.ShardedPIC(N, N_MESH, 1.0, L_BOX, 0.1, rank=rank, world_size=world, device=local,
-                              collective="nccl", deposit=args.deposit)
+                              collective=args.collective, deposit=args.deposit)
     eng = sim.engine
     if args.threads:
         eng.set_tuning(args.threads, args.unroll, args.ctas)
@@ -344,6 +344,7 @@ def run_gpu_arm(args):
             "config": {"workload": "large-N single env: %.3g particles, %d cells, bump-on-tail, particle-sharded over %d GPU(s)"
                                    % (N, N_MESH, world),
                        "n_particles": N, "n_mesh": N_MESH, "L": L_BOX, "dt": sim.dt, "parallelism": "particle-shard x%d" % world,
+                       "collective": sim.collective,
                        "l2_policy": "inputs (16 B x %.3g particles per rank) exceed the 126 MB L2" % N_local,
                        "launch": info},
             "clocks": clocks,
@@ -375,6 +376,8 @@ def main():
     ap.add_argument("--threads", type=int, default=1024)
     ap.add_argument("--unroll", type=int, default=2)
     ap.add_argument("--ctas", type=int, default=0)
+    ap.add_argument("--collective", default="fused", choices=["fused", "nccl"],
+                    help="density exchange of the particle-sharded mode: fused peer-memory exchange or ncclAllReduce")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-batched", action="store_true")
     ap.add_argument("--no-roundtrip", action="store_true")

@@ -136,7 +136,8 @@ int pic_phase_hist(pic_handle* h, uint32_t* counts /* host [n_envs][nbins][nbins
 int pic_set_feq(pic_handle* h, const double* feq);
 int pic_kl_divergence(pic_handle* h, double* kl /* host [n_envs] */);
 int pic_sync(pic_handle* h);
-/* sticky numeric flags raised on the device (bit 0: cell index out of range, bit 1: non-finite position) */
+/* sticky flags raised on the device (bit 0: cell index out of range, bit 1: non-finite position, bit 2: a peer
+ * of the fused exchange did not arrive in time) */
 int pic_get_error_flags(pic_handle* h, uint32_t* flags);
 
 /* --- zero-copy views for the policy side (device pointers owned by the handle) ------------------------------- */
@@ -161,6 +162,16 @@ int pic_comm_init(pic_handle* h, void* nccl_comm, int32_t rank, int32_t world_si
  * means (torch.distributed object broadcast, MPI, a file), then every rank calls pic_comm_init_rank. */
 int pic_nccl_unique_id(char* out128);
 int pic_comm_init_rank(pic_handle* h, const char* id128, int32_t rank, int32_t world_size);
+/* Fused exchange over NVLink peer memory -- no collective library in the step loop.  The caller provides, for every
+ * rank r of the node, a device pointer to r's exchange buffer (pic_comm_exchange_words() 64-bit words each) and to
+ * r's flag array (world 64-bit words, ZERO-initialised before the first step on every rank), all mapped into this
+ * process (CUDA IPC, cuMem fabric handles, or torch symmetric memory).  The last CTA of every push kernel then
+ * writes the rank's finished partial density straight into every peer's buffer and raises a flag; the next kernel's
+ * prologue waits for the flags and sums the slots in rank order (integer sum: bit-identical on every rank and for
+ * every GPU count).  world <= 8.  A peer that never arrives raises error flag bit 2 instead of hanging the GPU. */
+int64_t pic_comm_exchange_words(const pic_handle* h, int32_t world_size);
+int pic_comm_init_peer(pic_handle* h, int32_t rank, int32_t world_size, void* const* exchange_ptrs,
+                       void* const* flag_ptrs, int64_t exchange_words);
 /* Alternative used when the collective is driven from the host side (e.g. torch.distributed): run sub-stage
  * `stage` (1..3, 4 = finalize, -1 = init deposit; 0 is a no-op because the drift-only stage 0 of a step is executed
  * ahead of time by stage 3 / init of the state it starts from) and leave the local density in the buffer returned

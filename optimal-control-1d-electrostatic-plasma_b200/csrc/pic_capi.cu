@@ -103,6 +103,12 @@ struct pic_handle {
     void* comm = nullptr;
     bool own_comm = false;
     int rank = 0, world = 1;
+    // fused exchange over peer memory (pic_comm_init_peer): no collective library in the step loop
+    bool fused = false;
+    unsigned long long* exch[COMM_MAX_WORLD] = {};
+    unsigned long long* cflags[COMM_MAX_WORLD] = {};
+    unsigned long long seq = 0, seq_state = 0;       // last exchange issued; the exchange holding the state density
+    unsigned* ticket = nullptr;
 
     long long launches = 0;
     std::string last_error;
@@ -180,8 +186,18 @@ int configure_launch(pic_handle* h) {
     return PIC_OK;
 }
 
+int comm_slot_len(const pic_handle* h) { return 2 * h->M * h->n_envs + 2 * h->n_envs; }
+
+void fill_comm(const pic_handle* h, CommArgs& c, unsigned long long seq_in, int in_offset, unsigned long long seq_out,
+               const unsigned long long* out_src, int out_words) {
+    c.world = h->fused ? h->world : 1; c.rank = h->rank; c.slot_len = comm_slot_len(h);
+    for (int r = 0; r < COMM_MAX_WORLD; ++r) { c.exch[r] = h->exch[r]; c.flags[r] = h->cflags[r]; }
+    c.seq_in = seq_in; c.in_offset = in_offset; c.seq_out = seq_out; c.out_src = out_src; c.out_words = out_words;
+    c.ticket = h->ticket;
+}
+
 int allreduce_u64(pic_handle* h, unsigned long long* buf, size_t count) {
-    if (h->world <= 1) return PIC_OK;
+    if (h->world <= 1 || h->fused) return PIC_OK;
     int r = nccl_api().allreduce(buf, buf, count, kNcclUint64, kNcclSum, h->comm, h->stream);
     if (r != 0) return fail(h, PIC_ENCCL, std::string("ncclAllReduce(uint64): ") +
                             (nccl_api().errstr ? nccl_api().errstr(r) : "error"));
@@ -311,15 +327,17 @@ int run_stage(pic_handle* h, int stage, const double* ext, const double* coeffs,
         f.partial = h->partial; f.vsum = h->vsum; f.n_partial = h->grid_x;
         f.rw = h->rw; f.coeffs = coeffs; f.two_m = 2 * h->m; f.step_done = trace_row != nullptr;
         f.tw_cos = h->tw_cos; f.tw_sin = h->tw_sin; f.n_modes = h->n_modes; f.modes = h->n_modes > 0 ? h->modes : nullptr;
+        fill_comm(h, f.comm, h->seq_state, 0, 0, nullptr, 0);
+        f.rho_reduced = h->rho[3]; f.err = h->err;
         void* args[] = {&f};
         CK(h, cudaLaunchKernel((const void*)&field_finalize_kernel<256>, dim3(h->n_envs), dim3(256), args,
                                smem_plan_bytes<double>(h->M, 256, false), h->stream));
         h->launches++;
-        if (h->world > 1) {
+        if (h->world > 1 && !h->fused) {
             int r = nccl_api().allreduce(h->vsum, h->vsum, 2 * (size_t)h->n_envs, kNcclFloat64, kNcclSum, h->comm, h->stream);
             if (r != 0) return fail(h, PIC_ENCCL, "ncclAllReduce(float64) failed");
         }
-        if (h->world > 1 || trace_row) {
+        if ((h->world > 1 && !h->fused) || trace_row) {
             apply_vsum_kernel<<<(h->n_envs + 127) / 128, 128, 0, h->stream>>>(h->vsum, h->diag, trace_row, h->n_envs);
             h->launches++;
         }
@@ -345,6 +363,16 @@ int run_stage(pic_handle* h, int stage, const double* ext, const double* coeffs,
     }
     if (stage >= 1) { a.c = h->cs[stage]; a.d = h->ds[stage]; }
     if (stage == -1) CK(h, cudaMemsetAsync(h->rho_block, 0, sizeof(unsigned long long) * 4 * sz, h->stream));
+    if (h->fused) {
+        // consume: stage 1 reads the next-stage-0 half of the exchange that carried the state (offset sz), stages 2, 3
+        // read the previous sub-stage's exchange; produce: a new exchange from the buffer this kernel reduces into
+        const unsigned long long seq_in = stage == 1 ? h->seq_state : (stage == -1 ? 0 : h->seq);
+        const unsigned long long seq_out = ++h->seq;
+        fill_comm(h, a.comm, seq_in, stage == 1 ? (int)sz : 0, seq_out, reduce, (int)reduce_count);
+        if (stage == 3 || stage == -1) h->seq_state = seq_out;
+    } else {
+        fill_comm(h, a.comm, 0, 0, 0, nullptr, 0);
+    }
     void* args[] = {&a};
     CK(h, cudaLaunchKernel(stream_kernel(h, mode), dim3(h->grid_x, h->n_envs), dim3(h->threads), args, h->smem, h->stream));
     h->launches++;
@@ -547,6 +575,8 @@ int pic_create(const pic_config* cfg, pic_handle** out) {
     cudaMemsetAsync(h->diag, 0, sizeof(double) * DIAG_N * h->n_envs, h->stream);
     cudaMemsetAsync(h->vsum, 0, sizeof(double) * 2 * h->n_envs, h->stream);
     cudaMemsetAsync(h->err, 0, sizeof(unsigned), h->stream);
+    if (cudaMalloc(&h->ticket, sizeof(unsigned)) != cudaSuccess) { pic_destroy(h); return fail(nullptr, PIC_ENOMEM, "cudaMalloc"); }
+    cudaMemsetAsync(h->ticket, 0, sizeof(unsigned), h->stream);
     int rc = configure_launch(h);
     if (rc) { g_create_error = h->last_error; pic_destroy(h); return rc; }
     *out = h;
@@ -560,7 +590,7 @@ int pic_destroy(pic_handle* h) {
     if (h->own_comm && h->comm && nccl_api().destroy) nccl_api().destroy(h->comm);
     void* bufs[] = {h->x, h->v, h->xp, h->rho_block, h->n, h->E, h->diag, h->vsum, h->partial,
                     h->ext, h->coeffs, h->bcos, h->bsin, h->trace, h->stage64, h->err, h->tw_cos, h->tw_sin, h->modes,
-                    h->mode_trace, h->ph_counts, h->ph_feq, h->ph_kl};
+                    h->mode_trace, h->ph_counts, h->ph_feq, h->ph_kl, h->ticket};
     for (void* b : bufs) if (b) cudaFree(b);
     delete h;
     return PIC_OK;
@@ -954,6 +984,25 @@ int pic_comm_init(pic_handle* h, void* comm, int32_t rank, int32_t world) {
     if (h->resident) return fail(h, PIC_EUNSUPPORTED, "particle sharding needs streaming mode");
     if (!nccl_api().ok) return fail(h, PIC_ENCCL, "libnccl not available in this process");
     h->comm = comm; h->own_comm = false; h->rank = rank; h->world = world;
+    return PIC_OK;
+}
+
+int64_t pic_comm_exchange_words(const pic_handle* h, int32_t world) {
+    return h ? (int64_t)COMM_SETS * world * comm_slot_len(h) : 0;
+}
+
+int pic_comm_init_peer(pic_handle* h, int32_t rank, int32_t world, void* const* exch_ptrs, void* const* flag_ptrs,
+                       int64_t exch_words) {
+    if (!h || !exch_ptrs || !flag_ptrs) return PIC_EINVAL;
+    if (h->resident || h->n_envs != 1) return fail(h, PIC_EUNSUPPORTED, "the fused exchange needs streaming mode with one env");
+    if (world < 2 || world > COMM_MAX_WORLD || rank < 0 || rank >= world)
+        return fail(h, PIC_EINVAL, "world must be 2.." + std::to_string(COMM_MAX_WORLD));
+    if (exch_words < pic_comm_exchange_words(h, world)) return fail(h, PIC_EINVAL, "exchange buffer too small");
+    for (int r = 0; r < world; ++r) {
+        if (!exch_ptrs[r] || !flag_ptrs[r]) return fail(h, PIC_EINVAL, "null peer pointer");
+        h->exch[r] = (unsigned long long*)exch_ptrs[r]; h->cflags[r] = (unsigned long long*)flag_ptrs[r];
+    }
+    h->rank = rank; h->world = world; h->fused = true; h->seq = 0; h->seq_state = 0;
     return PIC_OK;
 }
 

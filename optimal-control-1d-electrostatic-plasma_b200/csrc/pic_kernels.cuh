@@ -24,6 +24,69 @@ constexpr int MODE_KICK = 1;    // stages 1,2: kick + drift                    (
 constexpr int MODE_FINAL = 2;   // stage 3: kick + drift + state wrap (pic.py:139) + kinetic sums, then stage 0 of the next step
 constexpr int MODE_INIT = 3;    // no motion: wrap in place + deposit (pic.py:76 / util.py:51), then stage 0 of the next step
 
+// ------------------------------------------------------------------ fused density exchange over NVLink
+// Particle-sharded mode without a collective library in the step loop.  Every rank owns an exchange buffer that all
+// peers can write (symmetric / peer-mapped memory): SETS slot sets x `world` slots x `slot_len` 64-bit words, plus
+// one flag word per source rank.  The LAST CTA of a push kernel (ticket counter) copies the rank's finished partial
+// density -- and, after a state-producing pass, its kinetic sums -- into slot[set][rank] of EVERY rank with 16-byte
+// peer stores, fences, and then publishes the exchange number `seq` in flag[rank] on every rank.  The next kernel's
+// prologue waits until all `world` flags have reached `seq` and reads the density as the sum over the slots in rank
+// order: an integer sum, identical on every rank.  The transfer therefore overlaps the tail of the producing kernel
+// and the head of the consuming one; there is no separate reduction kernel and no host involvement.
+// Two slot sets would suffice (a rank can produce exchange s+2 only after every rank has consumed exchange s); four
+// are used.  Waits are bounded: a missing peer raises ERR_COMM_TIMEOUT instead of hanging the GPU.
+constexpr int COMM_MAX_WORLD = 8;
+constexpr int COMM_SETS = 4;
+constexpr unsigned ERR_COMM_TIMEOUT = 4u;
+
+struct CommArgs {
+    int world, rank;                                   // world <= 1: disabled
+    int slot_len;                                      // words per slot (2 * n_envs * M + 2 * n_envs)
+    unsigned long long* exch[COMM_MAX_WORLD];          // exchange buffer of every rank (peer pointers); [rank] is local
+    unsigned long long* flags[COMM_MAX_WORLD];         // flag array of every rank; this rank writes entry [rank] of each
+    unsigned long long seq_in;                         // exchange to consume in the prologue (0: none)
+    unsigned long long seq_out;                        // exchange produced by this kernel (0: none)
+    int in_offset;                                     // word offset of the density to consume inside a slot
+    int out_words;                                     // words this kernel publishes
+    unsigned* ticket;                                  // CTA completion counter (zero between kernels)
+    const unsigned long long* out_src;                 // local finished partial density, out_words contiguous words
+};
+
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// every thread of the CTA calls this; returns after all ranks have published exchange `seq`
+__device__ __forceinline__ void comm_wait(const CommArgs& c, unsigned long long seq, unsigned* err) {
+    if (threadIdx.x < c.world) {
+        const unsigned long long* f = c.flags[c.rank] + threadIdx.x;
+        long long spins = 0;
+        while (ld_acquire_sys(f) < seq) {
+            if (++spins > (1ll << 24)) { atomicOr(err, ERR_COMM_TIMEOUT); break; }    // ~ a second: bail out, never hang
+            __nanosleep(64);
+        }
+    }
+    __syncthreads();
+}
+
+struct PeerSumRho {                                   // density = sum over ranks of their published partial density
+    const unsigned long long* slots;                  // slot[set][0] + in_offset of the local exchange buffer
+    int slot_len, world;
+    __device__ __forceinline__ unsigned long long operator()(int j) const {
+        unsigned long long s = 0;
+        for (int r = 0; r < world; ++r) s += __ldcg(slots + (size_t)r * slot_len + j);
+        return s;
+    }
+};
+__device__ __forceinline__ const unsigned long long* comm_in_slots(const CommArgs& c, unsigned long long seq) {
+    return c.exch[c.rank] + (size_t)(seq % COMM_SETS) * c.world * c.slot_len + c.in_offset;
+}
+
 struct ActuatorArgs {
     const double* ext;       // mesh mode: [n_envs][M] (device) or nullptr
     const double* coeffs;    // coefficient mode: [n_envs][2m] (device) or nullptr
@@ -46,6 +109,7 @@ struct StreamArgs {
     ActuatorArgs act;
     double c, d;
     double c_next;                     // c0 of the Yoshida scheme
+    CommArgs comm;                     // fused exchange over peer memory (world <= 1: off)
     double* partial;                   // [n_envs][gridDim.x][2] per-CTA sum v^2, sum v (MODE_FINAL / MODE_INIT)
     unsigned* err;
 };
@@ -116,10 +180,17 @@ __global__ void __launch_bounds__(THREADS) push_stream_kernel(const StreamArgs a
     H hist_next; hist_next.init(sm.hist2, M);
     const PartConst<R> pc = make_part_const<R>(a.mc);
 
+    const bool fused = a.comm.world > 1;
     if (KICK) {                                         // D_s aliases the histogram: solve first, then clear
         const ExtSrc ext = stage_ext(a.act, env, M);
-        GlobalRho rho{a.rho_in + (size_t)env * M};
-        block_field<R, THREADS>(rho, sm.E_s, sm.D_s, sm.red, a.mc, ext, nullptr, nullptr, 0.0, 0.0, [] {});
+        if (fused) {
+            comm_wait(a.comm, a.comm.seq_in, a.err);
+            PeerSumRho rho{comm_in_slots(a.comm, a.comm.seq_in), a.comm.slot_len, a.comm.world};
+            block_field<R, THREADS>(rho, sm.E_s, sm.D_s, sm.red, a.mc, ext, nullptr, nullptr, 0.0, 0.0, [] {});
+        } else {
+            GlobalRho rho{a.rho_in + (size_t)env * M};
+            block_field<R, THREADS>(rho, sm.E_s, sm.D_s, sm.red, a.mc, ext, nullptr, nullptr, 0.0, 0.0, [] {});
+        }
     }
     hist.zero(tid, THREADS);
     if (SUMS) hist_next.zero(tid, THREADS);
@@ -220,6 +291,37 @@ __global__ void __launch_bounds__(THREADS) push_stream_kernel(const StreamArgs a
         }
     }
     if (err) atomicOr(a.err, err);
+    if (fused) {                                        // single env per handle in this mode
+        __shared__ double s_extra[2];                   // the last CTA also publishes the rank's kinetic sums
+        __shared__ unsigned s_is_last;
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) s_is_last = atomicAdd(a.comm.ticket, 1u) == gridDim.x - 1 ? 1u : 0u;
+        __syncthreads();
+        if (s_is_last) {
+            __threadfence();
+            int n_extra = 0;
+            if (SUMS) {
+                double q2 = 0.0, q1 = 0.0;
+                for (int i = tid; i < (int)gridDim.x; i += THREADS) { q2 += __ldcg(a.partial + 2 * i); q1 += __ldcg(a.partial + 2 * i + 1); }
+                q2 = block_sum<THREADS>(q2, sm.red);
+                q1 = block_sum<THREADS>(q1, sm.red);
+                if (tid == 0) { s_extra[0] = q2; s_extra[1] = q1; }
+                __syncthreads();
+                n_extra = 2;
+            }
+            const size_t slot = ((size_t)(a.comm.seq_out % COMM_SETS) * a.comm.world + a.comm.rank) * a.comm.slot_len;
+            for (int r = 0; r < a.comm.world; ++r) {
+                unsigned long long* dst = a.comm.exch[r] + slot;
+                for (int j = tid; j < a.comm.out_words; j += THREADS) dst[j] = __ldcg(a.comm.out_src + j);
+                if (tid < n_extra) dst[a.comm.out_words + tid] = (unsigned long long)__double_as_longlong(s_extra[tid]);
+            }
+            __threadfence_system();
+            __syncthreads();
+            if (tid < a.comm.world) st_release_sys(a.comm.flags[tid] + a.comm.rank, a.comm.seq_out);
+            if (tid == 0) *a.comm.ticket = 0u;
+        }
+    }
 }
 
 // ----------------------------------------------------------------- finalize
@@ -239,6 +341,9 @@ struct FinalizeArgs {
     const double* partial;             // [n_envs][n_partial][2] or nullptr
     double* vsum;                      // [n_envs][2] local sum v^2, sum v (all-reduced by the host when sharded)
     int n_partial;
+    CommArgs comm;                     // fused exchange: consume the state density + kinetic sums of all ranks
+    unsigned long long* rho_reduced;   // fused exchange: where the summed state density is stored (the S buffer)
+    unsigned* err;
 };
 
 template <int THREADS>
@@ -246,16 +351,33 @@ __global__ void __launch_bounds__(THREADS) field_finalize_kernel(const FinalizeA
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int env = blockIdx.x, M = a.mc.M, tid = threadIdx.x;
     SmemLayout<double> sm(smem_raw, M, false);
-    GlobalRho rho{a.rho + (size_t)env * M};
     const ExtSrc none{nullptr, nullptr, nullptr, nullptr, 0};
-    double s2 = 0.0, s1 = 0.0;
-    if (a.partial) {
-        const double* p = a.partial + (size_t)env * a.n_partial * 2;
-        for (int i = tid; i < a.n_partial; i += THREADS) { s2 += p[2 * i]; s1 += p[2 * i + 1]; }
-    }
     const ModeOut mo{a.tw_cos, a.tw_sin, a.modes ? a.modes + (size_t)env * 2 * a.n_modes : nullptr, a.n_modes};
-    const FieldTotals t = block_field<double, THREADS>(rho, sm.E_s, sm.D_s, sm.red, a.mc, none,
-                                                       a.n_out + (size_t)env * M, a.E_out + (size_t)env * M, s2, s1, [] {}, mo);
+    const bool fused = a.comm.world > 1;
+    double s2 = 0.0, s1 = 0.0;
+    FieldTotals t;
+    if (fused) {                                       // single env: density and kinetic sums come from the slots
+        comm_wait(a.comm, a.comm.seq_in, a.err);
+        const unsigned long long* slots = comm_in_slots(a.comm, a.comm.seq_in);
+        PeerSumRho rho{slots, a.comm.slot_len, a.comm.world};
+        if (tid == 0) {                                // rank order: the same doubles in the same order on every rank
+            const int kin = 2 * M;                     // words 2M, 2M+1 of a slot: sum v^2, sum v of that rank
+            for (int r = 0; r < a.comm.world; ++r) {
+                s2 += __longlong_as_double((long long)__ldcg(slots + (size_t)r * a.comm.slot_len + kin));
+                s1 += __longlong_as_double((long long)__ldcg(slots + (size_t)r * a.comm.slot_len + kin + 1));
+            }
+        }
+        for (int j = tid; j < M; j += THREADS) a.rho_reduced[j] = rho(j);
+        t = block_field<double, THREADS>(rho, sm.E_s, sm.D_s, sm.red, a.mc, none, a.n_out, a.E_out, s2, s1, [] {}, mo);
+    } else {
+        GlobalRho rho{a.rho + (size_t)env * M};
+        if (a.partial) {
+            const double* p = a.partial + (size_t)env * a.n_partial * 2;
+            for (int i = tid; i < a.n_partial; i += THREADS) { s2 += p[2 * i]; s1 += p[2 * i + 1]; }
+        }
+        t = block_field<double, THREADS>(rho, sm.E_s, sm.D_s, sm.red, a.mc, none,
+                                         a.n_out + (size_t)env * M, a.E_out + (size_t)env * M, s2, s1, [] {}, mo);
+    }
     if (a.rho_zero) for (int j = tid; j < M; j += THREADS) a.rho_zero[(size_t)env * M + j] = 0ull;
     if (tid == 0) {
         double* d = a.diag + (size_t)env * DIAG_N;
@@ -268,7 +390,7 @@ __global__ void __launch_bounds__(THREADS) field_finalize_kernel(const FinalizeA
         }
         d[DIAG_PE_MESH] = 0.5 * t.e2 * a.mc.dx;
         d[DIAG_SUM_E2] = t.e2;
-        if (a.partial) {
+        if (a.partial || fused) {
             a.vsum[env * 2] = t.s1; a.vsum[env * 2 + 1] = t.s2;
             d[DIAG_KE] = 0.5 * t.s1; d[DIAG_SUM_V] = t.s2;
         }

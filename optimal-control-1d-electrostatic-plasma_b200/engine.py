@@ -231,6 +231,16 @@ class Engine:
     def comm_init_rank(self, uid: bytes, rank, world):
         self._ck(self._lib.pic_comm_init_rank(self._h, uid, int(rank), int(world)))
 
+    def comm_exchange_words(self, world):
+        return int(self._lib.pic_comm_exchange_words(self._h, int(world)))
+
+    def comm_init_peer(self, rank, world, exch_ptrs, flag_ptrs, exch_words):
+        """Fused exchange over peer memory: exch_ptrs / flag_ptrs are the device addresses of every rank's exchange
+        buffer / flag array as mapped into THIS process."""
+        ea = (C.c_void_p * world)(*[C.c_void_p(int(p)) for p in exch_ptrs])
+        fa = (C.c_void_p * world)(*[C.c_void_p(int(p)) for p in flag_ptrs])
+        self._ck(self._lib.pic_comm_init_peer(self._h, int(rank), int(world), ea, fa, int(exch_words)))
+
     @staticmethod
     def nccl_unique_id():
         buf = C.create_string_buffer(128)

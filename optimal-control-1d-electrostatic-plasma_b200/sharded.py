@@ -6,7 +6,11 @@ point; the partial densities are summed over ranks with ONE NCCL all-reduce of N
 and every rank rebuilds the same field from the same integers in the next kernel's prologue.  Because the sum is an
 integer sum, x, v and the fields are bit-identical for every GPU count (tests/test_gpu_multi.py).
 
-Two ways to run the collective:
+Three ways to run the collective:
+  collective="fused"  no collective library in the step loop: the last CTA of every push kernel writes the rank's
+                      partial density into every peer's exchange buffer over NVLink (torch symmetric memory provides
+                      the peer mappings) and raises a flag; the next kernel's prologue waits for the flags and sums
+                      the slots in rank order.  <= 8 ranks of one node.
   collective="nccl"   the C library calls ncclAllReduce itself on the engine's stream (communicator built from a
                       unique id that is broadcast through torch.distributed);
   collective="torch"  sub-stages are driven one by one and `torch.distributed.all_reduce` runs on an int64 view of
@@ -54,7 +58,28 @@ class ShardedPIC:
         if self.collective == "nccl":
             uid = broadcast_bytes(Engine.nccl_unique_id() if self.rank == 0 else None, 0, group)
             self.engine.comm_init_rank(uid, self.rank, self.world)
+        elif self.collective == "fused":
+            self._init_fused(device, group)
         self._ext_dev = None
+
+    def _init_fused(self, device, group):
+        """Peer-mapped exchange buffer + flag array of every rank (torch symmetric memory does the mapping)."""
+        import torch
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+        dev = torch.device("cuda", device)
+        g = group if group is not None else dist.group.WORLD
+        words = self.engine.comm_exchange_words(self.world)
+        self._exch = symm_mem.empty(words, dtype=torch.int64, device=dev)
+        self._flags = symm_mem.empty(max(self.world, 16), dtype=torch.int64, device=dev)
+        self._exch.zero_()
+        self._flags.zero_()
+        torch.cuda.synchronize(dev)
+        he = symm_mem.rendezvous(self._exch, group=g)
+        hf = symm_mem.rendezvous(self._flags, group=g)
+        self._symm_handles = (he, hf)
+        dist.barrier(group=g)                       # every rank has zeroed its flags before anyone can raise one
+        self.engine.comm_init_peer(self.rank, self.world, list(he.buffer_ptrs), list(hf.buffer_ptrs), words)
 
     # ---- state
     def sample_state(self, kind="bump-on-tail", **kw):

@@ -45,8 +45,10 @@ def main():
         res["pe_equal"] = bool(d[1] == d1[1])
         res["ke_rel"] = float(abs(d[0] - d1[0]) / d1[0])
         res["sumv_abs"] = float(abs(d[2] - d1[2]))
+        res["flags"] = int(sim.engine.error_flags())
     # the device sampler draws the same population whatever the sharding
-    s = pic_b200.ShardedPIC(200_000, 512, 1.0, L, 0.05, rank=rank, world_size=world, device=local, collective="nccl")
+    s = pic_b200.ShardedPIC(200_000, 512, 1.0, L, 0.05, rank=rank, world_size=world, device=local,
+                            collective=collective if collective != "torch" else "nccl")
     s.sample_state("bump-on-tail", seed=5)
     xs, vs = s.get_state_local()
     if rank == 0:

@@ -11,7 +11,7 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.parametrize("collective", ["nccl", "torch"])
+@pytest.mark.parametrize("collective", ["fused", "nccl", "torch"])
 def test_sharded_equals_single_gpu(collective, tmp_path):
     import torch
     n = torch.cuda.device_count()
@@ -29,3 +29,4 @@ def test_sharded_equals_single_gpu(collective, tmp_path):
     assert res["rho_equal"] and res["x_equal"] and res["v_equal"] and res["pe_equal"], res
     assert res["ke_rel"] < 1e-14 and res["sumv_abs"] < 1e-8, res
     assert res["sampler_shard_equal"] and res["sampler_rho_equal"], res
+    assert res["flags"] == 0, res
