@@ -376,7 +376,7 @@ def main():
     ap.add_argument("--threads", type=int, default=1024)
     ap.add_argument("--unroll", type=int, default=2)
     ap.add_argument("--ctas", type=int, default=0)
-    ap.add_argument("--collective", default="fused", choices=["fused", "nccl"],
+    ap.add_argument("--collective", default="nccl", choices=["fused", "nccl"],
                     help="density exchange of the particle-sharded mode: fused peer-memory exchange or ncclAllReduce")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-batched", action="store_true")

@@ -311,11 +311,27 @@ __global__ void __launch_bounds__(THREADS) push_stream_kernel(const StreamArgs a
                 n_extra = 2;
             }
             const size_t slot = ((size_t)(a.comm.seq_out % COMM_SETS) * a.comm.world + a.comm.rank) * a.comm.slot_len;
-            for (int r = 0; r < a.comm.world; ++r) {
-                unsigned long long* dst = a.comm.exch[r] + slot;
-                for (int j = tid; j < a.comm.out_words; j += THREADS) dst[j] = __ldcg(a.comm.out_src + j);
-                if (tid < n_extra) dst[a.comm.out_words + tid] = (unsigned long long)__double_as_longlong(s_extra[tid]);
+            // each word is read once (all loads of a batch in flight together) and then posted to every peer
+            constexpr int BATCH = 8;
+            for (int j0 = tid; j0 < a.comm.out_words; j0 += THREADS * BATCH) {
+                unsigned long long w[BATCH];
+#pragma unroll
+                for (int b = 0; b < BATCH; ++b) {
+                    const int j = j0 + b * THREADS;
+                    w[b] = j < a.comm.out_words ? __ldcg(a.comm.out_src + j) : 0ull;
+                }
+                for (int r = 0; r < a.comm.world; ++r) {
+                    unsigned long long* dst = a.comm.exch[r] + slot;
+#pragma unroll
+                    for (int b = 0; b < BATCH; ++b) {
+                        const int j = j0 + b * THREADS;
+                        if (j < a.comm.out_words) dst[j] = w[b];
+                    }
+                }
             }
+            if (tid < n_extra)
+                for (int r = 0; r < a.comm.world; ++r)
+                    a.comm.exch[r][slot + a.comm.out_words + tid] = (unsigned long long)__double_as_longlong(s_extra[tid]);
             __threadfence_system();
             __syncthreads();
             if (tid < a.comm.world) st_release_sys(a.comm.flags[tid] + a.comm.rank, a.comm.seq_out);
