@@ -139,6 +139,7 @@ int pic_sync(pic_handle* h);
 /* sticky flags raised on the device (bit 0: cell index out of range, bit 1: non-finite position, bit 2: a peer
  * of the fused exchange did not arrive in time) */
 int pic_get_error_flags(pic_handle* h, uint32_t* flags);
+int pic_clear_error_flags(pic_handle* h);
 
 /* --- zero-copy views for the policy side (device pointers owned by the handle) ------------------------------- */
 typedef struct pic_device_views {

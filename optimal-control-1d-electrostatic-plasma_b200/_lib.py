@@ -68,6 +68,7 @@ SIGNATURES = {
     "pic_kl_divergence": (C.c_int, [_H, C.c_void_p]),
     "pic_sync": (C.c_int, [_H]),
     "pic_get_error_flags": (C.c_int, [_H, C.POINTER(C.c_uint32)]),
+    "pic_clear_error_flags": (C.c_int, [_H]),
     "pic_get_device_views": (C.c_int, [_H, C.POINTER(PicDeviceViews)]),
     "pic_comm_init": (C.c_int, [_H, C.c_void_p, C.c_int32, C.c_int32]),
     "pic_nccl_unique_id": (C.c_int, [C.c_char_p]),

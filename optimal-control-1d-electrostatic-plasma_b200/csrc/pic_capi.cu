@@ -949,6 +949,12 @@ int pic_get_error_flags(pic_handle* h, uint32_t* flags) {
     return PIC_OK;
 }
 
+int pic_clear_error_flags(pic_handle* h) {
+    if (!h) return PIC_EINVAL;
+    CK(h, cudaMemsetAsync(h->err, 0, sizeof(unsigned), h->stream));
+    return PIC_OK;
+}
+
 int pic_get_device_views(pic_handle* h, pic_device_views* out) {
     if (!h || !out) return PIC_EINVAL;
     out->x = h->x; out->v = h->v; out->ld = h->ld; out->n = h->n; out->E_mesh = h->E; out->diag = h->diag;

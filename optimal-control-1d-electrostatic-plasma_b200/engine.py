@@ -216,6 +216,9 @@ class Engine:
         self._ck(self._lib.pic_get_error_flags(self._h, C.byref(f)))
         return f.value
 
+    def clear_error_flags(self):
+        self._ck(self._lib.pic_clear_error_flags(self._h))
+
     # ---- staged driving / sharding
     def run_stage(self, stage):
         self._ck(self._lib.pic_run_stage(self._h, int(stage)))

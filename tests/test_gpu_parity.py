@@ -428,3 +428,47 @@ def test_streaming_multi_env_and_far_positions():
     x1, v1 = one.get_state()
     assert np.array_equal(x1[0], xg[1]) and np.array_equal(v1[0], vg[1])
     assert eng.error_flags() == 0
+
+
+def test_error_behaviour():
+    """Errors are loud and typed: bad configs, calls out of order, unsupported combinations, and the sticky device
+    flags for positions the reference itself cannot handle (NaN -> np.bincount raises there)."""
+    import pic_b200
+    from pic_b200 import Engine, PicError
+    with pytest.raises(PicError) as e:
+        Engine(0, 16, 10.0, 0.1)
+    assert e.value.code == -1
+    with pytest.raises(PicError) as e:
+        Engine(1000, 16, 10.0, 0.1, precision="f32", interpol="TSC")
+    assert e.value.code == -8
+    with pytest.raises(PicError) as e:
+        Engine(50_000, 16, 10.0, 0.1, mode="resident")            # does not fit one CTA's shared memory
+    assert e.value.code == -8
+    with pytest.raises(PicError) as e:
+        Engine(100_000, 20000, 10.0, 0.1, mode="streaming")       # mesh tables exceed shared memory
+    assert e.value.code == -8 and "n_mesh too large" in str(e.value)
+    eng = Engine(1000, 32, 10.0, 0.05, max_mode=2)
+    with pytest.raises(PicError) as e:
+        eng.step_mesh(None, 1)                                     # no state yet
+    assert e.value.code == -5
+    rng = np.random.RandomState(0)
+    x = rng.uniform(0, 10, 1000); v = rng.normal(size=1000)
+    eng.set_state(x[None], v[None])
+    with pytest.raises(PicError) as e:
+        eng.step_coeffs(np.zeros((1, 1, 4)), 1)                    # actuator basis not uploaded
+    assert e.value.code == -5
+    with pytest.raises(ValueError):
+        eng.step_mesh(np.zeros((1, 31)), 1)                        # wrong mesh length
+    assert eng.error_flags() == 0
+    x[3] = np.nan
+    x[4] = np.inf
+    eng.set_state(x[None], v[None])
+    eng.step_mesh(None, 2)
+    assert eng.error_flags() & 2                                   # non-finite position flagged, no crash
+    eng.clear_error_flags()
+    x[3] = 1.0; x[4] = 2.0
+    eng.set_state(x[None], v[None])
+    eng.step_mesh(None, 2)
+    assert eng.error_flags() == 0
+    rho, k = eng.get_density_fixed()
+    assert sum(int(r) for r in rho.ravel()) == 1000 * (1 << k)
