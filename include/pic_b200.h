@@ -137,7 +137,9 @@ int pic_set_feq(pic_handle* h, const double* feq);
 int pic_kl_divergence(pic_handle* h, double* kl /* host [n_envs] */);
 int pic_sync(pic_handle* h);
 /* sticky flags raised on the device (bit 0: cell index out of range, bit 1: non-finite position, bit 2: a peer
- * of the fused exchange did not arrive in time) */
+ * of the fused exchange did not arrive in time, bit 3: a cell's integer density overflowed -- the fixed-point format
+ * leaves 8x the mean per-cell density of headroom, far more when N/N_mesh is small; lower fixed_bits for denser
+ * clumps) */
 int pic_get_error_flags(pic_handle* h, uint32_t* flags);
 int pic_clear_error_flags(pic_handle* h);
 

@@ -54,6 +54,7 @@ struct ModeOut {
 
 constexpr unsigned ERR_INDEX_RANGE = 1u;   // floor(x/dx) fell outside [0, N_mesh) (the reference would raise in np.bincount)
 constexpr unsigned ERR_NONFINITE = 2u;     // non-finite position reached the deposit
+constexpr unsigned ERR_DENSITY_RANGE = 8u; // a cell's fixed-point sum left [0, 2^63): more than ~8x the mean density
 
 // ---------------------------------------------------------------- real traits
 template <typename R> struct RT;
@@ -421,7 +422,8 @@ template <typename R, int THREADS, typename RhoLoad, typename IdleWork>
 __device__ __forceinline__ FieldTotals block_field(RhoLoad rho, typename PairT<R>::type* E_s, double* D_s, double* red,
                                                    const MeshConst& mc, const ExtSrc& ext, double* __restrict__ n_out,
                                                    double* __restrict__ E_out, double x1, double x2,
-                                                   IdleWork idle_work, const ModeOut modes = ModeOut{nullptr, nullptr, nullptr, 0}) {
+                                                   IdleWork idle_work, const ModeOut modes = ModeOut{nullptr, nullptr, nullptr, 0},
+                                                   unsigned* range_err = nullptr) {
     constexpr int FT = FieldShape<THREADS>::FT, NWF = FieldShape<THREADS>::NWF, NW = FieldShape<THREADS>::NW;
     const int M = mc.M, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const bool field_thread = tid < FT;
@@ -436,7 +438,9 @@ __device__ __forceinline__ FieldTotals block_field(RhoLoad rho, typename PairT<R
     if (field_thread) {
         double ls = 0.0;
         for (int j = j0; j < j1; ++j) {
-            double nj = (double)(long long)rho(j) * mc.inv_fix * mc.scale;
+            const long long rj = (long long)rho(j);
+            if (range_err && rj < -(mc.fix_one << 2)) atomicOr(range_err, ERR_DENSITY_RANGE);   // wrapped past 2^63
+            double nj = (double)rj * mc.inv_fix * mc.scale;
             if (n_out) n_out[j] = nj;
             run += nj - mc.n0;
             D_s[j] = run;                              // inclusive prefix inside this thread's run of cells

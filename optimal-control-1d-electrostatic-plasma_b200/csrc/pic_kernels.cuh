@@ -384,7 +384,7 @@ __global__ void __launch_bounds__(THREADS) field_finalize_kernel(const FinalizeA
             }
         }
         for (int j = tid; j < M; j += THREADS) a.rho_reduced[j] = rho(j);
-        t = block_field<double, THREADS>(rho, sm.E_s, sm.D_s, sm.red, a.mc, none, a.n_out, a.E_out, s2, s1, [] {}, mo);
+        t = block_field<double, THREADS>(rho, sm.E_s, sm.D_s, sm.red, a.mc, none, a.n_out, a.E_out, s2, s1, [] {}, mo, a.err);
     } else {
         GlobalRho rho{a.rho + (size_t)env * M};
         if (a.partial) {
@@ -392,7 +392,7 @@ __global__ void __launch_bounds__(THREADS) field_finalize_kernel(const FinalizeA
             for (int i = tid; i < a.n_partial; i += THREADS) { s2 += p[2 * i]; s1 += p[2 * i + 1]; }
         }
         t = block_field<double, THREADS>(rho, sm.E_s, sm.D_s, sm.red, a.mc, none,
-                                         a.n_out + (size_t)env * M, a.E_out + (size_t)env * M, s2, s1, [] {}, mo);
+                                         a.n_out + (size_t)env * M, a.E_out + (size_t)env * M, s2, s1, [] {}, mo, a.err);
     }
     if (a.rho_zero) for (int j = tid; j < M; j += THREADS) a.rho_zero[(size_t)env * M + j] = 0ull;
     if (tid == 0) {
@@ -511,7 +511,7 @@ __global__ void __launch_bounds__(THREADS, THREADS <= 512 ? 1024 / THREADS : 1) 
         double s2, s1;
         kinetic(s2, s1);
         const ModeOut mo{a.tw_cos, a.tw_sin, a.modes ? a.modes + (size_t)env * 2 * a.n_modes : nullptr, a.n_modes};
-        write_diag(block_field<R, THREADS>(rho, sm.E_s, sm.D_s, sm.red, a.mc, none, n_out, E_out, s2, s1, clear_hist, mo),
+        write_diag(block_field<R, THREADS>(rho, sm.E_s, sm.D_s, sm.red, a.mc, none, n_out, E_out, s2, s1, clear_hist, mo, a.err),
                    -1, nullptr);
     }
 
@@ -556,7 +556,7 @@ __global__ void __launch_bounds__(THREADS, THREADS <= 512 ? 1024 / THREADS : 1) 
                 }
                 const ModeOut mo{a.tw_cos, a.tw_sin, mout, a.n_modes};
                 write_diag(block_field<R, THREADS>(rho, sm.E_s, sm.D_s, sm.red, a.mc, none, last ? n_out : nullptr,
-                                                   last ? E_out : nullptr, s2, s1, clear_hist, mo), step, ext.coeff);
+                                                   last ? E_out : nullptr, s2, s1, clear_hist, mo, a.err), step, ext.coeff);
             }
         }
     }
