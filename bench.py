@@ -117,23 +117,52 @@ def run_reference_arm(args):
 
 # ---------------------------------------------------------------------------------------------- clocks
 class ClockSampler:
+    """SM clock, power and throttle reasons sampled DURING a timed region (NVML every 10 ms; nvidia-smi as fallback)."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         self.index, self.rows, self._stop, self._t = index, [], threading.Event(), None
+        self.max_mhz = None
+        self._nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and all(t.strip().isdigit() for t in vis.split(",")) else index
+            self._dev = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self._dev, pynvml.NVML_CLOCK_SM))
+            self._nvml = pynvml
+        except Exception:
+            self._nvml = None
+
+    def _sample_nvml(self):
+        n = self._nvml
+        sm = float(n.nvmlDeviceGetClockInfo(self._dev, n.NVML_CLOCK_SM))
+        pw = n.nvmlDeviceGetPowerUsage(self._dev) / 1000.0
+        r = n.nvmlDeviceGetCurrentClocksThrottleReasons(self._dev)
+        flags = [bool(r & n.nvmlClocksThrottleReasonHwSlowdown), bool(r & n.nvmlClocksThrottleReasonHwThermalSlowdown),
+                 bool(r & n.nvmlClocksThrottleReasonSwThermalSlowdown), bool(r & n.nvmlClocksThrottleReasonSwPowerCap)]
+        self.rows.append((sm, pw, flags))
+
+    def _sample_smi(self):
+        out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
+                             capture_output=True, text=True, timeout=5).stdout
+        p = [t.strip() for t in out.strip().split(",")]
+        if len(p) >= 7:
+            self.max_mhz = float(p[1])
+            self.rows.append((float(p[0]), float(p[2]), [t.lower().startswith("active") for t in p[3:7]]))
 
     def _run(self):
         while not self._stop.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                parts = [p.strip() for p in out.strip().split(",")]
-                if len(parts) >= 7:
-                    self.rows.append(parts)
+                if self._nvml:
+                    self._sample_nvml()
+                else:
+                    self._sample_smi()
             except Exception:
                 pass
-            self._stop.wait(0.1)
+            self._stop.wait(0.01 if self._nvml else 0.1)
 
     def __enter__(self):
         self._t = threading.Thread(target=self._run, daemon=True)
@@ -146,12 +175,12 @@ class ClockSampler:
 
     def summary(self):
         if not self.rows:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
-        sm = [float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit()]
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unavailable"]}
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(r[3 + i].lower().startswith("active") for r in self.rows)]
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(self.rows[0][1]),
-                "power_w_max": max(float(r[2]) for r in self.rows), "samples": len(self.rows), "reasons": reasons}
+        reasons = [nm for i, nm in enumerate(names) if any(r[2][i] for r in self.rows)]
+        return {"sm_mhz": float(np.median([r[0] for r in self.rows])), "sm_max_mhz": self.max_mhz,
+                "power_w_max": max(r[1] for r in self.rows), "samples": len(self.rows), "reasons": reasons,
+                "source": "nvml" if self._nvml else "nvidia-smi"}
 
 
 # ---------------------------------------------------------------------------------------------- GPU arm

@@ -164,6 +164,37 @@ class PIC:
     def E_mesh(self):
         return self._fields()[1]
 
+    @property
+    def phi_mesh(self):
+        """Potential on the mesh, (N_mesh, 1), of the same 3-point discretisation (laplacian @ phi = n - n0) in the
+        zero-mean gauge.  A derived read-out for API completeness (no runner uses it), rebuilt on the host from the
+        device's density; the reference's own additive constant is numerical noise of its singular solve (its
+        Sherman-Morrison denominator is ~1e-15), so only differences of phi -- i.e. E -- are comparable."""
+        b = self.n - self.n0
+        S = np.cumsum(b)
+        D = self.dx * self.dx * (S - S.mean())           # D_j = phi_{j+1} - phi_j
+        phi = np.concatenate([[0.0], np.cumsum(D[:-1])])
+        return (phi - phi.mean()).reshape(-1, 1)
+
+    @property
+    def grad(self):
+        """Dense periodic centred-difference matrix of src/env/util.py:7-26 (attribute parity only)."""
+        M, g = self.N_mesh, np.zeros((self.N_mesh, self.N_mesh))
+        i = np.arange(M)
+        g[i, (i + 1) % M] = 1.0
+        g[i, (i - 1) % M] = -1.0
+        return g / (2 * self.dx)
+
+    @property
+    def laplacian(self):
+        """Dense periodic 3-point Laplacian of src/env/util.py:28-46 (attribute parity only)."""
+        M, a = self.N_mesh, np.zeros((self.N_mesh, self.N_mesh))
+        i = np.arange(M)
+        a[i, (i + 1) % M] = 1.0
+        a[i, (i - 1) % M] = 1.0
+        a[i, i] = -2.0
+        return a / self.dx ** 2
+
     def _cells(self):
         if "cells" not in self._cache:
             il, wl, wr, E, wm = self._engine().get_cells(want_wm=True)

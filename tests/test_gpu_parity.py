@@ -252,6 +252,10 @@ def test_pic_class_is_a_drop_in(golden):
     assert np.abs(sim.x[:, 0] - g["t10_x"]).max() < 1e-12
     assert np.array_equal(sim.indx_l[:, 0], g["t10_indx_l"].astype(np.int64))
     assert np.abs(sim.E_mesh[:, 0] - g["t10_E_mesh"]).max() < 1e-12
+    # derived attributes: phi solves the same discretisation (laplacian @ phi = n - n0) and -grad @ phi is E_mesh
+    phi = sim.phi_mesh
+    assert np.abs(sim.laplacian @ phi - (sim.n - sim.n0).reshape(-1, 1)).max() < 1e-9
+    assert np.abs(-(sim.grad @ phi) - sim.E_mesh).max() < 1e-11
     with pytest.raises(ValueError):
         PIC(N=100, N_mesh=10, interpol="NGP", init_dist=dist)
 
