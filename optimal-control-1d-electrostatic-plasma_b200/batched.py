@@ -30,7 +30,7 @@ class BatchedPIC:
     def __init__(self, n_envs: int, N: int = 5000, N_mesh: int = 250, n0: float = 1.0, L: float = 50.0,
                  dt: float = 0.05, max_mode: int = 3, *, rank: int = 0, world_size: int = 1, device: int = 0,
                  precision: str = "f64", mode: str = "auto", deposit: str = "auto", alpha: float = 1.0,
-                 beta: float = 1.0, n_actions: int = 10):
+                 beta: float = 1.0, n_actions: int = 10, interpol: str = "CIC"):
         self.n_envs_total = int(n_envs)
         self.env_lo, self.env_hi = shard_range(n_envs, rank, world_size)
         self.n_envs = self.env_hi - self.env_lo
@@ -42,7 +42,7 @@ class BatchedPIC:
         if self.dt > 2 / np.sqrt(self.N / self.L):                  # src/env/pic.py:71-72
             self.dt = 2 / np.sqrt(self.N / self.L)
         self.engine = Engine(self.N, self.N_mesh, self.L, self.dt, n0=n0, n_envs=self.n_envs, precision=precision,
-                             mode=mode, deposit=deposit, device=device, max_mode=self.max_mode)
+                             mode=mode, deposit=deposit, device=device, max_mode=self.max_mode, interpol=interpol)
         if self.max_mode > 0:
             from .actuator import E_field
             act = E_field(L, N_mesh, max_mode)

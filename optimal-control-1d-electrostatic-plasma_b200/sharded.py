@@ -43,7 +43,7 @@ def allreduce_fixed_density(t, group=None):
 class ShardedPIC:
     def __init__(self, N: int, N_mesh: int = 4096, n0: float = 1.0, L: float = 50.0, dt: float = 0.1, *,
                  rank: int = 0, world_size: int = 1, device: int = 0, precision: str = "f64",
-                 deposit: str = "auto", collective: str = "nccl", group=None, max_mode: int = 0):
+                 deposit: str = "auto", collective: str = "nccl", group=None, max_mode: int = 0, interpol: str = "CIC"):
         self.N, self.N_mesh, self.n0, self.L = int(N), int(N_mesh), n0, L
         self.rank, self.world = int(rank), int(world_size)
         self.lo, self.hi = shard_range(self.N, self.rank, self.world)
@@ -54,7 +54,8 @@ class ShardedPIC:
         self.group = group
         self.collective = collective if self.world > 1 else "none"
         self.engine = Engine(self.N_local, self.N_mesh, self.L, self.dt, n0=n0, n_particles_total=self.N,
-                             precision=precision, mode="streaming", deposit=deposit, device=device, max_mode=max_mode)
+                             precision=precision, mode="streaming", deposit=deposit, device=device, max_mode=max_mode,
+                             interpol=interpol)
         if self.collective == "nccl":
             uid = broadcast_bytes(Engine.nccl_unique_id() if self.rank == 0 else None, 0, group)
             self.engine.comm_init_rank(uid, self.rank, self.world)
