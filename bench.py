@@ -48,8 +48,12 @@ def measured_peaks():
 
 
 # ---------------------------------------------------------------------------------------------- CPU baseline
+_WARM = False
+
+
 def _oracle_worker(args):
     """One independent sample env advanced with the faithful oracle; returns (particle_steps, seconds)."""
+    global _WARM
     n, mesh, steps, seed = args
     os.environ.setdefault("OMP_NUM_THREADS", "1")
     from oracle import pic_oracle as O      # the one place bench.py executes oracle/: the CPU baseline legs
@@ -57,8 +61,10 @@ def _oracle_worker(args):
     x = rng.uniform(0, L_BOX, n)
     v = rng.normal(size=n) + 3.0 * (rng.uniform(size=n) < 1.0 / 6.0)
     p = O.PicParams(N=n, N_mesh=mesh, n0=1.0, L=L_BOX, dt=O.clip_dt(0.1, n, L_BOX))
-    O.step(x[:2000].copy(), v[:2000].copy(), O.PicParams(N=2000, N_mesh=mesh, n0=1.0, L=L_BOX, dt=0.01), None,
-           faithful=True)                   # JIT warm-up outside the timed region
+    if not _WARM:                           # JIT warm-up outside the timed region, once per process
+        O.step(x[:2000].copy(), v[:2000].copy(), O.PicParams(N=2000, N_mesh=mesh, n0=1.0, L=L_BOX, dt=0.01), None,
+               faithful=True)
+        _WARM = True
     t0 = time.perf_counter()
     for _ in range(steps):
         o = O.step(x, v, p, None, faithful=True)
@@ -66,17 +72,19 @@ def _oracle_worker(args):
     return n * steps, time.perf_counter() - t0
 
 
-def cpu_baseline(n_sample, steps, procs):
+def cpu_baseline(n_sample, steps, procs, pool=None):
     """Throughput of the oracle port (faithful mode: the reference's 8 deposits + 8 periodic solves per step) on
     `procs` host processes, each advancing its own sample env of n_sample particles."""
     jobs = [(n_sample, N_MESH, steps, 100 + i) for i in range(procs)]
     t0 = time.perf_counter()
     if procs == 1:
         res = [_oracle_worker(jobs[0])]
+    elif pool is not None:
+        res = pool.map(_oracle_worker, jobs, chunksize=1)
     else:
         import multiprocessing as mp
-        with mp.get_context("spawn").Pool(procs) as pool:
-            res = pool.map(_oracle_worker, jobs)
+        with mp.get_context("spawn").Pool(procs) as p:
+            res = p.map(_oracle_worker, jobs, chunksize=1)
     wall = time.perf_counter() - t0
     total = sum(r[0] for r in res)
     slowest = max(r[1] for r in res)
@@ -87,17 +95,22 @@ def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    import multiprocessing as mp
     procs = max(1, min(os.cpu_count() or 1, 64))
     n_sample = 1_000_000
-    per_step = []
-    for _ in range(args.warmup):
-        cpu_baseline(n_sample, 1, procs)
-    t0 = time.perf_counter()
-    vals = []
-    for _ in range(args.steps):
-        v, slow, _ = cpu_baseline(n_sample, 1, procs)
-        vals.append(v); per_step.append(slow)
-    wall = time.perf_counter() - t0
+    per_step, vals = [], []
+    pool = mp.get_context("spawn").Pool(procs) if procs > 1 else None
+    try:
+        for _ in range(max(1, args.warmup)):
+            cpu_baseline(n_sample, 1, procs, pool)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            v, slow, _ = cpu_baseline(n_sample, 1, procs, pool)
+            vals.append(v); per_step.append(slow)
+        wall = time.perf_counter() - t0
+    finally:
+        if pool is not None:
+            pool.close(); pool.join()
     value = float(np.mean(vals))
     sample = ("oracle port (faithful: 8 deposits + 8 Thomas/Sherman-Morrison solves per step) of the reference's "
               "numpy path, %d processes x one independent env of %d particles, N_mesh=%d, 1 step per timed step; the "
