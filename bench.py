@@ -222,6 +222,7 @@ def run_gpu_arm(args):
     sim.sample_state("bump-on-tail", a=0.2, v0=3.0, sigma=1.0, A=0.1, n_mode=2, seed=42)
     info = eng.launch_info()
     N_local = sim.N_local
+    sim_dt, sim_collective = sim.dt, sim.collective
 
     def barrier():
         torch.cuda.synchronize()
@@ -378,6 +379,31 @@ def run_gpu_arm(args):
                            "atomics (and the SM clock under the power cap), not HBM"}
         bp.close()
 
+    # ---- the separate float32 mode (own tolerance: tests/test_gpu_f32.py), same workload, device-timed
+    fp32 = None
+    if not args.no_fp32:
+        del sim, eng
+        torch.cuda.empty_cache()
+        s32 = pic_b200.ShardedPIC(N, N_MESH, 1.0, L_BOX, 0.1, rank=rank, world_size=world, device=local,
+                                  collective=args.collective, precision="f32")
+        s32.sample_state("bump-on-tail", a=0.2, v0=3.0, sigma=1.0, A=0.1, n_mode=2, seed=42)
+        for _ in range(3):
+            s32.engine.step_mesh_device(None, 1)
+        barrier()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        for _ in range(args.steps):
+            s32.engine.step_mesh_device(None, 1)
+        f1.record()
+        barrier()
+        fms = max_over_ranks(f0.elapsed_time(f1)) / args.steps
+        fp32 = {"value": N / (fms * 1e-3), "unit": UNIT, "ms_per_step": fms, "bytes_per_particle_step": 52,
+                "step_frac_of_hbm": (52.0 * s32.N_local / (fms * 1e-3) / 1e9) / hbm_peak,
+                "tolerance": "per step |dx| <= 2e-5, |dv| <= 1e-5, PE rel 1e-4 vs the float64 reference; indices "
+                             "bit-exact vs the float32 restatement (tests/test_gpu_f32.py)",
+                "error_flags": int(s32.engine.error_flags())}
+        s32.engine.close()
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -385,8 +411,8 @@ def run_gpu_arm(args):
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": "large-N single env: %.3g particles, %d cells, bump-on-tail, particle-sharded over %d GPU(s)"
                                    % (N, N_MESH, world),
-                       "n_particles": N, "n_mesh": N_MESH, "L": L_BOX, "dt": sim.dt, "parallelism": "particle-shard x%d" % world,
-                       "collective": sim.collective,
+                       "n_particles": N, "n_mesh": N_MESH, "L": L_BOX, "dt": sim_dt, "parallelism": "particle-shard x%d" % world,
+                       "collective": sim_collective,
                        "l2_policy": "inputs (16 B x %.3g particles per rank) exceed the 126 MB L2" % N_local,
                        "launch": info},
             "clocks": clocks,
@@ -398,6 +424,7 @@ def run_gpu_arm(args):
             "cpu_baseline": cpu,
             "batched": batched,
             "e2e_state_roundtrip": roundtrip,
+            "fp32_mode": fp32,
             "error_flags": int(flags),
             "energy_last": energies[-1] if energies else None,
         }
@@ -423,6 +450,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-batched", action="store_true")
     ap.add_argument("--no-roundtrip", action="store_true")
+    ap.add_argument("--no-fp32", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3                                   # timing rule: at least 3 warm-up steps
