@@ -506,3 +506,25 @@ def test_extreme_clustering_and_cell_sorted_order(mode):
         rho, k = eng.get_density_fixed()
         assert sum(int(r) for r in rho.ravel()) == N * (1 << k)
         assert eng.error_flags() == 0
+
+
+@pytest.mark.parametrize("mode", ["resident", "streaming"])
+def test_exact_weights_option(golden, mode):
+    """exact_weights=True divides by dx exactly as interpolate.py:11-12 does: the CIC weights are then the
+    reference's bits, not just within an ulp."""
+    g = golden("deposit_edges")
+    L, M = 50.0, 250
+    key = f"L{L:g}_M{M}"
+    x = g[key + "_x"]
+    N = x.shape[0]
+    eng = _engine(N, M, L, 0.01, mode=mode, exact_weights=True)
+    eng.set_state(x[None], np.zeros((1, N)))
+    il, wl, wr, _ = eng.get_cells()
+    assert np.array_equal(il[0], g[key + "_cic_il"])
+    assert np.array_equal(wl[0], g[key + "_cic_wl"]) and np.array_equal(wr[0], g[key + "_cic_wr"])
+    gb = golden("bump_vb3")
+    e2 = _engine(5000, 250, 50.0, 0.1, mode=mode, exact_weights=True)
+    e2.set_state(gb["t0_x"][None], gb["t0_v"][None])
+    e2.step_mesh(None, 10)
+    xg, vg = e2.get_state()
+    assert np.abs(xg[0] - gb["t10_x"]).max() < 1e-12 and np.abs(vg[0] - gb["t10_v"]).max() < 1e-12
