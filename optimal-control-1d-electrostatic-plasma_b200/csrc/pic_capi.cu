@@ -204,15 +204,6 @@ int allreduce_u64(pic_handle* h, unsigned long long* buf, size_t count) {
     return PIC_OK;
 }
 
-__global__ void apply_vsum_kernel(const double* vsum, double* diag, double* trace, int n_envs) {
-    int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e < n_envs) {
-        diag[e * DIAG_N + DIAG_KE] = 0.5 * vsum[2 * e];
-        diag[e * DIAG_N + DIAG_SUM_V] = vsum[2 * e + 1];
-        if (trace) for (int k = 0; k < DIAG_N; ++k) trace[e * DIAG_N + k] = diag[e * DIAG_N + k];
-    }
-}
-
 template <typename R, bool EXACT_W, int IP>
 __global__ void cells_kernel(const R* __restrict__ x, long long N, long long ld, MeshConst mc, int* il,
                              double* wl, double* wr, double* wm, const double* __restrict__ Emesh, double* Ep) {
@@ -277,6 +268,17 @@ __global__ void sample_kernel(R* __restrict__ x, R* __restrict__ v, long long N,
     }
 }
 
+// collective-library sharding: the kinetic sums are all-reduced as two doubles after the finalize kernel (folding them
+// into the 64 KB state all-reduce pushes it over NCCL's low-latency protocol limit: measured +100 us per step)
+__global__ void apply_vsum_kernel(const double* vsum, double* diag, double* trace, int n_envs) {
+    int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < n_envs) {
+        diag[e * DIAG_N + DIAG_KE] = 0.5 * vsum[2 * e];
+        diag[e * DIAG_N + DIAG_SUM_V] = vsum[2 * e + 1];
+        if (trace) for (int k = 0; k < DIAG_N; ++k) trace[e * DIAG_N + k] = diag[e * DIAG_N + k];
+    }
+}
+
 // Phase-space histogram of src/control/objective.py:8-14: np.histogram2d(x, v, bins=[nb, nb], range=[[0, L],
 // [vmin, vmax]]).  Bin i of a coordinate is the largest i with edge(i) <= value, edges as np.linspace builds them
 // (i * step + start, last edge = stop exactly), the right-most edge belongs to the last bin, outliers are dropped.
@@ -328,16 +330,15 @@ int run_stage(pic_handle* h, int stage, const double* ext, const double* coeffs,
         f.rw = h->rw; f.coeffs = coeffs; f.two_m = 2 * h->m; f.step_done = trace_row != nullptr;
         f.tw_cos = h->tw_cos; f.tw_sin = h->tw_sin; f.n_modes = h->n_modes; f.modes = h->n_modes > 0 ? h->modes : nullptr;
         fill_comm(h, f.comm, h->seq_state, 0, 0, nullptr, 0);
-        f.rho_reduced = h->rho[3]; f.err = h->err;
+        const bool nccl_sharded = h->world > 1 && !h->fused;
+        f.rho_reduced = h->rho[3]; f.err = h->err; f.trace_row = nccl_sharded ? nullptr : trace_row;
         void* args[] = {&f};
         CK(h, cudaLaunchKernel((const void*)&field_finalize_kernel<256>, dim3(h->n_envs), dim3(256), args,
                                smem_plan_bytes<double>(h->M, 256, false), h->stream));
         h->launches++;
-        if (h->world > 1 && !h->fused) {
+        if (nccl_sharded) {
             int r = nccl_api().allreduce(h->vsum, h->vsum, 2 * (size_t)h->n_envs, kNcclFloat64, kNcclSum, h->comm, h->stream);
             if (r != 0) return fail(h, PIC_ENCCL, "ncclAllReduce(float64) failed");
-        }
-        if ((h->world > 1 && !h->fused) || trace_row) {
             apply_vsum_kernel<<<(h->n_envs + 127) / 128, 128, 0, h->stream>>>(h->vsum, h->diag, trace_row, h->n_envs);
             h->launches++;
         }
@@ -552,7 +553,7 @@ int pic_create(const pic_config* cfg, pic_handle** out) {
     size_t pbytes = (size_t)h->ld * h->n_envs * h->esize, mbytes = sizeof(double) * (size_t)h->M * h->n_envs;
     bool okm = cudaMalloc(&h->x, pbytes) == cudaSuccess && cudaMalloc(&h->v, pbytes) == cudaSuccess;
     okm = okm && cudaMalloc(&h->rho_block, 4 * mbytes) == cudaSuccess;
-    if (okm) {
+    if (okm) {                                       // [S][W0][W1][W2]
         const size_t sz = (size_t)h->M * h->n_envs;
         h->rho[3] = h->rho_block; h->rho[0] = h->rho_block + sz; h->rho[1] = h->rho_block + 2 * sz; h->rho[2] = h->rho_block + 3 * sz;
     }

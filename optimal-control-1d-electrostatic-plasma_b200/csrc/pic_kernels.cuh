@@ -310,6 +310,7 @@ __global__ void __launch_bounds__(THREADS) push_stream_kernel(const StreamArgs a
                 __syncthreads();
                 n_extra = 2;
             }
+
             const size_t slot = ((size_t)(a.comm.seq_out % COMM_SETS) * a.comm.world + a.comm.rank) * a.comm.slot_len;
             // each word is read once (all loads of a batch in flight together) and then posted to every peer
             constexpr int BATCH = 8;
@@ -359,6 +360,7 @@ struct FinalizeArgs {
     int n_partial;
     CommArgs comm;                     // fused exchange: consume the state density + kinetic sums of all ranks
     unsigned long long* rho_reduced;   // fused exchange: where the summed state density is stored (the S buffer)
+    double* trace_row;                 // nullptr or [n_envs][DIAG_N]: copy of the diagnostics record of this step
     unsigned* err;
 };
 
@@ -410,6 +412,8 @@ __global__ void __launch_bounds__(THREADS) field_finalize_kernel(const FinalizeA
             a.vsum[env * 2] = t.s1; a.vsum[env * 2 + 1] = t.s2;
             d[DIAG_KE] = 0.5 * t.s1; d[DIAG_SUM_V] = t.s2;
         }
+        if (a.trace_row)
+            for (int k = 0; k < DIAG_N; ++k) a.trace_row[(size_t)env * DIAG_N + k] = d[k];
     }
 }
 
