@@ -2,7 +2,7 @@
 
 The reference has no batching: its RL loops step ONE `PIC` per process (src/control/rl/ppo.py:279, sac.py:354).
 This class keeps the per-env semantics of `PIC.update_state` (every env is bit-identical to the same env run alone
-through `PIC`) and adds the env axis: one CTA per env, particles in registers for the whole step, actuator
+through `PIC`) and adds the env axis: one CTA per env, particle state in shared memory for the whole launch, actuator
 coefficients in, (KE, PE_mesh) out, all on the device.
 
 Env sharding over GPUs: envs are independent, so rank r of W simply owns envs [lo, hi) = shard_range(n_envs, r, W);

@@ -1,10 +1,11 @@
 // Kernels of the PIC hot path (sm_100a).  See pic_device.cuh for the per-particle arithmetic.
 //
-//   push_stream_kernel   large-N "streaming" mode: one launch per Yoshida sub-stage.  Persistent CTAs stream the
-//                        SoA particle arrays once (16-byte loads/stores), every CTA rebuilds the mesh field from the
-//                        previous sub-stage's fixed-point density in its prologue (one block scan, no separate
-//                        Poisson launch), gathers/kicks/drifts, and deposits into a shared-memory privatised
-//                        histogram that is flushed with 64-bit global reductions.
+//   push_stream_kernel   large-N "streaming" mode: three launches per env step (KICK, KICK, FINAL; the drift-only
+//                        first Yoshida sub-stage rides along with the pass that produces the state).  Persistent CTAs
+//                        stream the SoA particle arrays once per pass (16-byte loads/stores), every CTA rebuilds the
+//                        mesh field from the previous sub-stage's fixed-point density in its prologue (one block scan,
+//                        no separate Poisson launch), gathers/kicks/drifts, and deposits into shared-memory privatised
+//                        histograms that are flushed with 64-bit global reductions.
 //   env_step_resident_kernel
 //                        small-N / batched mode: one CTA per env, particles live in shared memory for the whole
 //                        launch, all four sub-stages (and any number of env steps) run inside one launch.
@@ -28,8 +29,8 @@ constexpr int MODE_INIT = 3;    // no motion: wrap in place + deposit (pic.py:76
 // Particle-sharded mode without a collective library in the step loop.  Every rank owns an exchange buffer that all
 // peers can write (symmetric / peer-mapped memory): SETS slot sets x `world` slots x `slot_len` 64-bit words, plus
 // one flag word per source rank.  The LAST CTA of a push kernel (ticket counter) copies the rank's finished partial
-// density -- and, after a state-producing pass, its kinetic sums -- into slot[set][rank] of EVERY rank with 16-byte
-// peer stores, fences, and then publishes the exchange number `seq` in flag[rank] on every rank.  The next kernel's
+// density -- and, after a state-producing pass, its kinetic sums -- into slot[set][rank] of EVERY rank with peer
+// stores, fences, and then publishes the exchange number `seq` in flag[rank] on every rank.  The next kernel's
 // prologue waits until all `world` flags have reached `seq` and reads the density as the sum over the slots in rank
 // order: an integer sum, identical on every rank.  The transfer therefore overlaps the tail of the producing kernel
 // and the head of the consuming one; there is no separate reduction kernel and no host involvement.
