@@ -528,3 +528,30 @@ def test_exact_weights_option(golden, mode):
     e2.step_mesh(None, 10)
     xg, vg = e2.get_state()
     assert np.abs(xg[0] - gb["t10_x"]).max() < 1e-12 and np.abs(vg[0] - gb["t10_v"]).max() < 1e-12
+
+
+@pytest.mark.parametrize("mode", ["resident", "streaming"])
+@pytest.mark.parametrize("N,M", [(1, 2), (3, 5), (33, 7), (257, 31), (1025, 64)])
+def test_tiny_and_ragged_configs(mode, N, M):
+    """Degenerate sizes (one particle, two cells, sizes that are not multiples of any vector / warp / tile width)
+    against the oracle, with an external field."""
+    L, dt = 10.0, 0.05
+    rng = np.random.RandomState(N * 131 + M)
+    x = rng.uniform(-0.5 * L, 1.5 * L, N); v = rng.normal(size=N)
+    ext = 0.2 * np.sin(2 * np.pi * (np.arange(M) + 0.5) / M)
+    dtc = O.clip_dt(dt, N, L)
+    p = O.PicParams(N=N, N_mesh=M, n0=1.0, L=L, dt=dtc)
+    eng = _engine(N, M, L, dtc, mode=mode)
+    eng.set_state(x[None], v[None])
+    xo, vo = O.wrap(x, L), v
+    for _ in range(4):
+        o = O.step(xo, vo, p, ext)
+        xo, vo = o["x"], o["v"]
+    eng.step_mesh(ext[None], 4)
+    xg, vg = eng.get_state()
+    assert np.abs(xg[0] - xo).max() < 1e-11 and np.abs(vg[0] - vo).max() < 1e-11
+    il, *_ = eng.get_cells(False, False)
+    assert np.array_equal(il[0], o["indx_l"])
+    n, E = eng.get_fields()
+    assert np.abs(E[0] - o["E_mesh"]).max() < 1e-11 * max(1.0, np.abs(o["E_mesh"]).max())
+    assert eng.error_flags() == 0
