@@ -332,9 +332,9 @@ def run_gpu_arm(args):
                 "traffic": traffic, "traffic_source": traffic_src,
                 "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": kick_ms,
                 "stage_ms": [float(s) for s in stage_ms],
-                "stage_names": ["kick (32 B)", "kick (32 B)", "final + next stage 0 (40 B)", "field finalize"],
-                "bytes_per_particle_step": 104,
-                "step_frac_of_hbm": (104.0 * N_local / (float(stage_ms.sum()) * 1e-3) / 1e9) / hbm_peak}
+                "stage_names": ["kick (32 B)", "kick (32 B)", "final + next stage-0 deposit (32 B)", "field finalize"],
+                "bytes_per_particle_step": 96,
+                "step_frac_of_hbm": (96.0 * N_local / (float(stage_ms.sum()) * 1e-3) / 1e9) / hbm_peak}
     flags = eng.error_flags()
 
     # ---- CPU baseline beside it (rank 0, N=1 only)
@@ -397,8 +397,8 @@ def run_gpu_arm(args):
         f1.record()
         barrier()
         fms = max_over_ranks(f0.elapsed_time(f1)) / args.steps
-        fp32 = {"value": N / (fms * 1e-3), "unit": UNIT, "ms_per_step": fms, "bytes_per_particle_step": 52,
-                "step_frac_of_hbm": (52.0 * s32.N_local / (fms * 1e-3) / 1e9) / hbm_peak,
+        fp32 = {"value": N / (fms * 1e-3), "unit": UNIT, "ms_per_step": fms, "bytes_per_particle_step": 48,
+                "step_frac_of_hbm": (48.0 * s32.N_local / (fms * 1e-3) / 1e9) / hbm_peak,
                 "tolerance": "per step |dx| <= 2e-5, |dv| <= 1e-5, PE rel 1e-4 vs the float64 reference; indices "
                              "bit-exact vs the float32 restatement (tests/test_gpu_f32.py)",
                 "error_flags": int(s32.engine.error_flags())}

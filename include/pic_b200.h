@@ -176,8 +176,8 @@ int64_t pic_comm_exchange_words(const pic_handle* h, int32_t world_size);
 int pic_comm_init_peer(pic_handle* h, int32_t rank, int32_t world_size, void* const* exchange_ptrs,
                        void* const* flag_ptrs, int64_t exchange_words);
 /* Alternative used when the collective is driven from the host side (e.g. torch.distributed): run sub-stage
- * `stage` (1..3, 4 = finalize, -1 = init deposit; 0 is a no-op because the drift-only stage 0 of a step is executed
- * ahead of time by stage 3 / init of the state it starts from) and leave the local density in the buffer returned
+ * `stage` (1..3, 4 = finalize, -1 = init deposit; 0 is a no-op because the deposit of the drift-only stage 0 is done
+ * ahead of time by stage 3 / init of the state it starts from, and stage 1 redoes the drift itself on load) and leave the local density in the buffer returned
  * by pic_stage_density for the caller to all-reduce in place: [n_envs][n_mesh] uint64 for stages 1 and 2,
  * 2 x [n_envs][n_mesh] (state density followed by the next step's stage-0 density) for stages 3 and -1. */
 int pic_run_stage(pic_handle* h, int32_t stage);

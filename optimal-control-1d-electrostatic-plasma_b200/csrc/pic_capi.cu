@@ -77,7 +77,6 @@ struct pic_handle {
 
     // device buffers
     void *x = nullptr, *v = nullptr;
-    void* xp = nullptr;                             // streaming: x1 = state + c0 v dt of the NEXT step (stage 0 done ahead)
     unsigned long long* rho_block = nullptr;        // one allocation [S][W0][W1][W2], each n_envs * M
     unsigned long long* rho[4] = {nullptr, nullptr, nullptr, nullptr};   // W0, W1, W2, S (S and W0 are adjacent)
     double *n = nullptr, *E = nullptr, *diag = nullptr, *vsum = nullptr, *partial = nullptr;
@@ -162,7 +161,7 @@ int configure_launch(pic_handle* h) {
         return PIC_OK;
     }
     int occ_min = 1 << 30;
-    for (int mode = MODE_KICK; mode <= MODE_INIT; ++mode) {
+    for (int mode = MODE_KICK; mode <= MODE_KICK0; ++mode) {
         const void* k = stream_kernel(h, mode);
         if (!k) return fail(h, PIC_EUNSUPPORTED, "no streaming kernel variant for threads=" + std::to_string(h->threads) +
                             " unroll=" + std::to_string(h->per_thread));
@@ -353,12 +352,12 @@ int run_stage(pic_handle* h, int stage, const double* ext, const double* coeffs,
     int mode;
     unsigned long long* reduce = nullptr; size_t reduce_count = sz;
     switch (stage) {
-        case -1: mode = MODE_INIT; a.rho_out = h->rho[3]; a.rho_next = h->rho[0]; a.x_next = h->xp; a.c = 0; a.d = 0;
+        case -1: mode = MODE_INIT; a.rho_out = h->rho[3]; a.rho_next = h->rho[0]; a.c = 0; a.d = 0;
                  reduce = h->rho[3]; reduce_count = 2 * sz; break;
-        case 1: mode = MODE_KICK; a.x_in = h->xp; a.rho_in = h->rho[0]; a.rho_out = h->rho[1]; a.rho_zero = h->rho[3];
+        case 1: mode = MODE_KICK0; a.c_pre = h->cs[0]; a.rho_in = h->rho[0]; a.rho_out = h->rho[1]; a.rho_zero = h->rho[3];
                 reduce = h->rho[1]; break;
         case 2: mode = MODE_KICK; a.rho_in = h->rho[1]; a.rho_out = h->rho[2]; a.rho_zero = h->rho[0]; reduce = h->rho[2]; break;
-        case 3: mode = MODE_FINAL; a.rho_in = h->rho[2]; a.rho_out = h->rho[3]; a.rho_next = h->rho[0]; a.x_next = h->xp;
+        case 3: mode = MODE_FINAL; a.rho_in = h->rho[2]; a.rho_out = h->rho[3]; a.rho_next = h->rho[0];
                 a.rho_zero = h->rho[1]; reduce = h->rho[3]; reduce_count = 2 * sz; break;
         default: return fail(h, PIC_EINVAL, "stage must be -1..4");
     }
@@ -566,10 +565,6 @@ int pic_create(const pic_config* cfg, pic_handle** out) {
         okm = cudaMalloc(&h->bcos, sizeof(double) * (size_t)h->M * h->m) == cudaSuccess &&
               cudaMalloc(&h->bsin, sizeof(double) * (size_t)h->M * h->m) == cudaSuccess;
     if (!okm) { std::string e = cudaGetErrorString(cudaGetLastError()); pic_destroy(h); return fail(nullptr, PIC_ENOMEM, "cudaMalloc: " + e); }
-    if (okm && !h->resident) {
-        if (cudaMalloc(&h->xp, pbytes) != cudaSuccess) { pic_destroy(h); return fail(nullptr, PIC_ENOMEM, "cudaMalloc of the stage-0 buffer"); }
-        cudaMemsetAsync(h->xp, 0, pbytes, h->stream);
-    }
     cudaMemsetAsync(h->x, 0, pbytes, h->stream);
     cudaMemsetAsync(h->v, 0, pbytes, h->stream);
     cudaMemsetAsync(h->rho_block, 0, 4 * mbytes, h->stream);
@@ -589,7 +584,7 @@ int pic_destroy(pic_handle* h) {
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
     if (h->own_comm && h->comm && nccl_api().destroy) nccl_api().destroy(h->comm);
-    void* bufs[] = {h->x, h->v, h->xp, h->rho_block, h->n, h->E, h->diag, h->vsum, h->partial,
+    void* bufs[] = {h->x, h->v, h->rho_block, h->n, h->E, h->diag, h->vsum, h->partial,
                     h->ext, h->coeffs, h->bcos, h->bsin, h->trace, h->stage64, h->err, h->tw_cos, h->tw_sin, h->modes,
                     h->mode_trace, h->ph_counts, h->ph_feq, h->ph_kl, h->ticket};
     for (void* b : bufs) if (b) cudaFree(b);

@@ -21,9 +21,10 @@ namespace pic {
 // Sub-stages of the streaming mode.  Stage 0 of every step (d == 0, a pure drift, integration.py:71) is executed
 // ahead of time by the kernel that produces the state it starts from (MODE_FINAL / MODE_INIT, see next_stage0), so an
 // env step is three passes over the particles: KICK, KICK, FINAL.
-constexpr int MODE_KICK = 1;    // stages 1,2: kick + drift                    (integration.py:72-73)
+constexpr int MODE_KICK = 1;    // stage 2: kick + drift                       (integration.py:72-73)
 constexpr int MODE_FINAL = 2;   // stage 3: kick + drift + state wrap (pic.py:139) + kinetic sums, then stage 0 of the next step
 constexpr int MODE_INIT = 3;    // no motion: wrap in place + deposit (pic.py:76 / util.py:51), then stage 0 of the next step
+constexpr int MODE_KICK0 = 4;   // stage 1: the stage-0 drift redone on load (its deposit happened a pass ago), then kick + drift
 
 // ------------------------------------------------------------------ fused density exchange over NVLink
 // Particle-sharded mode without a collective library in the step loop.  Every rank owns an exchange buffer that all
@@ -98,10 +99,8 @@ struct ActuatorArgs {
 
 struct StreamArgs {
     MeshConst mc;
-    void* x;                           // [n_envs][ld] particle positions (R): read (unless x_in) and written
+    void* x;                           // [n_envs][ld] particle positions (R): read and written in place
     void* v;                           // [n_envs][ld] particle velocities (R)
-    const void* x_in;                  // nullptr, or where this sub-stage reads its positions (stage 1: the drifted x1)
-    void* x_next;                      // MODE_FINAL / MODE_INIT: receives x1 = state + c0 v dt of the next step
     long long N, ld;
     const unsigned long long* rho_in;  // [n_envs][M] density of the previous sub-stage (MODE_KICK / MODE_FINAL)
     unsigned long long* rho_out;       // [n_envs][M] must be zero on entry
@@ -109,7 +108,8 @@ struct StreamArgs {
     unsigned long long* rho_zero;      // [n_envs][M] or nullptr: cleared for a later sub-stage
     ActuatorArgs act;
     double c, d;
-    double c_next;                     // c0 of the Yoshida scheme
+    double c_next;                     // c0 of the Yoshida scheme (MODE_FINAL / MODE_INIT: stage 0 of the next step)
+    double c_pre;                      // MODE_KICK0: c0, the stage-0 drift redone on load
     CommArgs comm;                     // fused exchange over peer memory (world <= 1: off)
     double* partial;                   // [n_envs][gridDim.x][2] per-CTA sum v^2, sum v (MODE_FINAL / MODE_INIT)
     unsigned* err;
@@ -171,8 +171,8 @@ __global__ void __launch_bounds__(THREADS) push_stream_kernel(const StreamArgs a
     extern __shared__ __align__(16) unsigned char smem_raw[];
     using V = typename RT<R>::vec;
     constexpr int VEC = RT<R>::VEC;
-    static_assert(MODE == MODE_KICK || MODE == MODE_FINAL || MODE == MODE_INIT, "unknown sub-stage");
-    constexpr bool KICK = (MODE == MODE_KICK || MODE == MODE_FINAL);
+    static_assert(MODE == MODE_KICK || MODE == MODE_KICK0 || MODE == MODE_FINAL || MODE == MODE_INIT, "unknown sub-stage");
+    constexpr bool KICK = (MODE != MODE_INIT);
     constexpr bool SUMS = (MODE == MODE_FINAL || MODE == MODE_INIT);      // these also run stage 0 of the next step
     const int tid = threadIdx.x, env = blockIdx.y, M = a.mc.M;
     SmemLayout<R> sm(smem_raw, M, false, IP, SUMS);
@@ -203,36 +203,32 @@ __global__ void __launch_bounds__(THREADS) push_stream_kernel(const StreamArgs a
 
     R* xe = (R*)a.x + (size_t)env * a.ld;
     R* ve = (R*)a.v + (size_t)env * a.ld;
-    const R* xie = a.x_in ? (const R*)a.x_in + (size_t)env * a.ld : xe;
-    R* xne = SUMS ? (R*)a.x_next + (size_t)env * a.ld : nullptr;
     V* xv = (V*)xe;
     V* vv = (V*)ve;
-    const V* xiv = (const V*)xie;
-    V* xnv = (V*)xne;
     const long long nvec = a.N / VEC;
-    const R cc = (R)a.c, dd = (R)a.d, c0 = (R)a.c_next;
+    // c0: MODE_KICK0 re-drifts the state on load, MODE_FINAL / MODE_INIT drift the state they produce
+    const R cc = (R)a.c, dd = (R)a.d, c0 = (R)(MODE == MODE_KICK0 ? a.c_pre : a.c_next);
     unsigned err = 0;
     double s2 = 0.0, s1 = 0.0;
 
-    // x, v: updated in place; xn: x1 of the next step (MODE_FINAL / MODE_INIT only)
-    auto one = [&](R& x, R& v, R& xn, auto full_warp) {
+    // x, v: updated in place
+    auto one = [&](R& x, R& v, auto full_warp) {
         constexpr bool FW = decltype(full_warp)::value;
+        if (MODE == MODE_KICK0) x = drift<R>(x, v, c0, pc);             // stage 0 (its deposit was done a pass ago)
         particle_substage<R, IP, KICK, MODE != MODE_INIT, EXACT_W, FW>(x, v, hist, sm.E_s, cc, dd, pc, a.mc, SUMS, err);
         if (SUMS) {
             s2 += (double)v * (double)v; s1 += (double)v;
-            xn = next_stage0<R, IP, EXACT_W, FW>(x, v, hist_next, c0, pc, a.mc, err);
+            next_stage0<R, IP, EXACT_W, FW>(x, v, hist_next, c0, pc, a.mc, err);
         }
     };
     auto vec_pair = [&](long long i, auto full_warp) {      // one 16-byte vector of x and of v
-        V xq = ld_stream(xiv + i), vq = ld_stream(vv + i), xnq;
+        V xq = ld_stream(xv + i), vq = ld_stream(vv + i);
         R* px = reinterpret_cast<R*>(&xq);
         R* pv = reinterpret_cast<R*>(&vq);
-        R* pn = reinterpret_cast<R*>(&xnq);
 #pragma unroll
-        for (int e = 0; e < VEC; ++e) one(px[e], pv[e], pn[e], full_warp);
+        for (int e = 0; e < VEC; ++e) one(px[e], pv[e], full_warp);
         st_stream(xv + i, xq);
         if (KICK) st_stream(vv + i, vq);
-        if (SUMS) st_stream(xnv + i, xnq);
     };
 
     // full tiles: every lane of every warp has work, so warp-wide primitives may use the full mask
@@ -242,18 +238,15 @@ __global__ void __launch_bounds__(THREADS) push_stream_kernel(const StreamArgs a
         const long long base = tile * TILE + tid;
         V xs[UNROLL], vs[UNROLL];
 #pragma unroll
-        for (int u = 0; u < UNROLL; ++u) { xs[u] = ld_stream(xiv + base + u * THREADS); vs[u] = ld_stream(vv + base + u * THREADS); }
+        for (int u = 0; u < UNROLL; ++u) { xs[u] = ld_stream(xv + base + u * THREADS); vs[u] = ld_stream(vv + base + u * THREADS); }
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u) {
-            V xnq;
             R* px = reinterpret_cast<R*>(&xs[u]);
             R* pv = reinterpret_cast<R*>(&vs[u]);
-            R* pn = reinterpret_cast<R*>(&xnq);
 #pragma unroll
-            for (int e = 0; e < VEC; ++e) one(px[e], pv[e], pn[e], std::true_type{});
+            for (int e = 0; e < VEC; ++e) one(px[e], pv[e], std::true_type{});
             st_stream(xv + base + u * THREADS, xs[u]);
             if (KICK) st_stream(vv + base + u * THREADS, vs[u]);
-            if (SUMS) st_stream(xnv + base + u * THREADS, xnq);
         }
     }
     // ragged remainder (< one tile of vectors) and the scalar tail (N not a multiple of the vector width)
@@ -263,11 +256,10 @@ __global__ void __launch_bounds__(THREADS) push_stream_kernel(const StreamArgs a
     if (blockIdx.x == 0) {
         long long i = nvec * VEC + tid;
         if (i < a.N) {
-            R x = xie[i], v = ve[i], xn = (R)0;
-            one(x, v, xn, std::false_type{});
+            R x = xe[i], v = ve[i];
+            one(x, v, std::false_type{});
             xe[i] = x;
             if (KICK) ve[i] = v;
-            if (SUMS) xne[i] = xn;
         }
     }
     __syncthreads();

@@ -2,7 +2,7 @@
 
 Times every streaming sub-stage kernel (CUDA events on the launching stream) for a grid of launch shapes and
 deposit flavours, and the resident batched kernel for its shapes.  Prints achieved algorithmic GB/s
-(32 B/particle for stages 1-2, 40 B for stage 3 which also runs stage 0 of the next step) and writes gpurun_out/kbench.json.
+(32 B/particle per pass; stage 3 also deposits stage 0 of the next step) and writes gpurun_out/kbench.json.
 """
 import argparse
 import json
@@ -94,7 +94,7 @@ def main():
                         eng.set_state_device(xin.data_ptr(), vin.data_ptr())
                         mean, best = time_stages(eng, a.reps)
                         esz = 4 if prec == "f32" else 8
-                        bytes_ = np.array([4, 4, 5]) * esz * N          # kick, kick, final + next stage 0
+                        bytes_ = np.array([4, 4, 4]) * esz * N          # kick, kick, final (+ next stage-0 deposit)
                         gbs = bytes_ / (mean[:3] * 1e-3) / 1e9
                         info = eng.launch_info()
                         rec = dict(prec=prec, order=oname, dep=dep, threads=th, unroll=un, occ_req=occ, grid=info["grid_x"],

@@ -14,7 +14,7 @@ for interpol in ("CIC", "TSC"):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(); eng.step_mesh_device(None, 10); e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / 10
-    print("streaming %s: %.3f ms/step  %.2f G particle-steps/s  (%.0f GB/s of 104 B)" % (interpol, ms, N / ms / 1e6, 104 * N / ms / 1e6), flush=True)
+    print("streaming %s: %.3f ms/step  %.2f G particle-steps/s  (%.0f GB/s of 96 B)" % (interpol, ms, N / ms / 1e6, 96 * N / ms / 1e6), flush=True)
     eng.close()
     B = 4096
     bp = pic_b200.Engine(5000, 250, L, 0.05, n_envs=B, mode="resident", max_mode=3, interpol=interpol)
