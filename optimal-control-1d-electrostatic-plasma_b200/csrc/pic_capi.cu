@@ -515,6 +515,7 @@ int pic_create(const pic_config* cfg, pic_handle** out) {
 
     MeshConst& mc = h->mc;
     mc.M = h->M; mc.L = cfg->L; mc.dx = cfg->L / cfg->n_mesh; mc.inv_dx = 1.0 / mc.dx; mc.n0 = cfg->n0; mc.dt = cfg->dt;
+    mc.dx2 = mc.dx * mc.dx; mc.inv2dx = 1.0 / (2.0 * mc.dx);
     mc.scale = cfg->n0 * cfg->L / (double)h->Ntotal / mc.dx;
     int k = cfg->fixed_bits;
     if (k <= 0) {                                         // headroom: 8x the mean per-cell weight sum below 2^62

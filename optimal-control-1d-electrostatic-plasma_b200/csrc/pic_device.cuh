@@ -125,6 +125,7 @@ template <> struct PairT<float> { using type = float2; };
 struct MeshConst {
     int M;                 // N_mesh
     double L, dx, inv_dx;  // dx = L / N_mesh (src/env/pic.py:36)
+    double dx2, inv2dx;    // dx * dx, 1 / (2 dx): field-solve constants
     double n0;
     double scale;          // n0 * L / N / dx, left to right (src/env/interpolate.py:18)
     double fix_scale;      // 2^k
@@ -401,7 +402,8 @@ struct ExtSrc {
 //   n_out/E_out : nullptr or global outputs of the density (interpolate.py:18) / self-consistent field
 //   x1, x2   : two per-thread values summed over the block on the way (kinetic sums)
 //   modes    : optional Fourier read-out of the self-consistent field (written by warp 0 after barrier C)
-// Returns {sum_j E_j^2 (self-consistent field), sum x1, sum x2}; valid in warp 0 only.
+// Returns {sum_j E_j^2 (self-consistent field), sum x1, sum x2}; valid in warp 0 only.  TOTALS = false (the field is
+// only needed for the next kick): the three block sums and their shuffles are skipped, the result is zeros.
 struct FieldTotals { double e2, s1, s2; };
 
 template <int THREADS> struct FieldShape {
@@ -418,7 +420,7 @@ __device__ __forceinline__ double warp_sum(double v) {
     return v;
 }
 
-template <typename R, int THREADS, typename RhoLoad, typename IdleWork>
+template <typename R, int THREADS, bool TOTALS = true, typename RhoLoad, typename IdleWork>
 __device__ __forceinline__ FieldTotals block_field(RhoLoad rho, typename PairT<R>::type* E_s, double* D_s, double* red,
                                                    const MeshConst& mc, const ExtSrc& ext, double* __restrict__ n_out,
                                                    double* __restrict__ E_out, double x1, double x2,
@@ -434,8 +436,9 @@ __device__ __forceinline__ FieldTotals block_field(RhoLoad rho, typename PairT<R
     const bool has_ext = ext.any();
     const bool want_modes = modes.out != nullptr;
 
-    double run = 0.0, excl = 0.0;
+    double run = 0.0, excl = 0.0, ext0 = 0.0;
     if (field_thread) {
+        if (has_ext && j0 < j1) ext0 = ext.at(j0);     // global loads: in flight across the scan and barrier (A)
         double ls = 0.0;
         for (int j = j0; j < j1; ++j) {
             const long long rj = (long long)rho(j);
@@ -447,6 +450,8 @@ __device__ __forceinline__ FieldTotals block_field(RhoLoad rho, typename PairT<R
             ls += run;
         }
         const double ncell = j1 > j0 ? (double)(j1 - j0) : 0.0;
+        const int wc0 = (tid - lane) * cpt;            // cells owned by this warp: a closed form, no reduction
+        const double c = (double)max(0, min(M, wc0 + 32 * cpt) - wc0);
         double inc = run;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -455,7 +460,6 @@ __device__ __forceinline__ FieldTotals block_field(RhoLoad rho, typename PairT<R
         }
         excl = inc - run;
         const double a = warp_sum(ls + ncell * excl);
-        const double c = warp_sum(ncell);
         const double wt = __shfl_sync(0xffffffffu, inc, 31);
         if (lane == 0) { red[3 * w] = wt; red[3 * w + 1] = a; red[3 * w + 2] = c; }
     }
@@ -472,7 +476,7 @@ __device__ __forceinline__ FieldTotals block_field(RhoLoad rho, typename PairT<R
         }
         const double meanS = sumS / (double)M;
         const double off = myoff + excl;
-        const double dx2 = mc.dx * mc.dx, inv2dx = 1.0 / (2.0 * mc.dx);
+        const double dx2 = mc.dx2, inv2dx = mc.inv2dx;
         double prevS = j0 == 0 ? total : off;          // S_{j0-1}; periodic: S_{-1} = S_{M-1} = total
         for (int j = j0; j < j1; ++j) {
             const int jm = j == 0 ? M - 1 : j - 1;
@@ -480,9 +484,9 @@ __device__ __forceinline__ FieldTotals block_field(RhoLoad rho, typename PairT<R
             const double E = -(dx2 * (S - meanS) + dx2 * (prevS - meanS)) * inv2dx;
             prevS = S;
             if (E_out) E_out[j] = E;
-            e2 += E * E;
+            if (TOTALS) e2 += E * E;
             if (want_modes) D_s[j] = E;                 // S_j is dead from here on; keep E_j for the read-out below
-            const double Et = has_ext ? E + ext.at(j) : E;
+            const double Et = has_ext ? E + (j == j0 ? ext0 : ext.at(j)) : E;
             E_s[j].x = (R)Et;
             E_s[jm].y = (R)Et;
         }
@@ -501,12 +505,14 @@ __device__ __forceinline__ FieldTotals block_field(RhoLoad rho, typename PairT<R
         idle_work();
     }
     if (FT == THREADS) idle_work();                    // no spare threads: everyone does it after its share
-    e2 = warp_sum(e2); x1 = warp_sum(x1); x2 = warp_sum(x2);
-    if (lane == 0) { red2[3 * w] = e2; red2[3 * w + 1] = x1; red2[3 * w + 2] = x2; }
+    if (TOTALS) {
+        e2 = warp_sum(e2); x1 = warp_sum(x1); x2 = warp_sum(x2);
+        if (lane == 0) { red2[3 * w] = e2; red2[3 * w + 1] = x1; red2[3 * w + 2] = x2; }
+    }
     __syncthreads();                                   // (C) gather table, idle work and partial sums complete
 
     FieldTotals t{0.0, 0.0, 0.0};
-    if (w == 0) {
+    if (TOTALS && w == 0) {
         t.e2 = warp_sum(lane < NW ? red2[3 * lane] : 0.0);
         t.s1 = warp_sum(lane < NW ? red2[3 * lane + 1] : 0.0);
         t.s2 = warp_sum(lane < NW ? red2[3 * lane + 2] : 0.0);

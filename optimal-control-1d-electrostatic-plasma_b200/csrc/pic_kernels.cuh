@@ -187,10 +187,10 @@ __global__ void __launch_bounds__(THREADS) push_stream_kernel(const StreamArgs a
         if (fused) {
             comm_wait(a.comm, a.comm.seq_in, a.err);
             PeerSumRho rho{comm_in_slots(a.comm, a.comm.seq_in), a.comm.slot_len, a.comm.world};
-            block_field<R, THREADS>(rho, sm.E_s, sm.D_s, sm.red, a.mc, ext, nullptr, nullptr, 0.0, 0.0, [] {});
+            block_field<R, THREADS, false>(rho, sm.E_s, sm.D_s, sm.red, a.mc, ext, nullptr, nullptr, 0.0, 0.0, [] {});
         } else {
             GlobalRho rho{a.rho_in + (size_t)env * M};
-            block_field<R, THREADS>(rho, sm.E_s, sm.D_s, sm.red, a.mc, ext, nullptr, nullptr, 0.0, 0.0, [] {});
+            block_field<R, THREADS, false>(rho, sm.E_s, sm.D_s, sm.red, a.mc, ext, nullptr, nullptr, 0.0, 0.0, [] {});
         }
     }
     hist.zero(tid, THREADS);
@@ -473,13 +473,13 @@ __global__ void __launch_bounds__(THREADS, THREADS <= 512 ? 1024 / THREADS : 1) 
     };
     double pe_pre = 0.0;
     if (tid == 0 && a.n_steps > 0) pe_pre = a.diag[(size_t)env * DIAG_N + DIAG_PE_MESH];
-    auto write_diag = [&](const FieldTotals& t, int step, const double* coeff) {
+    auto write_diag = [&](const FieldTotals& t, int step, double input_e) {
         if (tid == 0) {
             double rec[DIAG_N];
             rec[DIAG_KE] = 0.5 * t.s1; rec[DIAG_PE_MESH] = 0.5 * t.e2 * a.mc.dx; rec[DIAG_SUM_V] = t.s2; rec[DIAG_SUM_E2] = t.e2;
             rec[DIAG_REWARD] = 0.0; rec[DIAG_INPUT_E] = 0.0;
             if (step >= 0) {
-                rec[DIAG_INPUT_E] = coeff ? input_energy(coeff, 2 * a.act.m, a.rw.L) : 0.0;
+                rec[DIAG_INPUT_E] = input_e;
                 rec[DIAG_REWARD] = reward_of(a.rw, pe_pre, rec[DIAG_INPUT_E]);
                 pe_pre = rec[DIAG_PE_MESH];
             }
@@ -509,7 +509,7 @@ __global__ void __launch_bounds__(THREADS, THREADS <= 512 ? 1024 / THREADS : 1) 
         kinetic(s2, s1);
         const ModeOut mo{a.tw_cos, a.tw_sin, a.modes ? a.modes + (size_t)env * 2 * a.n_modes : nullptr, a.n_modes};
         write_diag(block_field<R, THREADS>(rho, sm.E_s, sm.D_s, sm.red, a.mc, none, n_out, E_out, s2, s1, clear_hist, mo, a.err),
-                   -1, nullptr);
+                   -1, 0.0);
     }
 
     for (int step = 0; step < a.n_steps; ++step) {
@@ -518,6 +518,8 @@ __global__ void __launch_bounds__(THREADS, THREADS <= 512 ? 1024 / THREADS : 1) 
         if (act.ext) act.ext += (size_t)step * a.ext_step_stride;
         const ExtSrc ext = stage_ext(act, env, M);
         const bool last = step == a.n_steps - 1;
+        double input_e = 0.0;                                       // loaded now, used after the last field solve
+        if (tid == 0 && ext.coeff) input_e = input_energy(ext.coeff, 2 * a.act.m, a.rw.L);
         {                                                           // stage 0: drift only (integration.py:71)
             const R cc = (R)a.c[0];
 #pragma unroll 2
@@ -527,34 +529,40 @@ __global__ void __launch_bounds__(THREADS, THREADS <= 512 ? 1024 / THREADS : 1) 
                 x_s[i] = x;
             }
             __syncthreads();
-            block_field<R, THREADS>(rho, sm.E_s, sm.D_s, sm.red, a.mc, ext, nullptr, nullptr, 0.0, 0.0, clear_hist);
+            block_field<R, THREADS, false>(rho, sm.E_s, sm.D_s, sm.red, a.mc, ext, nullptr, nullptr, 0.0, 0.0, clear_hist);
         }
 #pragma unroll 1
-        for (int st = 1; st < 4; ++st) {
+        for (int st = 1; st < 3; ++st) {                            // stages 1, 2: kick + drift
             const R cc = (R)a.c[st], dd = (R)a.d[st];
-            const bool fin = st == 3;
 #pragma unroll 2
             for (int i = tid; i < N; i += THREADS) {
                 R x = x_s[i], v = v_s[i];
-                particle_substage<R, IP, true, true, EXACT_W, false>(x, v, hist, sm.E_s, cc, dd, pc, a.mc, fin, err);
+                particle_substage<R, IP, true, true, EXACT_W, false>(x, v, hist, sm.E_s, cc, dd, pc, a.mc, false, err);
                 x_s[i] = x; v_s[i] = v;
             }
             __syncthreads();
-            if (!fin) {
-                block_field<R, THREADS>(rho, sm.E_s, sm.D_s, sm.red, a.mc, ext, nullptr, nullptr, 0.0, 0.0, clear_hist);
-            } else {
-                if (last) dump_rho();
-                double s2, s1;
-                kinetic(s2, s1);
-                double* mout = nullptr;
-                if (a.n_modes > 0) {
-                    if (a.mode_trace) mout = a.mode_trace + ((size_t)step * gridDim.x + env) * 2 * a.n_modes;
-                    else if (last && a.modes) mout = a.modes + (size_t)env * 2 * a.n_modes;
-                }
-                const ModeOut mo{a.tw_cos, a.tw_sin, mout, a.n_modes};
-                write_diag(block_field<R, THREADS>(rho, sm.E_s, sm.D_s, sm.red, a.mc, none, last ? n_out : nullptr,
-                                                   last ? E_out : nullptr, s2, s1, clear_hist, mo, a.err), step, ext.coeff);
+            block_field<R, THREADS, false>(rho, sm.E_s, sm.D_s, sm.red, a.mc, ext, nullptr, nullptr, 0.0, 0.0, clear_hist);
+        }
+        {                                                           // stage 3: kick + drift + state wrap + kinetic sums
+            const R cc = (R)a.c[3], dd = (R)a.d[3];
+            double s2 = 0.0, s1 = 0.0;
+#pragma unroll 2
+            for (int i = tid; i < N; i += THREADS) {
+                R x = x_s[i], v = v_s[i];
+                particle_substage<R, IP, true, true, EXACT_W, false>(x, v, hist, sm.E_s, cc, dd, pc, a.mc, true, err);
+                x_s[i] = x; v_s[i] = v;
+                s2 += (double)v * (double)v; s1 += (double)v;
             }
+            __syncthreads();
+            if (last) dump_rho();
+            double* mout = nullptr;
+            if (a.n_modes > 0) {
+                if (a.mode_trace) mout = a.mode_trace + ((size_t)step * gridDim.x + env) * 2 * a.n_modes;
+                else if (last && a.modes) mout = a.modes + (size_t)env * 2 * a.n_modes;
+            }
+            const ModeOut mo{a.tw_cos, a.tw_sin, mout, a.n_modes};
+            write_diag(block_field<R, THREADS>(rho, sm.E_s, sm.D_s, sm.red, a.mc, none, last ? n_out : nullptr,
+                                               last ? E_out : nullptr, s2, s1, clear_hist, mo, a.err), step, input_e);
         }
     }
     for (int i = tid; i < N; i += THREADS) { xe[i] = x_s[i]; ve[i] = v_s[i]; }
