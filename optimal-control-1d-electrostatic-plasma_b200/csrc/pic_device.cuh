@@ -83,6 +83,14 @@ template <> struct RT<double> {
         ok = __double2hiint(t) == 0x43380000;
         return __dsub_rn(t, MAGIC);
     }
+    // floor(q) the same way with a round-down add (a rounding-mode flag on the same DADD): no nearest-integer fix-up
+    static __device__ __forceinline__ double floor_magic(double q, int& i, bool& ok) {
+        const double MAGIC = 6755399441055744.0;
+        double t = __dadd_rd(q, MAGIC);
+        i = __double2loint(t);
+        ok = __double2hiint(t) == 0x43380000;
+        return __dsub_rn(t, MAGIC);
+    }
 };
 
 template <> struct RT<float> {
@@ -101,6 +109,13 @@ template <> struct RT<float> {
     static __device__ __forceinline__ float rint_magic(float q, int& i, bool& ok) {       // ok: 0 <= rint(q) < 2^22
         const float MAGIC = 12582912.0f;
         float t = __fadd_rn(q, MAGIC);
+        i = __float_as_int(t) - __float_as_int(MAGIC);
+        ok = (__float_as_int(t) >> 22) == (0x4B400000 >> 22);
+        return __fsub_rn(t, MAGIC);
+    }
+    static __device__ __forceinline__ float floor_magic(float q, int& i, bool& ok) {      // ok: 0 <= floor(q) < 2^22
+        const float MAGIC = 12582912.0f;
+        float t = __fadd_rd(q, MAGIC);
         i = __float_as_int(t) - __float_as_int(MAGIC);
         ok = (__float_as_int(t) >> 22) == (0x4B400000 >> 22);
         return __fsub_rn(t, MAGIC);
@@ -137,6 +152,7 @@ struct MeshConst {
 
 template <typename R> struct PartConst {   // per-particle constants in the particle precision
     R L, twoL, dx, inv_dx, dt, idx_thr;
+    R half_m_thr;          // 0.5 - idx_thr
 };
 
 template <typename R>
@@ -144,6 +160,7 @@ __host__ __device__ inline PartConst<R> make_part_const(const MeshConst& m) {
     PartConst<R> c;
     c.L = (R)m.L; c.twoL = (R)(2.0 * m.L); c.dx = (R)m.dx; c.inv_dx = (R)1 / c.dx; c.dt = (R)m.dt;
     c.idx_thr = (R)m.idx_thr;
+    c.half_m_thr = (R)0.5 - c.idx_thr;
     return c;
 }
 
@@ -554,13 +571,11 @@ __device__ __forceinline__ R drift(R x, R v, R cc, const PartConst<R>& c) {
 template <typename R>
 __device__ __forceinline__ bool fast_cell(R xw, const PartConst<R>& c, int M, int& il, R& f) {
     R q = RT<R>::mul(xw, c.inv_dx);
-    int i; bool ok;
-    R r = RT<R>::rint_magic(q, i, ok);
-    R diff = RT<R>::sub(q, r);
-    const bool neg = diff < (R)0;
-    f = neg ? RT<R>::sub(r, (R)1) : r;
-    il = neg ? i - 1 : i;
-    return !ok | !(RT<R>::abs(diff) > c.idx_thr) | ((unsigned)il >= (unsigned)M);
+    bool ok;
+    f = RT<R>::floor_magic(q, il, ok);
+    const R frac = RT<R>::sub(q, f);                 // exact, in [0, 1)
+    // frac in (thr, 1 - thr)  <=>  |frac - 1/2| < 1/2 - thr  (the rounding of either side is far inside the margin)
+    return !ok | !(RT<R>::abs(RT<R>::sub(frac, (R)0.5)) < c.half_m_thr) | ((unsigned)il >= (unsigned)M);
 }
 
 // the three TSC weights from the in-cell distance d = (x - m dx)/dx, formulas followed literally (interpolate.py:28-32)
