@@ -286,33 +286,45 @@ __device__ __forceinline__ unsigned atom_shared_u32(unsigned addr, unsigned v) {
     asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(addr), "r"(v) : "memory");
     return old;
 }
+// the same at a constant byte offset from addr (folded into the instruction's immediate)
+template <int OFF> __device__ __forceinline__ void red_shared_u32_at(unsigned addr, unsigned v) {
+    asm volatile("red.shared.add.u32 [%0+%2], %1;" ::"r"(addr), "r"(v), "n"(OFF) : "memory");
+}
+template <int OFF> __device__ __forceinline__ unsigned atom_shared_u32_at(unsigned addr, unsigned v) {
+    unsigned old;
+    asm volatile("atom.shared.add.u32 %0, [%1+%3], %2;" : "=r"(old) : "r"(addr), "r"(v), "n"(OFF) : "memory");
+    return old;
+}
 
+// Layout: three words per cell side by side (cnt, S.lo, S.hi), so one address computation serves all three atomics
+// (immediate offsets 0 / 4 / 8).  The stride of 3 words is coprime with the 32 banks: random cells spread over the
+// banks exactly as three separate arrays would, and a flush that walks the cells in order is conflict-free.
 template <> struct Hist<DEP_SPLIT32> {
-    unsigned *cnt, *lo, *hi;
-    unsigned cnt_a, lo_a, hi_a;          // the same arrays as shared-window byte addresses
+    unsigned* w;
+    unsigned w_a;                        // the same array as a shared-window byte address
     int M;
     static __host__ __device__ constexpr size_t bytes(int M) { return (size_t)M * 12 + 8; }
     __device__ __forceinline__ void init(void* base, int M_) {
-        M = M_; cnt = (unsigned*)base; lo = cnt + M; hi = lo + M;
-        cnt_a = (unsigned)__cvta_generic_to_shared(cnt); lo_a = cnt_a + 4u * M; hi_a = lo_a + 4u * M;
+        M = M_; w = (unsigned*)base;
+        w_a = (unsigned)__cvta_generic_to_shared(w);
     }
     __device__ __forceinline__ void zero(int tid, int nthreads) {
-        for (int j = tid; j < 3 * M; j += nthreads) cnt[j] = 0u;
+        for (int j = tid; j < 3 * M; j += nthreads) w[j] = 0u;
     }
     __device__ __forceinline__ void deposit_group(int il, unsigned long long S, unsigned count, long long) {
-        const unsigned wl = (unsigned)S, wh = (unsigned)(S >> 32), off = 4u * (unsigned)il;
-        const unsigned old = atom_shared_u32(lo_a + off, wl);
-        red_shared_u32(cnt_a + off, count);
-        red_shared_u32(hi_a + off, wh + ((old + wl) < old ? 1u : 0u));
+        const unsigned wl = (unsigned)S, wh = (unsigned)(S >> 32), cell = w_a + 12u * (unsigned)il;
+        const unsigned old = atom_shared_u32_at<4>(cell, wl);
+        red_shared_u32_at<0>(cell, count);
+        red_shared_u32_at<8>(cell, wh + ((old + wl) < old ? 1u : 0u));
     }
     __device__ __forceinline__ void deposit(int il, long long Wr, long long one) {
         deposit_group(il, (unsigned long long)Wr, 1u, one);
     }
     __device__ __forceinline__ unsigned long long S(int j) const {
-        return ((unsigned long long)hi[j] << 32) | (unsigned long long)lo[j];
+        return ((unsigned long long)w[3 * j + 2] << 32) | (unsigned long long)w[3 * j + 1];
     }
     __device__ __forceinline__ unsigned long long get(int j, long long one) const {
-        return (unsigned long long)cnt[j] * (unsigned long long)one - S(j) + S(j == 0 ? M - 1 : j - 1);
+        return (unsigned long long)w[3 * j] * (unsigned long long)one - S(j) + S(j == 0 ? M - 1 : j - 1);
     }
 };
 
