@@ -408,6 +408,8 @@ int launch_resident(pic_handle* h, int n_steps, const double* ext, const double*
     for (int i = 0; i < 4; ++i) { a.c[i] = h->cs[i]; a.d[i] = h->ds[i]; }
     a.n_out = h->n; a.E_out = h->E; a.diag = h->diag; a.trace = n_steps > 0 ? h->trace : nullptr;
     a.rho_out = h->rho[3]; a.err = h->err;
+    a.lay = h->f32 ? smem_offsets<float>(h->M, h->threads, true, h->ip, false, h->N)
+                   : smem_offsets<double>(h->M, h->threads, true, h->ip, false, h->N);
     a.rw = h->rw; a.tw_cos = h->tw_cos; a.tw_sin = h->tw_sin; a.n_modes = h->n_modes;
     a.modes = h->n_modes > 0 ? h->modes : nullptr;
     a.mode_trace = (h->n_modes > 0 && n_steps > 0) ? h->mode_trace : nullptr;
@@ -543,8 +545,15 @@ int pic_create(const pic_config* cfg, pic_handle** out) {
             delete h;
             return fail(nullptr, PIC_EUNSUPPORTED, "n_particles too large for resident mode (env does not fit in shared memory)");
         }
-        // two 512-thread CTAs per SM when two envs fit side by side (measured best), else one 1024-thread CTA
-        h->threads = 2 * (res512 + 1024) <= (size_t)h->max_smem + 1024 ? 512 : 1024;
+        // as many envs per SM as fit side by side, so that one env's field solves overlap the others' particle loops
+        // (measured best in every case tried): four 256-thread CTAs, else two of 512 threads, else one of 1024
+        const size_t res256 = h->f32 ? resident_smem_bytes<float>(h->M, 256, h->N, h->ip) : resident_smem_bytes<double>(h->M, 256, h->N, h->ip);
+        const size_t per_sm = (size_t)h->max_smem + 1024;          // every CTA reserves 1 KB on top of its request
+        h->threads = 2 * (res512 + 1024) <= per_sm ? 512 : 1024;
+        if (4 * (res256 + 1024) <= per_sm) {
+            h->threads = 256;
+            if (!resident_kernel(h)) h->threads = 512;             // variant not compiled (exact_weights)
+        }
         h->per_thread = 0;
     } else {
         h->threads = 1024; h->per_thread = 2;       // measured best: 1024 threads x 2 vectors in flight, 1 CTA per SM

@@ -131,18 +131,33 @@ __host__ __device__ constexpr size_t smem_plan_bytes(int M, int threads, bool se
          + (size_t)(field_scratch_doubles(threads) + threads / 32 + 2) * 8;   // field / reduction scratch
 }
 
+// byte offsets of the regions inside the dynamic shared memory of a CTA (the gather table sits at offset 0)
+struct SmemOffsets { unsigned hist, hist2, D, red, x, v; };
+template <typename R>
+__host__ __device__ inline SmemOffsets smem_offsets(int M, int threads, bool separate_d, int ip = IP_CIC,
+                                                    bool second_hist = false, long long n_resident = 0) {
+    SmemOffsets o;
+    size_t b = (size_t)M * 2 * sizeof(R);
+    o.hist = (unsigned)b;       b += hist_region_bytes(M, ip);
+    o.hist2 = (unsigned)b;      if (second_hist) b += hist_region_bytes(M, ip);
+    o.D = separate_d ? (unsigned)b : o.hist;
+    if (separate_d) b += (size_t)M * 8;
+    o.red = (unsigned)b;
+    o.x = (unsigned)smem_plan_bytes<R>(M, threads, separate_d, ip, second_hist);       // resident particle state
+    o.v = o.x + (unsigned)((n_resident + 1) / 2 * 2 * sizeof(R));
+    return o;
+}
+
 template <typename R>
 struct SmemLayout {
     void* hist; void* hist2; typename PairT<R>::type* E_s; double* D_s; double* red;
-    __device__ __forceinline__ SmemLayout(unsigned char* base, int M, bool separate_d, int ip = IP_CIC,
-                                          bool second_hist = false) {
-        E_s = (typename PairT<R>::type*)base;   base += (size_t)M * 2 * sizeof(R);
-        hist = base;                            base += hist_region_bytes(M, ip);
-        hist2 = base;                           if (second_hist) base += hist_region_bytes(M, ip);
-        D_s = separate_d ? (double*)base : (double*)hist;
-        if (separate_d) base += (size_t)M * 8;
-        red = (double*)base;
+    __device__ __forceinline__ SmemLayout(unsigned char* base, const SmemOffsets& o) {
+        E_s = (typename PairT<R>::type*)base;
+        hist = base + o.hist; hist2 = base + o.hist2; D_s = (double*)(base + o.D); red = (double*)(base + o.red);
     }
+    __device__ __forceinline__ SmemLayout(unsigned char* base, int M, bool separate_d, int ip = IP_CIC,
+                                          bool second_hist = false)
+        : SmemLayout(base, smem_offsets<R>(M, 0, separate_d, ip, second_hist)) {}
 };
 
 struct GlobalRho {
@@ -430,6 +445,8 @@ struct ResidentArgs {
     double* trace;                     // nullptr or [n_steps][n_envs][DIAG_N]
     unsigned long long* rho_out;       // nullptr or [n_envs][M] fixed-point state density (for parity tests)
     unsigned* err;
+    SmemOffsets lay;                   // shared-memory plan, computed on the host (smem_offsets): the kernel re-derives
+                                       // addresses inside its particle loops, and a constant-bank load is the cheapest way
 };
 
 // One CTA per env; the particle state of the env lives in SHARED memory for the whole launch (any number of env
@@ -446,9 +463,9 @@ template <typename R, int THREADS, int DEP, bool EXACT_W, int IP = IP_CIC>
 __global__ void __launch_bounds__(THREADS, THREADS <= 512 ? 1024 / THREADS : 1) env_step_resident_kernel(const ResidentArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x, env = blockIdx.x, M = a.mc.M, N = (int)a.N;
-    SmemLayout<R> sm(smem_raw, M, true, IP);
-    R* x_s = (R*)(smem_raw + smem_plan_bytes<R>(M, THREADS, true, IP));
-    R* v_s = x_s + (N + 1) / 2 * 2;
+    SmemLayout<R> sm(smem_raw, a.lay);
+    R* x_s = (R*)(smem_raw + a.lay.x);
+    R* v_s = (R*)(smem_raw + a.lay.v);
     using H = typename HistSel<DEP, IP>::type;
     H hist; hist.init(sm.hist, M);
     const PartConst<R> pc = make_part_const<R>(a.mc);
