@@ -550,7 +550,11 @@ int pic_create(const pic_config* cfg, pic_handle** out) {
         const size_t res256 = h->f32 ? resident_smem_bytes<float>(h->M, 256, h->N, h->ip) : resident_smem_bytes<double>(h->M, 256, h->N, h->ip);
         const size_t per_sm = (size_t)h->max_smem + 1024;          // every CTA reserves 1 KB on top of its request
         h->threads = 2 * (res512 + 1024) <= per_sm ? 512 : 1024;
-        if (4 * (res256 + 1024) <= per_sm) {
+        if (h->n_envs <= h->sm_count) {
+            // every env has an SM to itself: nothing to overlap, the step latency decides (measured: 1024 threads
+            // win from ~4000 particles per env, 512 below)
+            h->threads = h->N >= 4096 ? 1024 : 512;
+        } else if (4 * (res256 + 1024) <= per_sm) {
             h->threads = 256;
             if (!resident_kernel(h)) h->threads = 512;             // variant not compiled (exact_weights)
         }
