@@ -138,6 +138,7 @@ class ClockSampler:
         self.index, self.rows, self._stop, self._t = index, [], threading.Event(), None
         self.max_mhz = None
         self._nvml = None
+        self.mode = os.environ.get("PIC_BENCH_CLOCKS", "on")          # experiment switch: on | off
         try:
             import pynvml
             pynvml.nvmlInit()
@@ -178,13 +179,17 @@ class ClockSampler:
             self._stop.wait(0.01 if self._nvml else 0.1)
 
     def __enter__(self):
+        if self.mode == "off":
+            self._t = None
+            return self
         self._t = threading.Thread(target=self._run, daemon=True)
         self._t.start()
         return self
 
     def __exit__(self, *a):
         self._stop.set()
-        self._t.join(timeout=6)
+        if self._t is not None:
+            self._t.join(timeout=6)
 
     def summary(self):
         if not self.rows:
