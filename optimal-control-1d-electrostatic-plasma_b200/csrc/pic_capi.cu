@@ -343,7 +343,7 @@ int run_stage(pic_handle* h, int stage, const double* ext, const double* coeffs,
         }
         return PIC_OK;
     }
-    if (stage == 0) return PIC_OK;      // stage 0 (pure drift) was executed ahead of time by the previous stage 3 / init
+    if (stage == 0) return PIC_OK;      // stage 0 (pure drift): deposited ahead of time by stage 3 / init, redone by stage 1
     StreamArgs a{};
     a.mc = h->mc; a.x = h->x; a.v = h->v; a.N = h->N; a.ld = h->ld;
     a.act.ext = ext; a.act.coeffs = coeffs; a.act.bcos = h->bcos; a.act.bsin = h->bsin; a.act.m = h->m;

@@ -1,7 +1,8 @@
 // Kernels of the PIC hot path (sm_100a).  See pic_device.cuh for the per-particle arithmetic.
 //
-//   push_stream_kernel   large-N "streaming" mode: three launches per env step (KICK, KICK, FINAL; the drift-only
-//                        first Yoshida sub-stage rides along with the pass that produces the state).  Persistent CTAs
+//   push_stream_kernel   large-N "streaming" mode: three launches per env step (KICK0, KICK, FINAL; the deposit of the
+//                        drift-only first Yoshida sub-stage rides along with the pass that produces the state, and the
+//                        stage-1 pass redoes the drift on load).  Persistent CTAs
 //                        stream the SoA particle arrays once per pass (16-byte loads/stores), every CTA rebuilds the
 //                        mesh field from the previous sub-stage's fixed-point density in its prologue (one block scan,
 //                        no separate Poisson launch), gathers/kicks/drifts, and deposits into shared-memory privatised
@@ -18,12 +19,13 @@
 
 namespace pic {
 
-// Sub-stages of the streaming mode.  Stage 0 of every step (d == 0, a pure drift, integration.py:71) is executed
-// ahead of time by the kernel that produces the state it starts from (MODE_FINAL / MODE_INIT, see next_stage0), so an
-// env step is three passes over the particles: KICK, KICK, FINAL.
+// Sub-stages of the streaming mode.  Stage 0 of every step (d == 0, a pure drift, integration.py:71) is deposited
+// ahead of time by the kernel that produces the state it starts from (MODE_FINAL / MODE_INIT, see next_stage0) and its
+// drift is redone on load by the stage-1 kernel, so an env step is three passes over the particles of 32 bytes per
+// particle each: KICK0, KICK, FINAL.
 constexpr int MODE_KICK = 1;    // stage 2: kick + drift                       (integration.py:72-73)
-constexpr int MODE_FINAL = 2;   // stage 3: kick + drift + state wrap (pic.py:139) + kinetic sums, then stage 0 of the next step
-constexpr int MODE_INIT = 3;    // no motion: wrap in place + deposit (pic.py:76 / util.py:51), then stage 0 of the next step
+constexpr int MODE_FINAL = 2;   // stage 3: kick + drift + state wrap (pic.py:139) + kinetic sums, then the stage-0 deposit of the next step
+constexpr int MODE_INIT = 3;    // no motion: wrap in place + deposit (pic.py:76 / util.py:51), then the stage-0 deposit of the next step
 constexpr int MODE_KICK0 = 4;   // stage 1: the stage-0 drift redone on load (its deposit happened a pass ago), then kick + drift
 
 // ------------------------------------------------------------------ fused density exchange over NVLink
@@ -188,7 +190,7 @@ __global__ void __launch_bounds__(THREADS) push_stream_kernel(const StreamArgs a
     constexpr int VEC = RT<R>::VEC;
     static_assert(MODE == MODE_KICK || MODE == MODE_KICK0 || MODE == MODE_FINAL || MODE == MODE_INIT, "unknown sub-stage");
     constexpr bool KICK = (MODE != MODE_INIT);
-    constexpr bool SUMS = (MODE == MODE_FINAL || MODE == MODE_INIT);      // these also run stage 0 of the next step
+    constexpr bool SUMS = (MODE == MODE_FINAL || MODE == MODE_INIT);      // these also deposit stage 0 of the next step
     const int tid = threadIdx.x, env = blockIdx.y, M = a.mc.M;
     SmemLayout<R> sm(smem_raw, M, false, IP, SUMS);
     using H = typename HistSel<DEP, IP>::type;

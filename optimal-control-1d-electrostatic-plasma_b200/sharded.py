@@ -157,7 +157,7 @@ class ShardedPIC:
             self.engine.set_stage_actuation(self._ext_dev.data_ptr(), None)
         else:
             self.engine.set_stage_actuation(None, None)
-        for st in (1, 2, 3):                 # stage 0 of this step was done by the previous stage 3 / init
+        for st in (1, 2, 3):                 # stage 0 was deposited by the previous stage 3 / init; stage 1 redoes its drift
             self.engine.run_stage(st)
             allreduce_fixed_density(self._rho_tensor(st), self.group)
         self.engine.run_stage(4)
