@@ -35,6 +35,7 @@ UNIT = "particle-steps/s"
 N_FULL = 1_000_000_000
 N_MESH = 4096
 L_BOX = 50.0
+SETTLE_S = 0.25          # minimum wall time of the untimed warm-up (W steps + extra untimed steps), see run_gpu_arm
 FALLBACK_HBM_GBS = 6650.0
 
 
@@ -245,6 +246,17 @@ def run_gpu_arm(args):
     # ---- value: K steps, state resident in HBM, device-timed, max over ranks
     for _ in range(args.warmup):
         eng.step_mesh_device(None, 1)
+    # With many GPUs a step is ~2 ms and W steps are over before clocks and NCCL channels have settled: keep stepping,
+    # untimed, until the warm-up has lasted ~SETTLE_S.  The count is derived from one timed step (max over ranks) so
+    # that every rank runs the same number of collectives.
+    torch.cuda.synchronize()
+    t_w = time.perf_counter()
+    eng.step_mesh_device(None, 1)
+    torch.cuda.synchronize()
+    one_step_s = max_over_ranks((time.perf_counter() - t_w) * 1e3) * 1e-3
+    settle_steps = 1 + int(min(100, max(0, np.ceil(SETTLE_S / max(one_step_s, 1e-4)) - args.warmup - 1)))
+    for _ in range(settle_steps - 1):
+        eng.step_mesh_device(None, 1)
     barrier()
     l0 = eng.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -419,7 +431,7 @@ def run_gpu_arm(args):
                        "n_particles": N, "n_mesh": N_MESH, "L": L_BOX, "dt": sim_dt, "parallelism": "particle-shard x%d" % world,
                        "collective": sim_collective,
                        "l2_policy": "inputs (16 B x %.3g particles per rank) exceed the 126 MB L2" % N_local,
-                       "launch": info},
+                       "launch": info, "extra_untimed_warmup_steps": settle_steps},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": N_MESH * 8, "d2h_bytes_per_step": diag_bytes,
                     "api": "pic_step_mesh(host E_external) + pic_get_diag per step (what PIC.update_state + "
