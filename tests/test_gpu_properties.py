@@ -1,0 +1,65 @@
+"""Size-independent properties of the CUDA path at sizes the oracle cannot reach (the CPU counterparts are in
+test_oracle_properties.py): translation by whole cells, linear response of the field to the control, and
+independence of the result from how the particles are ordered in memory."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _state(N, L, seed):
+    rng = np.random.RandomState(seed)
+    x = rng.uniform(0, L, size=N)
+    v = rng.normal(size=N) + 3.0 * (rng.uniform(size=N) < 0.1667)
+    return x, v * (1 + 0.1 * np.sin(4 * np.pi * x / L))
+
+
+@pytest.mark.parametrize("mode,N,M", [("streaming", 3_000_001, 4096), ("resident", 5000, 250)])
+def test_translation_by_whole_cells(mode, N, M):
+    from pic_b200 import Engine
+    L, dt, steps, shift = 50.0, 0.02, 5, 37
+    x, v = _state(N, L, 11)
+    s = shift * (L / M)
+    a = Engine(N, M, L, dt, mode=mode); a.set_state(x[None], v[None]); a.step_mesh(None, steps)
+    b = Engine(N, M, L, dt, mode=mode); b.set_state(np.mod(x + s, L)[None], v[None]); b.step_mesh(None, steps)
+    xa, va = a.get_state(); xb, vb = b.get_state()
+    d = np.abs(np.mod(xa[0] + s, L) - xb[0]); d = np.minimum(d, L - d)
+    assert d.max() < 1e-9 and np.abs(va[0] - vb[0]).max() < 1e-9
+    na, Ea = a.get_fields(); nb, Eb = b.get_fields()
+    assert np.abs(np.roll(na[0], shift) - nb[0]).max() < 1e-9 * na.max()
+    assert np.abs(np.roll(Ea[0], shift) - Eb[0]).max() < 1e-9 * max(1.0, np.abs(Ea).max())
+    assert a.error_flags() == 0 and b.error_flags() == 0
+
+
+@pytest.mark.parametrize("mode,N,M", [("streaming", 2_000_003, 4096), ("resident", 5000, 250)])
+def test_particle_order_does_not_matter(mode, N, M):
+    """Integer deposit: the density -- and with it every particle's trajectory -- is bit-identical for any
+    permutation of the particles in memory (which changes warps, CTAs and the order of every atomic)."""
+    from pic_b200 import Engine
+    L, dt, steps = 50.0, 0.02, 6
+    x, v = _state(N, L, 5)
+    perm = np.random.RandomState(1).permutation(N)
+    a = Engine(N, M, L, dt, mode=mode); a.set_state(x[None], v[None]); a.step_mesh(None, steps)
+    b = Engine(N, M, L, dt, mode=mode); b.set_state(x[perm][None], v[perm][None]); b.step_mesh(None, steps)
+    xa, va = a.get_state(); xb, vb = b.get_state()
+    assert np.array_equal(xa[0][perm], xb[0]) and np.array_equal(va[0][perm], vb[0])
+    ra, _ = a.get_density_fixed(); rb, _ = b.get_density_fixed()
+    assert np.array_equal(ra, rb)
+    assert np.array_equal(a.get_fields()[1], b.get_fields()[1])
+
+
+def test_external_field_enters_linearly_in_the_first_kick():
+    """One step from the same state with E_ext, 2 E_ext and none: to first order in dt the velocity change due to
+    the control is linear in it (the self-consistent feedback enters at higher order)."""
+    from pic_b200 import Engine
+    N, M, L, dt = 1_000_003, 1024, 50.0, 1e-3
+    x, v = _state(N, L, 3)
+    ext = 0.05 * np.sin(2 * np.pi * np.arange(M) / M)
+    out = []
+    for f in (0.0, 1.0, 2.0):
+        e = Engine(N, M, L, dt, mode="streaming"); e.set_state(x[None], v[None])
+        e.step_mesh(None if f == 0.0 else (f * ext)[None], 1)
+        out.append(e.get_state()[1][0])
+    d1, d2 = out[1] - out[0], out[2] - out[0]
+    assert np.abs(d1).max() > 1e-6                            # the control did something
+    assert np.abs(d2 - 2 * d1).max() < 1e-6 * np.abs(d1).max()
