@@ -418,10 +418,11 @@ struct ExtSrc {
 // (src/env/util.py:99-100) without forming phi.
 //
 // Block-cooperative with TWO block barriers (A after the per-thread prefix sums, C before the result is used).
-// The first FIELD_THREADS (<= 256) threads own contiguous runs of cells; each warp publishes three numbers --
-// its sum of b, the sum of its local prefixes and its cell count -- from which every field thread derives its own
-// offset, the grand total and sum_j S_j without further communication (S_{j-1} of a thread's first cell is its
-// exclusive offset, so D_{j-1} never comes from a neighbour).  The other threads meanwhile run `idle_work` (the
+// The first FIELD_THREADS (<= 256) threads own contiguous runs of cells; each warp publishes two numbers -- its sum
+// of b and its share of sum_j S_j = sum_i b_i (M - i), a weighted sum that does not depend on the scan, so its
+// shuffles overlap the scan's -- from which every field thread derives its own offset, the grand total and
+// sum_j S_j without further communication (S_{j-1} of a thread's first cell is its exclusive offset, so D_{j-1}
+// never comes from a neighbour).  The other threads meanwhile run `idle_work` (the
 // resident kernel clears the histogram there).  Every thread must call this.
 //
 //   rho      : M fixed-point cell sums (functor; global or shared memory)
@@ -468,19 +469,17 @@ __device__ __forceinline__ FieldTotals block_field(RhoLoad rho, typename PairT<R
     double run = 0.0, excl = 0.0, ext0 = 0.0;
     if (field_thread) {
         if (has_ext && j0 < j1) ext0 = ext.at(j0);     // global loads: in flight across the scan and barrier (A)
-        double ls = 0.0;
+        double ws = 0.0;
         for (int j = j0; j < j1; ++j) {
             const long long rj = (long long)rho(j);
             if (range_err && rj < -(mc.fix_one << 2)) atomicOr(range_err, ERR_DENSITY_RANGE);   // wrapped past 2^63
             double nj = (double)rj * mc.inv_fix * mc.scale;
             if (n_out) n_out[j] = nj;
-            run += nj - mc.n0;
+            const double b = nj - mc.n0;
+            run += b;
             D_s[j] = run;                              // inclusive prefix inside this thread's run of cells
-            ls += run;
+            ws += b * (double)(M - j);                 // b_j enters S_j, S_{j+1}, ..., S_{M-1}
         }
-        const double ncell = j1 > j0 ? (double)(j1 - j0) : 0.0;
-        const int wc0 = (tid - lane) * cpt;            // cells owned by this warp: a closed form, no reduction
-        const double c = (double)max(0, min(M, wc0 + 32 * cpt) - wc0);
         double inc = run;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -488,9 +487,9 @@ __device__ __forceinline__ FieldTotals block_field(RhoLoad rho, typename PairT<R
             if (lane >= o) inc += t;
         }
         excl = inc - run;
-        const double a = warp_sum(ls + ncell * excl);
+        const double a = warp_sum(ws);
         const double wt = __shfl_sync(0xffffffffu, inc, 31);
-        if (lane == 0) { red[3 * w] = wt; red[3 * w + 1] = a; red[3 * w + 2] = c; }
+        if (lane == 0) { red[3 * w] = wt; red[3 * w + 1] = a; }
     }
     __syncthreads();                                   // (A) warp triples published; all reads of rho are done
 
@@ -500,7 +499,7 @@ __device__ __forceinline__ FieldTotals block_field(RhoLoad rho, typename PairT<R
 #pragma unroll
         for (int k = 0; k < NWF; ++k) {
             if (k == w) myoff = total;
-            sumS += red[3 * k + 1] + red[3 * k + 2] * total;
+            sumS += red[3 * k + 1];
             total += red[3 * k];
         }
         const double meanS = sumS / (double)M;

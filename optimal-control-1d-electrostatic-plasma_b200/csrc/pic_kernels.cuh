@@ -134,7 +134,7 @@ __host__ __device__ constexpr size_t smem_plan_bytes(int M, int threads, bool se
 }
 
 // byte offsets of the regions inside the dynamic shared memory of a CTA (the gather table sits at offset 0)
-struct SmemOffsets { unsigned hist, hist2, D, red, x, v; };
+struct SmemOffsets { unsigned hist, hist2, D, red, x, v, ext; };
 template <typename R>
 __host__ __device__ inline SmemOffsets smem_offsets(int M, int threads, bool separate_d, int ip = IP_CIC,
                                                     bool second_hist = false, long long n_resident = 0) {
@@ -147,6 +147,7 @@ __host__ __device__ inline SmemOffsets smem_offsets(int M, int threads, bool sep
     o.red = (unsigned)b;
     o.x = (unsigned)smem_plan_bytes<R>(M, threads, separate_d, ip, second_hist);       // resident particle state
     o.v = o.x + (unsigned)((n_resident + 1) / 2 * 2 * sizeof(R));
+    o.ext = o.v + (unsigned)((n_resident + 1) / 2 * 2 * sizeof(R));                    // resident: E_ext of the step, M doubles
     return o;
 }
 
@@ -458,7 +459,7 @@ struct ResidentArgs {
 // overlaps the barriers of the field solve.  With the state in shared memory two 512-thread CTAs share an SM.)
 template <typename R>
 __host__ __device__ constexpr size_t resident_smem_bytes(int M, int threads, long long n, int ip = IP_CIC) {
-    return smem_plan_bytes<R>(M, threads, true, ip) + (size_t)((n + 1) / 2 * 2) * 2 * sizeof(R);
+    return smem_plan_bytes<R>(M, threads, true, ip) + (size_t)((n + 1) / 2 * 2) * 2 * sizeof(R) + (size_t)M * 8;
 }
 
 template <typename R, int THREADS, int DEP, bool EXACT_W, int IP = IP_CIC>
@@ -468,6 +469,7 @@ __global__ void __launch_bounds__(THREADS, THREADS <= 512 ? 1024 / THREADS : 1) 
     SmemLayout<R> sm(smem_raw, a.lay);
     R* x_s = (R*)(smem_raw + a.lay.x);
     R* v_s = (R*)(smem_raw + a.lay.v);
+    double* ext_s = (double*)(smem_raw + a.lay.ext);
     using H = typename HistSel<DEP, IP>::type;
     H hist; hist.init(sm.hist, M);
     const PartConst<R> pc = make_part_const<R>(a.mc);
@@ -535,10 +537,18 @@ __global__ void __launch_bounds__(THREADS, THREADS <= 512 ? 1024 / THREADS : 1) 
         ActuatorArgs act = a.act;
         if (act.coeffs) act.coeffs += (size_t)step * a.coeff_step_stride;
         if (act.ext) act.ext += (size_t)step * a.ext_step_stride;
-        const ExtSrc ext = stage_ext(act, env, M);
+        const ExtSrc ext_g = stage_ext(act, env, M);
         const bool last = step == a.n_steps - 1;
         double input_e = 0.0;                                       // loaded now, used after the last field solve
-        if (tid == 0 && ext.coeff) input_e = input_energy(ext.coeff, 2 * a.act.m, a.rw.L);
+        if (tid == 0 && ext_g.coeff) input_e = input_energy(ext_g.coeff, 2 * a.act.m, a.rw.L);
+        // E_external is held for all sub-stages of a step (pic.py:131-137): evaluate it on the mesh once, here, where its
+        // global loads overlap the stage-0 particle loop, instead of inside each of the three kick-stage field solves.
+        // The first reader is behind the block barriers of the stage-0 solve.
+        ExtSrc ext = none;
+        if (ext_g.any()) {
+            for (int j = tid; j < M; j += THREADS) ext_s[j] = ext_g.at(j);
+            ext.ext = ext_s;
+        }
         {                                                           // stage 0: drift only (integration.py:71)
             const R cc = (R)a.c[0];
 #pragma unroll 2
