@@ -26,7 +26,7 @@ extern "C" {
 #pragma GCC visibility push(default)   /* the library is built with -fvisibility=hidden; these are its exports */
 #endif
 
-#define PIC_B200_ABI_VERSION 1
+#define PIC_B200_ABI_VERSION 2
 
 enum { PIC_OK = 0, PIC_EINVAL = -1, PIC_ENODEVICE = -2, PIC_ECUDA = -3, PIC_ENOMEM = -4, PIC_ESTATE = -5,
        PIC_ENUMERIC = -6, PIC_ENCCL = -7, PIC_EUNSUPPORTED = -8 };
@@ -96,6 +96,9 @@ int pic_get_fields(pic_handle* h, double* n, double* E_mesh);
 int pic_get_density_fixed(pic_handle* h, uint64_t* rho, int32_t* fixed_bits);
 /* [n_envs][PIC_DIAG_N] for the current state (get_energy / get_electric_energy are derived on the host side). */
 int pic_get_diag(pic_handle* h, double* diag);
+/* the same plus the sticky device error flags (pic_get_error_flags) in ONE synchronisation: what the host classes
+ * call after every step so that a flagged step raises where the reference's np.bincount would (interpolate.py:16) */
+int pic_get_diag_flags(pic_handle* h, double* diag, uint32_t* flags);
 /* per-step records of the last pic_step_* call: [n_steps][n_envs][PIC_DIAG_N] */
 int pic_get_trace(pic_handle* h, double* trace, int32_t n_steps);
 /* cell index floor(x/dx), weights and gathered field of the current state (pic.py:102-123); [n_envs][n_particles]
@@ -154,6 +157,11 @@ typedef struct pic_device_views {
     int32_t elem_size;  /* 8 or 4 */
 } pic_device_views;
 int pic_get_device_views(pic_handle* h, pic_device_views* out);
+/* The views are READ-ONLY by contract: density, field, diagnostics and the pre-deposited first sub-stage of the next
+ * step were all built from the x, v they alias.  A caller that does write particles through them (a reset kernel, a
+ * torch policy) must call this before the next step: it re-runs what pic_set_state does after its copy (wrap,
+ * deposit, field, next-step pre-deposit). */
+int pic_refresh_fields(pic_handle* h);
 
 /* --- particle sharding over several GPUs (one process per GPU) ------------------------------------------------ */
 /* Each rank holds n_particles of the n_particles_total; after every sub-stage deposit the fixed-point density is

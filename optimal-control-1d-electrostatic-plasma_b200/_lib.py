@@ -9,12 +9,21 @@ import os
 from . import build as _build
 
 PIC_OK = 0
+PIC_ENUMERIC = -6
 PIC_F64, PIC_F32 = 0, 1
 PIC_MODE_AUTO, PIC_MODE_RESIDENT, PIC_MODE_STREAMING = 0, 1, 2
 PIC_DEPOSIT_AUTO, PIC_DEPOSIT_CAS64, PIC_DEPOSIT_SPLIT32 = -1, 0, 1
 PIC_INTERP_CIC, PIC_INTERP_TSC = 0, 1
 DIAG_KE, DIAG_PE_MESH, DIAG_SUM_V, DIAG_SUM_E2, DIAG_REWARD, DIAG_INPUT_E, DIAG_N = 0, 1, 2, 3, 4, 5, 6
-ERR_INDEX_RANGE, ERR_NONFINITE = 1, 2
+ERR_INDEX_RANGE, ERR_NONFINITE, ERR_COMM_TIMEOUT, ERR_DENSITY_RANGE = 1, 2, 4, 8
+ERR_TEXT = {
+    ERR_INDEX_RANGE: "a cell index floor(x/dx) fell outside [0, N_mesh) (the reference raises in np.bincount, "
+                     "src/env/interpolate.py:16)",
+    ERR_NONFINITE: "a non-finite particle position reached the deposit",
+    ERR_COMM_TIMEOUT: "a peer rank of the fused density exchange did not arrive in time; the step was abandoned",
+    ERR_DENSITY_RANGE: "a cell's fixed-point density overflowed its headroom (density far above the mean): lower "
+                       "fixed_bits or use the split32 deposit",
+}
 
 
 class PicConfig(C.Structure):
@@ -51,6 +60,7 @@ SIGNATURES = {
     "pic_get_fields": (C.c_int, [_H, C.c_void_p, C.c_void_p]),
     "pic_get_density_fixed": (C.c_int, [_H, C.c_void_p, C.POINTER(C.c_int32)]),
     "pic_get_diag": (C.c_int, [_H, C.c_void_p]),
+    "pic_get_diag_flags": (C.c_int, [_H, C.c_void_p, C.POINTER(C.c_uint32)]),
     "pic_get_trace": (C.c_int, [_H, C.c_void_p, C.c_int32]),
     "pic_get_cells": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "pic_step_mesh": (C.c_int, [_H, C.c_void_p, C.c_int32]),
@@ -66,6 +76,7 @@ SIGNATURES = {
     "pic_phase_hist": (C.c_int, [_H, C.c_void_p]),
     "pic_set_feq": (C.c_int, [_H, C.c_void_p]),
     "pic_kl_divergence": (C.c_int, [_H, C.c_void_p]),
+    "pic_refresh_fields": (C.c_int, [_H]),
     "pic_sync": (C.c_int, [_H]),
     "pic_get_error_flags": (C.c_int, [_H, C.POINTER(C.c_uint32)]),
     "pic_clear_error_flags": (C.c_int, [_H]),
@@ -119,6 +130,16 @@ class PicError(RuntimeError):
     def __init__(self, code, msg):
         super().__init__("pic_b200 error %d: %s" % (code, msg))
         self.code = code
+
+
+class PicDeviceError(PicError):
+    """Sticky device-side error flags were found set (pic_get_error_flags)."""
+
+    def __init__(self, flags):
+        texts = [t for bit, t in ERR_TEXT.items() if flags & bit]
+        RuntimeError.__init__(self, "pic_b200 device error flags 0x%x: %s" % (flags, "; ".join(texts) or "unknown"))
+        self.code = PIC_ENUMERIC
+        self.flags = flags
 
 
 def check(rc, handle=None):

@@ -82,11 +82,17 @@ class BatchedPIC:
 
     def observe(self):
         """Zero-copy observation for a device-side policy: dict of torch CUDA tensors aliasing the env state --
-        x, v of shape (n_envs_local, N) in `get_state()` order, plus the per-env diagnostics (n_envs_local, 6)."""
+        x, v of shape (n_envs_local, N) in `get_state()` order, plus the per-env diagnostics (n_envs_local, 6).
+        Read-only by contract (Engine.views); after writing particles through them call `refresh()`."""
         import torch
         vw = self.engine.views()
         dev = "cuda:%d" % self.engine.device
         return {k: torch.as_tensor(vw[k], device=dev) for k in ("x", "v", "diag", "E_mesh", "n")}
+
+    def refresh(self):
+        """Rebuild every env's density / field / diagnostics from the particle arrays as they are now on the device
+        (needed after in-place writes through `observe()` / `views()`)."""
+        self.engine.refresh_fields()
 
     def get_state(self):
         """(n_envs_local, 2N): row e is `PIC.get_state()` of env e flattened (x then v)."""
@@ -106,6 +112,7 @@ class BatchedPIC:
                 a = np.broadcast_to(a, (n_steps,) + a.shape)
             self.engine.step_coeffs(np.ascontiguousarray(a), n_steps)
         tr = self.engine.get_trace(n_steps)
+        self.engine.check_errors()      # a flagged step (out-of-range / non-finite particle) raises, as np.bincount would
         out = {"pe_mesh": tr[:, :, L.DIAG_PE_MESH], "ke": tr[:, :, L.DIAG_KE], "sum_v": tr[:, :, L.DIAG_SUM_V],
                "reward": tr[:, :, L.DIAG_REWARD], "input_energy": tr[:, :, L.DIAG_INPUT_E]}
         if self.engine.n_modes > 0:

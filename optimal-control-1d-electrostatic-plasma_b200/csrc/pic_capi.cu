@@ -531,6 +531,7 @@ int pic_create(const pic_config* cfg, pic_handle** out) {
     h->fixed_bits = k;
     mc.fix_scale = ldexp(1.0, k); mc.inv_fix = ldexp(1.0, -k); mc.fix_one = 1LL << k;
     mc.idx_thr = (double)h->M * (h->f32 ? ldexp(1.0, -20) : ldexp(1.0, -49));
+    mc.range_floor = h->ip == IP_TSC ? -(1LL << 61) : -(mc.fix_one << 2);
 
     h->dep = cfg->deposit == PIC_DEPOSIT_CAS64 ? DEP_CAS64 : DEP_SPLIT32;     // auto: native 32-bit atomics
     if (h->f32) h->dep = DEP_SPLIT32;
@@ -742,6 +743,15 @@ int pic_get_diag(pic_handle* h, double* diag) {
     return PIC_OK;
 }
 
+int pic_get_diag_flags(pic_handle* h, double* diag, uint32_t* flags) {
+    if (!h || !diag || !flags) return PIC_EINVAL;
+    if (!h->have_state) return fail(h, PIC_ESTATE, "no state");
+    CK(h, cudaMemcpyAsync(diag, h->diag, sizeof(double) * DIAG_N * h->n_envs, cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaMemcpyAsync(flags, h->err, sizeof(unsigned), cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));
+    return PIC_OK;
+}
+
 int pic_get_trace(pic_handle* h, double* trace, int32_t n_steps) {
     if (!h || !trace) return PIC_EINVAL;
     if (n_steps < 1 || n_steps > h->trace_steps) return fail(h, PIC_EINVAL, "n_steps exceeds the last call's step count");
@@ -944,6 +954,13 @@ int pic_kl_divergence(pic_handle* h, double* kl) {
     CK(h, cudaMemcpyAsync(kl, h->ph_kl, sizeof(double) * (size_t)h->n_envs, cudaMemcpyDeviceToHost, h->stream));
     CK(h, cudaStreamSynchronize(h->stream));
     return PIC_OK;
+}
+
+int pic_refresh_fields(pic_handle* h) {
+    if (!h) return PIC_EINVAL;
+    if (!h->have_state) return fail(h, PIC_ESTATE, "no state");
+    CK(h, cudaSetDevice(h->device));
+    return init_fields(h);
 }
 
 int pic_sync(pic_handle* h) {

@@ -148,6 +148,9 @@ struct MeshConst {
     long long fix_one;     // 2^k as an integer: what one particle deposits in total
     double idx_thr;        // |q - rint(q)| below this => redo the cell index with IEEE division
     double dt;
+    long long range_floor; // a cell sum below this has wrapped past 2^63 (ERR_DENSITY_RANGE).  CIC sums are never
+                           // negative: -4 * 2^k; TSC's middle weight goes down to -0.25 per particle, so a clumped cell
+                           // is legitimately negative: -2^61, far below anything the 8x headroom rule admits
 };
 
 template <typename R> struct PartConst {   // per-particle constants in the particle precision
@@ -472,7 +475,7 @@ __device__ __forceinline__ FieldTotals block_field(RhoLoad rho, typename PairT<R
         double ws = 0.0;
         for (int j = j0; j < j1; ++j) {
             const long long rj = (long long)rho(j);
-            if (range_err && rj < -(mc.fix_one << 2)) atomicOr(range_err, ERR_DENSITY_RANGE);   // wrapped past 2^63
+            if (range_err && rj < mc.range_floor) atomicOr(range_err, ERR_DENSITY_RANGE);   // wrapped past 2^63
             double nj = (double)rj * mc.inv_fix * mc.scale;
             if (n_out) n_out[j] = nj;
             const double b = nj - mc.n0;

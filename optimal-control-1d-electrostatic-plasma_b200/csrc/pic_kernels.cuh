@@ -65,17 +65,28 @@ __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned l
     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
-// every thread of the CTA calls this; returns after all ranks have published exchange `seq`
-__device__ __forceinline__ void comm_wait(const CommArgs& c, unsigned long long seq, unsigned* err) {
+// every thread of the CTA calls this; returns after all ranks have published exchange `seq`.
+// Returns true (to every thread) when a peer did not arrive within the bound: the caller must then leave the
+// particle state alone -- the densities in the slots are incomplete, and a step built on them would overwrite x and v
+// with garbage.  The sticky ERR_COMM_TIMEOUT flag makes the host classes raise on their next read.
+#ifndef PIC_COMM_SPIN_LIMIT
+#define PIC_COMM_SPIN_LIMIT (1ll << 25)              // x (64 ns sleep + one system-scope load): a few seconds
+#endif
+__device__ __forceinline__ bool comm_wait(const CommArgs& c, unsigned long long seq, unsigned* err) {
+    int timed_out = 0;
     if (threadIdx.x < c.world) {
         const unsigned long long* f = c.flags[c.rank] + threadIdx.x;
         long long spins = 0;
         while (ld_acquire_sys(f) < seq) {
-            if (++spins > (1ll << 24)) { atomicOr(err, ERR_COMM_TIMEOUT); break; }    // ~ a second: bail out, never hang
+            if (++spins > PIC_COMM_SPIN_LIMIT || ((spins & 0xfff) == 0 && (__ldcg(err) & ERR_COMM_TIMEOUT))) {
+                atomicOr(err, ERR_COMM_TIMEOUT);       // never hang the GPU; another CTA's verdict is taken over at once
+                timed_out = 1;
+                break;
+            }
             __nanosleep(64);
         }
     }
-    __syncthreads();
+    return __syncthreads_or(timed_out) != 0;
 }
 
 struct PeerSumRho {                                   // density = sum over ranks of their published partial density
@@ -200,10 +211,11 @@ __global__ void __launch_bounds__(THREADS) push_stream_kernel(const StreamArgs a
     const PartConst<R> pc = make_part_const<R>(a.mc);
 
     const bool fused = a.comm.world > 1;
+    bool dead = false;                                  // fused exchange timed out: leave the particle state untouched
     if (KICK) {                                         // D_s aliases the histogram: solve first, then clear
         const ExtSrc ext = stage_ext(a.act, env, M);
         if (fused) {
-            comm_wait(a.comm, a.comm.seq_in, a.err);
+            dead = comm_wait(a.comm, a.comm.seq_in, a.err);
             PeerSumRho rho{comm_in_slots(a.comm, a.comm.seq_in), a.comm.slot_len, a.comm.world};
             block_field<R, THREADS, false>(rho, sm.E_s, sm.D_s, sm.red, a.mc, ext, nullptr, nullptr, 0.0, 0.0, [] {});
         } else {
@@ -251,7 +263,7 @@ __global__ void __launch_bounds__(THREADS) push_stream_kernel(const StreamArgs a
 
     // full tiles: every lane of every warp has work, so warp-wide primitives may use the full mask
     constexpr long long TILE = (long long)THREADS * UNROLL;
-    const long long n_tiles = nvec / TILE;
+    const long long n_tiles = dead ? 0 : nvec / TILE;
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const long long base = tile * TILE + tid;
         V xs[UNROLL], vs[UNROLL];
@@ -268,10 +280,10 @@ __global__ void __launch_bounds__(THREADS) push_stream_kernel(const StreamArgs a
         }
     }
     // ragged remainder (< one tile of vectors) and the scalar tail (N not a multiple of the vector width)
-    if (blockIdx.x == (unsigned)(n_tiles % gridDim.x)) {
+    if (!dead && blockIdx.x == (unsigned)(n_tiles % gridDim.x)) {
         for (long long i = n_tiles * TILE + tid; i < nvec; i += THREADS) vec_pair(i, std::false_type{});
     }
-    if (blockIdx.x == 0) {
+    if (!dead && blockIdx.x == 0) {
         long long i = nvec * VEC + tid;
         if (i < a.N) {
             R x = xe[i], v = ve[i];

@@ -112,10 +112,24 @@ class Engine:
         self._ck(self._lib.pic_get_density_fixed(self._h, _ptr(rho), C.byref(k)))
         return rho, k.value
 
-    def get_diag(self):
+    def get_diag(self, check=False):
+        """(n_envs, DIAG_N) diagnostics of the current state.  check=True: the sticky device error flags come back
+        in the same round trip and raise PicDeviceError when set."""
         d = np.empty((self.n_envs, L.DIAG_N))
-        self._ck(self._lib.pic_get_diag(self._h, _ptr(d)))
+        if not check:
+            self._ck(self._lib.pic_get_diag(self._h, _ptr(d)))
+            return d
+        f = C.c_uint32()
+        self._ck(self._lib.pic_get_diag_flags(self._h, _ptr(d), C.byref(f)))
+        if f.value:
+            raise L.PicDeviceError(f.value)
         return d
+
+    def check_errors(self):
+        """Raise PicDeviceError if the device has flagged anything since the flags were last cleared."""
+        f = self.error_flags()
+        if f:
+            raise L.PicDeviceError(f)
 
     def get_trace(self, n_steps):
         t = np.empty((n_steps, self.n_envs, L.DIAG_N))
@@ -205,6 +219,11 @@ class Engine:
         self._ck(self._lib.pic_kl_divergence(self._h, _ptr(kl)))
         return kl
 
+    def refresh_fields(self):
+        """Rebuild density / field / diagnostics / next-step pre-deposit from the particle arrays as they are now on
+        the device: mandatory after writing x or v through `views()` (which are read-only by contract otherwise)."""
+        self._ck(self._lib.pic_refresh_fields(self._h))
+
     def sync(self):
         self._ck(self._lib.pic_sync(self._h))
 
@@ -269,7 +288,12 @@ class Engine:
         return int(self._lib.pic_kernel_launch_count(self._h))
 
     def views(self):
-        """Zero-copy device views: x, v as (n_envs, N) with env stride ld; n, E_mesh (n_envs, M); diag (n_envs, 4)."""
+        """Zero-copy device views: x, v as (n_envs, N) with env stride ld; n, E_mesh (n_envs, M); diag (n_envs, 6).
+
+        READ-ONLY by contract.  (`__cuda_array_interface__` has a read-only flag, but torch.as_tensor rejects
+        arrays that set it, so it cannot be used to enforce this.)  Density, field, diagnostics and the
+        pre-deposited first sub-stage of the next step were built from these x, v: after writing through a view call
+        `refresh_fields()`, or load new particles with set_state / set_state_device, which do it themselves."""
         dv = L.PicDeviceViews()
         self._ck(self._lib.pic_get_device_views(self._h, C.byref(dv)))
         es = dv.elem_size

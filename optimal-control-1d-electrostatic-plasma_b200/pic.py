@@ -21,11 +21,13 @@ class PIC:
                  mode: str = "auto", deposit: str = "auto", exact_weights: bool = False, max_mode: int = 0):
         if interpol not in ("CIC", "TSC"):
             raise ValueError("interpol must be 'CIC' or 'TSC' (src/env/interpolate.py), got %r" % (interpol,))
+        self._eng: Optional[Engine] = None
+        self._cache = {}
         self.N = N
         self.N_mesh = N_mesh
         self.n0 = n0
         self.L = L
-        self.dt = dt
+        self._dt = dt
         self.tmin = tmin
         self.tmax = tmax
         self.dx = L / N_mesh
@@ -33,12 +35,10 @@ class PIC:
         self.A = A
         self.n_mode = n_mode
         self.init_dist = init_dist
-        self.interpol = interpol
+        self._interpol = interpol
         self._opts = dict(device=device, precision=precision, mode=mode, deposit=deposit,
                           exact_weights=exact_weights, max_mode=max_mode)
-        self._eng: Optional[Engine] = None
-        self._cache = {}
-        self._basis_set = False
+        self._basis = None
         if init_dist is not None:
             self.initialize()
 
@@ -55,6 +55,51 @@ class PIC:
     def engine(self) -> Engine:
         return self._engine()
 
+    def _rebuild_engine(self):
+        """A parameter the device handle was created with has changed (dt, interpol): move the state into a new
+        handle.  `pic_set_state` re-wraps (a no-op on a wrapped state), re-deposits and also re-deposits the next
+        step's drift-only sub-stage, which had the old c0*dt baked in."""
+        if self._eng is None:
+            return
+        x, v = self._eng.get_state()
+        self._eng.close()
+        self._eng = None
+        self._cache = {}
+        eng = self._engine()
+        if self._basis is not None:
+            eng.set_actuator_basis(*self._basis)
+        eng.set_state(x, v)
+
+    # dt and interpol are plain attributes in the reference (pic.py:35,47) that `update_state` reads on every call
+    # (pic.py:133, util.py:94), so assigning them -- directly or through update_params (pic.py:79-82) -- must take
+    # effect on the next step here as well.
+    @property
+    def dt(self):
+        return self._dt
+
+    @dt.setter
+    def dt(self, value):
+        value = float(value)
+        if not value > 0:
+            raise ValueError("dt must be positive")
+        changed = value != self._dt
+        self._dt = value
+        if changed:
+            self._rebuild_engine()
+
+    @property
+    def interpol(self):
+        return self._interpol
+
+    @interpol.setter
+    def interpol(self, value):
+        if value not in ("CIC", "TSC"):
+            raise ValueError("interpol must be 'CIC' or 'TSC' (src/env/interpolate.py), got %r" % (value,))
+        changed = value != self._interpol
+        self._interpol = value
+        if changed:
+            self._rebuild_engine()
+
     # ------------------------------------------------------- src/env/pic.py:63-91
     def initialize(self):
         self.init_dist.reinit()
@@ -62,9 +107,9 @@ class PIC:
         x = np.asarray(x, dtype=np.float64).reshape(-1, 1)
         v = np.asarray(v, dtype=np.float64).reshape(-1, 1)
         v *= (1 + self.A * np.sin(2 * np.pi * self.n_mode * x / self.L))     # pic.py:68
-        if self.dt > 2 / np.sqrt(self.N / self.L):                           # pic.py:71-73
-            self.dt = 2 / np.sqrt(self.N / self.L)
-            print("CFL condtion invalid: change dt = {:.4f}".format(self.dt))
+        if self._dt > 2 / np.sqrt(self.N / self.L):                          # pic.py:71-73
+            self._dt = 2 / np.sqrt(self.N / self.L)
+            print("CFL condtion invalid: change dt = {:.4f}".format(self._dt))
             if self._eng is not None:
                 self._eng.close()
                 self._eng = None
@@ -93,9 +138,9 @@ class PIC:
         basis_cos @ a + basis_sin @ b (src/control/actuator.py:62).  Needs max_mode at construction."""
         eng = self._engine()
         if basis_cos is not None:
-            eng.set_actuator_basis(basis_cos, basis_sin)
-            self._basis_set = True
-        if not self._basis_set:
+            self._basis = (np.array(basis_cos, dtype=np.float64), np.array(basis_sin, dtype=np.float64))
+            eng.set_actuator_basis(*self._basis)
+        if self._basis is None:
             raise RuntimeError("pass basis_cos / basis_sin (E_field.basis_cos / .basis_sin) on the first call")
         c = np.concatenate([np.asarray(coeff_cos, dtype=np.float64).ravel(),
                             np.asarray(coeff_sin, dtype=np.float64).ravel()])
@@ -105,12 +150,21 @@ class PIC:
     # ------------------------------------------------------------------ getters
     def _state(self):
         if "xv" not in self._cache:
+            self._diag()                                   # raises if the device flagged the step that made this state
             x, v = self._engine().get_state()
-            self._cache["xv"] = (x.reshape(-1, 1), v.reshape(-1, 1))
+            x, v = x.reshape(-1, 1), v.reshape(-1, 1)
+            # The arrays are host COPIES of the device state, cached until the next step.  In the reference `sim.x`
+            # IS the state, so `sim.x[:] = ...` changes the env; here such a write would be silently lost -- the
+            # arrays are therefore read-only and the write fails loudly.  Assign instead (`sim.x = new_x`, or
+            # `set_state(x, v)`): the setters upload and rebuild density / field on the device.
+            x.setflags(write=False)
+            v.setflags(write=False)
+            self._cache["xv"] = (x, v)
         return self._cache["xv"]
 
     @property
     def x(self):
+        """(N, 1) float64 positions, read-only host copy (see _state); `.copy()` it or assign a new array."""
         return self._state()[0]
 
     @x.setter
@@ -131,7 +185,10 @@ class PIC:
 
     def _diag(self):
         if "diag" not in self._cache:
-            self._cache["diag"] = self._engine().get_diag()[0]
+            # one D2H round trip brings the diagnostics record and the sticky device error flags: where the reference
+            # raises (np.bincount on an out-of-range or NaN index, interpolate.py:16) the device path clamps, flags
+            # and keeps going -- the flag becomes an exception here, before any number of that state is handed out
+            self._cache["diag"] = self._engine().get_diag(check=True)[0]
         return self._cache["diag"]
 
     def get_electric_energy(self):                                     # util.py:119-131
@@ -232,9 +289,18 @@ class PIC:
     def E(self):
         return self._cells()[3]
 
+    _STRUCTURAL = ("N", "N_mesh", "L", "n0")
+
     def update_params(self, **kwargs):                                 # pic.py:79-82
+        """Same contract as the reference: every known, non-None keyword is assigned.  `dt` and `interpol` take effect
+        on the next step (the device handle is rebuilt around the current state).  N, N_mesh, L, n0 size the device
+        buffers and the mesh; the reference would keep its old dx / grad / laplacian after such a change
+        (pic.py:36,52-53 are only evaluated in __init__) and compute garbage, so they are refused here."""
         for key in kwargs.keys():
             if hasattr(self, key) is True and kwargs[key] is not None:
+                if key in self._STRUCTURAL and kwargs[key] != getattr(self, key) and self._eng is not None:
+                    raise ValueError("update_params(%s=...) after initialisation is not supported: build a new PIC "
+                                     "(the reference keeps a stale dx/grad/laplacian in this case)" % key)
                 setattr(self, key, kwargs[key])
 
     def simulate(self, E_external_traj=None, n_steps: Optional[int] = None):

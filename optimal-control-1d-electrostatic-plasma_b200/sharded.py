@@ -99,6 +99,7 @@ class ShardedPIC:
             self.engine.set_state(np.asarray(x).reshape(1, -1), np.asarray(v).reshape(1, -1))
 
     def get_state_local(self):
+        self.engine.check_errors()
         x, v = self.engine.get_state()
         return x[0], v[0]
 
@@ -109,9 +110,15 @@ class ShardedPIC:
                 self._step_staged(E_ext)
         else:
             self.engine.step_mesh(None if E_ext is None else np.asarray(E_ext).reshape(1, -1), n_steps)
+        # stepping stays asynchronous; errors surface in diag() / energy() / get_state_local() (check_errors())
+
+    def check_errors(self):
+        self.engine.check_errors()
 
     def diag(self):
-        d = self.engine.get_diag()[0]
+        # the sticky device flags ride along: an exchange timeout (a stalled peer), an out-of-range or non-finite
+        # particle, or a density overflow raises here instead of returning plausible-looking numbers
+        d = self.engine.get_diag(check=True)[0]
         if self.collective == "torch":                 # kinetic sums are rank-local in this mode
             import torch
             import torch.distributed as dist

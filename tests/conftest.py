@@ -10,6 +10,15 @@ if ROOT not in sys.path:
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 
+def reference_dir():
+    """The UNMODIFIED reference tree: $PIC_REFERENCE, /root/reference (build container), or the copy that
+    tools/stage_reference.py puts under baseline/_ref/ (git-ignored, but it travels to the GPU box).  None if absent."""
+    for p in (os.environ.get("PIC_REFERENCE"), "/root/reference", os.path.join(ROOT, "baseline", "_ref")):
+        if p and os.path.exists(os.path.join(p, "src", "env", "pic.py")):
+            return p
+    return None
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 

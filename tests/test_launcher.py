@@ -9,7 +9,9 @@ import textwrap
 import numpy as np
 import pytest
 
-REF = os.environ.get("PIC_REFERENCE", "/root/reference")
+from conftest import reference_dir
+
+REF = reference_dir() or "/nonexistent"
 
 
 @pytest.mark.skipif(not os.path.exists(os.path.join(REF, "run_wo_oc.py")), reason="reference tree not present")
