@@ -252,8 +252,18 @@ __device__ __forceinline__ Cell cell_weights(R xw, const PartConst<R>& c, int M,
 //                 The cell density in fixed point is then  cnt[j] 2^k - S[j] + S[j-1]  -- three atomics per
 //                 particle instead of four and no wrap cell.
 // Both give the identical integer density (tests/test_gpu_parity.py::test_bitwise_reproducibility_across_kernels).
+//   DEP_PACK2   : TWO native 32-bit atomics per particle (large-N streaming mode, where the six / three atomics of
+//                 DEP_SPLIT32 make the LSU data pipe the binding unit).  Needs weights of at most 32 bits
+//                 (fixed_bits <= 31).  Word lo[il] += W_r with the old value returned; word hi[il] += 2^16 + carry:
+//                 the particle count lives in the upper half of hi, the carries of the low word (the bits 32.. of the
+//                 64-bit sum) in the lower half.  Both fields hold fewer than 2^16 = 65536 particles per cell, per CTA
+//                 and per flush: the kernel flushes often enough for 16x the mean density and CHECKS -- the counts it
+//                 reads back must add up to the particles it deposited, else ERR_DENSITY_RANGE (a field overflow loses
+//                 a carry out of bit 31, so the sum comes out short: the check is exact, never silent).
 constexpr int DEP_CAS64 = 0;
 constexpr int DEP_SPLIT32 = 1;
+constexpr int DEP_PACK2 = 2;
+constexpr int PACK2_MAX_BITS = 31;
 
 template <int DEP> struct Hist;
 
@@ -328,6 +338,40 @@ template <> struct Hist<DEP_SPLIT32> {
     }
     __device__ __forceinline__ unsigned long long get(int j, long long one) const {
         return (unsigned long long)w[3 * j] * (unsigned long long)one - S(j) + S(j == 0 ? M - 1 : j - 1);
+    }
+};
+
+// Layout: lo[0..M) then hi[0..M) (stride of one word: random cells spread over all 32 banks; cell-interleaved
+// (lo, hi) pairs would put every lo in an even bank and double the conflicts of each atomic instruction).
+template <> struct Hist<DEP_PACK2> {
+    unsigned* w;
+    unsigned lo_a, hi_off;               // lo[] as a shared-window byte address; byte distance from lo[j] to hi[j]
+    int M;
+    static __host__ __device__ constexpr size_t bytes(int M) { return (size_t)M * 8 + 8; }
+    __device__ __forceinline__ void init(void* base, int M_) {
+        M = M_; w = (unsigned*)base;
+        lo_a = (unsigned)__cvta_generic_to_shared(w);
+        hi_off = 4u * (unsigned)M_;
+    }
+    __device__ __forceinline__ void zero(int tid, int nthreads) {
+        for (int j = tid; j < 2 * M; j += nthreads) w[j] = 0u;
+    }
+    __device__ __forceinline__ void deposit_group(int il, unsigned long long S, unsigned count, long long) {
+        const unsigned wl = (unsigned)S, wh = (unsigned)(S >> 32), cell = lo_a + 4u * (unsigned)il;
+        const unsigned old = atom_shared_u32(cell, wl);
+        red_shared_u32(cell + hi_off, (count << 16) + wh + ((old + wl) < old ? 1u : 0u));
+    }
+    __device__ __forceinline__ void deposit(int il, long long Wr, long long) {      // Wr <= 2^31: no high word
+        const unsigned wl = (unsigned)Wr, cell = lo_a + 4u * (unsigned)il;
+        const unsigned old = atom_shared_u32(cell, wl);
+        red_shared_u32(cell + hi_off, 0x10000u + ((old + wl) < old ? 1u : 0u));
+    }
+    __device__ __forceinline__ unsigned cnt(int j) const { return w[M + j] >> 16; }
+    __device__ __forceinline__ unsigned long long S(int j) const {
+        return ((unsigned long long)(w[M + j] & 0xFFFFu) << 32) | (unsigned long long)w[j];
+    }
+    __device__ __forceinline__ unsigned long long get(int j, long long one) const {
+        return (unsigned long long)cnt(j) * (unsigned long long)one - S(j) + S(j == 0 ? M - 1 : j - 1);
     }
 };
 
