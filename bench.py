@@ -7,16 +7,20 @@
 Workload (BASELINE.json configs[4], the configuration the metric's roofline target is quoted on): ONE env,
 N = 1e9 particles, N_mesh = 4096, L = 50, bump-on-tail (a = 0.2, vb = 3), dt clipped to 2/sqrt(N/L) as the reference
 does (src/env/pic.py:71-72), float64.  A "step" is one `PIC.update_state` = one Yoshida-4 env step = 3 fused
-push/gather/deposit passes (the drift-only first sub-stage rides along with the previous pass) + field solves.  At N GPUs the 1e9 particles are sharded over the ranks (strong scaling)
-with one NCCL all-reduce of the 4096-cell fixed-point density per sub-stage.  Inputs are synthetic: the device-side
-sampler draws the reference's bump-on-tail distribution.
+push/gather/deposit passes over the particles (32 + 24 + 32 = 88 bytes per particle) + field solves.  At N GPUs the 1e9
+particles are sharded over the ranks (strong scaling) with one NCCL all-reduce of the 4096-cell fixed-point density per
+sub-stage.  Inputs are synthetic: the device-side sampler draws the reference's bump-on-tail distribution.
 
-One JSON line on stdout (rank 0).  `value` = particle-steps/s with the state resident in HBM; `e2e` = the same
-through the reference-facing call with HOST buffers (E_external from pinned host memory in, energies out, every
-step); `roofline` = the dominant kernel (kick+drift+deposit pass) against the measured HBM peak; `cpu_baseline` = the
-oracle port of the reference's numpy path on this box's host cores.  `--impl reference` times that CPU path alone.
+One JSON line on stdout (rank 0).  `value` = particle-steps/s with the state resident in HBM; `e2e` = the same through
+the reference-facing call with HOST buffers (E_external from pinned host memory in, energies out, every step);
+`roofline` = the kernel with the largest share of the step against the measured HBM peak (all three passes listed);
+`cpu_baseline` = the reference's own `PIC.update_state` (unmodified, from $PIC_REFERENCE / /root/reference /
+baseline/_ref) on this box's host cores, or the oracle port when the reference is absent; `config.parity` = a fixed
+5-step side check whose density hash must be the same at every GPU count.  `--impl reference` times that CPU path alone.
+BASELINE configs 1-4 ride along as `single_env` and `batched`, each with its CPU baseline at N = 1.
 """
 import argparse
+import hashlib
 import json
 import os
 import subprocess
@@ -35,8 +39,11 @@ UNIT = "particle-steps/s"
 N_FULL = 1_000_000_000
 N_MESH = 4096
 L_BOX = 50.0
+BYTES_PER_PARTICLE_STEP = 88          # float64: stage 1 32 B, stage 2 24 B (v only), stage 3 32 B  
 SETTLE_S = 0.25          # minimum wall time of the untimed warm-up (W steps + extra untimed steps), see run_gpu_arm
+TIMED_MIN_S = 0.5        # the K-step timed region is repeated until this much time has been measured (mean reported)
 FALLBACK_HBM_GBS = 6650.0
+PARITY_N, PARITY_SEED, PARITY_STEPS = 4_000_000, 1234, 5
 
 
 def measured_peaks():
@@ -48,81 +55,189 @@ def measured_peaks():
         return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
 
 
-# ---------------------------------------------------------------------------------------------- CPU baseline
-_WARM = False
+def find_reference():
+    """The UNMODIFIED reference tree, if this box has one (tools/stage_reference.py ships it as baseline/_ref)."""
+    for p in (os.environ.get("PIC_REFERENCE"), "/root/reference", os.path.join(ROOT, "baseline", "_ref")):
+        if p and os.path.exists(os.path.join(p, "src", "env", "pic.py")):
+            return p
+    return None
 
 
-def _oracle_worker(args):
-    """One independent sample env advanced with the faithful oracle; returns (particle_steps, seconds)."""
-    global _WARM
-    n, mesh, steps, seed = args
+# ---------------------------------------------------------------------------------------------- CPU baselines
+class _DirectDist:
+    """Stands in for src/env/dist.py in the CPU-baseline workers: the reference's samplers append to Python lists
+    (dist.py:151-189), unusable beyond ~1e5 particles; the PIC class only calls reinit() and get_sample() on it."""
+
+    def __init__(self, x, v):
+        self._x, self._v = x, v
+
+    def reinit(self):
+        pass
+
+    def get_sample(self):
+        return self._x.copy(), self._v.copy()
+
+
+def _cpu_worker(conn, kind, ref_path, n, mesh, seed):
+    """One host process advancing its own env: kind 'reference' = the reference's PIC class, imported unmodified;
+    'port' = oracle/pic_oracle.py (faithful mode).  Commands: ('step', k) -> seconds for k update_state calls;
+    ('body', k) -> seconds for k iterations of run_wo_oc.py's loop body (:111-122 without the Reward calls)."""
     os.environ.setdefault("OMP_NUM_THREADS", "1")
-    from oracle import pic_oracle as O      # the one place bench.py executes oracle/: the CPU baseline legs
-    rng = np.random.RandomState(seed)
-    x = rng.uniform(0, L_BOX, n)
-    v = rng.normal(size=n) + 3.0 * (rng.uniform(size=n) < 1.0 / 6.0)
-    p = O.PicParams(N=n, N_mesh=mesh, n0=1.0, L=L_BOX, dt=O.clip_dt(0.1, n, L_BOX))
-    if not _WARM:                           # JIT warm-up outside the timed region, once per process
-        O.step(x[:2000].copy(), v[:2000].copy(), O.PicParams(N=2000, N_mesh=mesh, n0=1.0, L=L_BOX, dt=0.01), None,
-               faithful=True)
-        _WARM = True
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        o = O.step(x, v, p, None, faithful=True)
-        x, v = o["x"], o["v"]
-    return n * steps, time.perf_counter() - t0
+    os.environ.setdefault("MKL_NUM_THREADS", "1")
+    os.environ.setdefault("OPENBLAS_NUM_THREADS", "1")
+    sys.dont_write_bytecode = True
+    try:
+        rng = np.random.RandomState(seed)
+        x = rng.uniform(0, L_BOX, n)
+        v = rng.normal(size=n) + 3.0 * (rng.uniform(size=n) < 1.0 / 6.0)
+        if kind == "reference":
+            sys.path.insert(0, ref_path)
+            import contextlib
+            import io
+            from src.env.pic import PIC                     # the reference itself (src/env/pic.py:11)
+            with contextlib.redirect_stdout(io.StringIO()):  # its CFL-clip print (pic.py:73)
+                sim = PIC(N=n, N_mesh=mesh, n0=1.0, L=L_BOX, dt=0.1, tmin=0.0, tmax=50.0, gamma=5.0, A=0.1, n_mode=2,
+                          interpol="CIC", init_dist=_DirectDist(x, v))
+                sim.update_state(None)                      # numba JIT + first-touch outside any timed region
+
+            def step():
+                sim.update_state(None)
+
+            def body():
+                sim.update_state(None)
+                sim.get_energy(); sim.get_electric_energy()
+                sim.x.copy(); sim.v.copy()
+                sim.get_state()
+        else:
+            from oracle import pic_oracle as O              # CPU-baseline legs are the one place bench.py runs oracle/
+            p = O.PicParams(N=n, N_mesh=mesh, n0=1.0, L=L_BOX, dt=O.clip_dt(0.1, n, L_BOX))
+            st = {"x": x, "v": v}
+
+            def step():
+                o = O.step(st["x"], st["v"], p, None, faithful=True)
+                st["x"], st["v"] = o["x"], o["v"]
+
+            def body():
+                step()
+                O.hamiltonian(st["x"], st["v"], p, faithful=True); O.electric_energy(st["x"], p, faithful=True)
+                st["x"].copy(); st["v"].copy()
+                np.concatenate([st["x"], st["v"]])
+            step()
+        conn.send(("ready", None))
+        while True:
+            cmd, k = conn.recv()
+            if cmd == "quit":
+                break
+            fn = step if cmd == "step" else body
+            t0 = time.perf_counter()
+            for _ in range(k):
+                fn()
+            conn.send(("done", time.perf_counter() - t0))
+    except Exception as e:          # noqa: BLE001
+        conn.send(("error", repr(e)))
 
 
-def cpu_baseline(n_sample, steps, procs, pool=None):
-    """Throughput of the oracle port (faithful mode: the reference's 8 deposits + 8 periodic solves per step) on
-    `procs` host processes, each advancing its own sample env of n_sample particles."""
-    jobs = [(n_sample, N_MESH, steps, 100 + i) for i in range(procs)]
-    t0 = time.perf_counter()
-    if procs == 1:
-        res = [_oracle_worker(jobs[0])]
-    elif pool is not None:
-        res = pool.map(_oracle_worker, jobs, chunksize=1)
-    else:
+class CpuPool:
+    """`procs` independent host processes, each with its own env of n particles (the reference is single-threaded
+    Python/numpy: the only way it uses more than one core is one env per process)."""
+
+    def __init__(self, kind, procs, n, mesh, ref_path=None):
         import multiprocessing as mp
-        with mp.get_context("spawn").Pool(procs) as p:
-            res = p.map(_oracle_worker, jobs, chunksize=1)
-    wall = time.perf_counter() - t0
-    total = sum(r[0] for r in res)
-    slowest = max(r[1] for r in res)
-    return total / slowest, slowest, wall
+        ctx = mp.get_context("spawn")
+        self.kind, self.procs, self.n, self.mesh = kind, procs, n, mesh
+        self.pipes, self.ps = [], []
+        for i in range(procs):
+            a, b = ctx.Pipe()
+            p = ctx.Process(target=_cpu_worker, args=(b, kind, ref_path, n, mesh, 100 + i), daemon=True)
+            p.start()
+            self.pipes.append(a); self.ps.append(p)
+        for a in self.pipes:
+            tag, val = a.recv()
+            if tag != "ready":
+                self.close()
+                raise RuntimeError("CPU baseline worker failed: %s" % val)
+
+    def run(self, cmd, k):
+        """All workers run k iterations concurrently; returns the slowest worker's seconds."""
+        for a in self.pipes:
+            a.send((cmd, k))
+        out = []
+        for a in self.pipes:
+            tag, val = a.recv()
+            if tag != "done":
+                raise RuntimeError("CPU baseline worker failed: %s" % val)
+            out.append(val)
+        return max(out)
+
+    def close(self):
+        for a in self.pipes:
+            try:
+                a.send(("quit", 0))
+            except Exception:
+                pass
+        for p in self.ps:
+            p.join(timeout=5)
+            if p.is_alive():
+                p.kill()            # the exact processes this object started
+
+
+def cpu_kind():
+    ref = find_reference()
+    return ("reference", ref) if ref else ("port", None)
+
+
+def host_procs(n, mesh, want=None):
+    """Worker count: one per core, bounded by memory (the reference holds ~6 dense N_mesh^2 matrices and ~40 N-vectors)."""
+    cores = os.cpu_count() or 1
+    procs = min(cores, 64) if want is None else want
+    try:
+        import psutil
+        per = 6 * mesh * mesh * 8 + 48 * n * 8 + 400e6
+        procs = max(1, min(procs, int(0.5 * psutil.virtual_memory().available / per)))
+    except Exception:
+        procs = min(procs, 16)
+    return procs
+
+
+def sample_text(kind, procs, n, mesh, what):
+    if kind == "reference":
+        return ("the reference's own PIC.update_state (src/env/pic.py:131-146, imported unmodified), %d process(es) x one "
+                "independent env of %d particles, N_mesh=%d, %s; particles assigned directly (the reference's list-based "
+                "sampler is unusable at this size); at this sample size the dense O(N_mesh^2) solves/matmuls of "
+                "solve.py:5-53 / util.py:87-100 are a large part of each step -- the reference cannot hold 1e9 particles"
+                % (procs, n, mesh, what))
+    return ("oracle port of the reference's numpy path (faithful mode: 8 deposits + 8 periodic solves per step, but "
+            "an O(N_mesh) tridiagonal walk where the reference copies dense N_mesh^2 matrices, solve.py:5-53), "
+            "%d process(es) x one independent env of %d particles, N_mesh=%d, %s; reference tree not present on this box"
+            % (procs, n, mesh, what))
 
 
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    import multiprocessing as mp
-    procs = max(1, min(os.cpu_count() or 1, 64))
-    n_sample = 1_000_000
-    per_step, vals = [], []
-    pool = mp.get_context("spawn").Pool(procs) if procs > 1 else None
+    kind, ref = cpu_kind()
+    n_sample = 2_000_000
+    procs = host_procs(n_sample, N_MESH)
+    pool = CpuPool(kind, procs, n_sample, N_MESH, ref)
     try:
         for _ in range(max(1, args.warmup)):
-            cpu_baseline(n_sample, 1, procs, pool)
+            pool.run("step", 1)
         t0 = time.perf_counter()
-        for _ in range(args.steps):
-            v, slow, _ = cpu_baseline(n_sample, 1, procs, pool)
-            vals.append(v); per_step.append(slow)
+        per_step = [pool.run("step", 1) for _ in range(args.steps)]
         wall = time.perf_counter() - t0
     finally:
-        if pool is not None:
-            pool.close(); pool.join()
-    value = float(np.mean(vals))
-    sample = ("oracle port (faithful: 8 deposits + 8 Thomas/Sherman-Morrison solves per step) of the reference's "
-              "numpy path, %d processes x one independent env of %d particles, N_mesh=%d, 1 step per timed step; the "
-              "reference itself is single-threaded Python and cannot run 1e9 particles" % (procs, n_sample, N_MESH))
+        pool.close()
+    value = procs * n_sample / float(np.mean(per_step))
+    sample = sample_text(kind, procs, n_sample, N_MESH, "1 env step per timed step")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(per_step)), "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "large-N single env: 1e9 particles, 4096 cells (bounded CPU sample)", "n_particles": N_FULL,
-                   "n_mesh": N_MESH, "L": L_BOX, "sample_particles_per_process": n_sample},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": procs, "kind": "port", "sample": sample},
+                   "n_mesh": N_MESH, "L": L_BOX, "sample_particles_per_process": n_sample, "processes": procs,
+                   "reference_path": ref},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": procs, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "wall_s": wall,
     }
@@ -202,6 +317,27 @@ class ClockSampler:
                 "source": "nvml" if self._nvml else "nvidia-smi"}
 
 
+# ---------------------------------------------------------------------------------------------- parity side check
+def parity_side_check(rank=0, world=1, device=0, collective="nccl"):
+    """Driver-visible multi-GPU correctness: a FIXED small run -- 4e6 particles, 4096 cells, device sampler (Philox,
+    counter = global particle index, so every sharding draws the same population), exactly 5 env steps -- whose
+    fixed-point state density is hashed.  The density is an integer sum, so the hash must be identical at 1, 2, 4 and
+    8 GPUs, and it is asserted against a constant on one GPU in tests/test_gpu_parity.py."""
+    import pic_b200
+    sim = pic_b200.ShardedPIC(PARITY_N, N_MESH, 1.0, L_BOX, 0.1, rank=rank, world_size=world, device=device,
+                              collective=collective)
+    sim.sample_state("bump-on-tail", a=0.2, v0=3.0, sigma=1.0, A=0.1, n_mode=2, seed=PARITY_SEED)
+    sim.step(None, PARITY_STEPS)
+    d = sim.diag()
+    rho, k = sim.engine.get_density_fixed()
+    out = {"rho_crc": hashlib.blake2b(np.ascontiguousarray(rho).tobytes(), digest_size=8).hexdigest(),
+           "rho_crc_kind": "blake2b-64 of the uint64[4096] fixed-point state density after %d steps" % PARITY_STEPS,
+           "fixed_bits": int(k), "pe_mesh": repr(float(d[1])), "sum_v": "%.10e" % float(d[2]),
+           "n_particles": PARITY_N, "seed": PARITY_SEED, "ranks": world}
+    sim.engine.close()
+    return out
+
+
 # ---------------------------------------------------------------------------------------------- GPU arm
 def run_gpu_arm(args):
     import torch
@@ -220,16 +356,6 @@ def run_gpu_arm(args):
     N = int(args.particles)
     hbm_peak, peak_src = measured_peaks()
 
-    sim = pic_b200.ShardedPIC(N, N_MESH, 1.0, L_BOX, 0.1, rank=rank, world_size=world, device=local,
-                              collective=args.collective, deposit=args.deposit)
-    eng = sim.engine
-    if args.threads:
-        eng.set_tuning(args.threads, args.unroll, args.ctas)
-    sim.sample_state("bump-on-tail", a=0.2, v0=3.0, sigma=1.0, A=0.1, n_mode=2, seed=42)
-    info = eng.launch_info()
-    N_local = sim.N_local
-    sim_dt, sim_collective = sim.dt, sim.collective
-
     def barrier():
         torch.cuda.synchronize()
         if world > 1:
@@ -242,6 +368,20 @@ def run_gpu_arm(args):
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t[0])
+
+    # ---- fixed parity side check first (small, bit-reproducible; same hash expected at every GPU count)
+    parity = parity_side_check(rank, world, local, args.collective)
+    barrier()
+
+    sim = pic_b200.ShardedPIC(N, N_MESH, 1.0, L_BOX, 0.1, rank=rank, world_size=world, device=local,
+                              collective=args.collective, deposit=args.deposit)
+    eng = sim.engine
+    if args.threads:
+        eng.set_tuning(args.threads, args.unroll, args.ctas)
+    sim.sample_state("bump-on-tail", a=0.2, v0=3.0, sigma=1.0, A=0.1, n_mode=2, seed=42)
+    info = eng.launch_info()
+    N_local = sim.N_local
+    sim_dt, sim_collective = sim.dt, sim.collective
 
     # ---- value: K steps, state resident in HBM, device-timed, max over ranks
     for _ in range(args.warmup):
@@ -257,17 +397,24 @@ def run_gpu_arm(args):
     settle_steps = 1 + int(min(100, max(0, np.ceil(SETTLE_S / max(one_step_s, 1e-4)) - args.warmup - 1)))
     for _ in range(settle_steps - 1):
         eng.step_mesh_device(None, 1)
-    barrier()
-    l0 = eng.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    # The timed region is EXACTLY K steps between barriers; when K steps are shorter than TIMED_MIN_S (many GPUs) the
+    # region is measured `reps` times back to back and the mean is reported, so that a few-percent effect is not
+    # decided by one 40 ms sample.
+    reps = int(min(25, max(1, np.ceil(TIMED_MIN_S / max(one_step_s * args.steps, 1e-4)))))
+    rep_ms, launches = [], 0
     with ClockSampler(local) as clk:
-        e0.record()
-        for _ in range(args.steps):
-            eng.step_mesh_device(None, 1)
-        e1.record()
-        barrier()
-    ms_total = max_over_ranks(e0.elapsed_time(e1))
-    launches = eng.launch_count() - l0
+        for _ in range(reps):
+            barrier()
+            l0 = eng.launch_count()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(args.steps):
+                eng.step_mesh_device(None, 1)
+            e1.record()
+            barrier()
+            rep_ms.append(max_over_ranks(e0.elapsed_time(e1)))
+            launches = eng.launch_count() - l0
+    ms_total = float(np.mean(rep_ms))
     ms_per_step = ms_total / args.steps
     value = N * args.steps / (ms_total * 1e-3)
     clocks = clk.summary()
@@ -280,23 +427,21 @@ def run_gpu_arm(args):
     for _ in range(max(1, args.warmup // 2)):
         eng.step_mesh_ptr(ext_host.data_ptr(), 1)
         eng.get_diag()
-    barrier()
-    t0 = time.perf_counter()
-    energies = []
-    for _ in range(args.steps):
-        eng.step_mesh_ptr(ext_host.data_ptr(), 1)        # H2D copy of this step's input inside the call
-        d = eng.get_diag()[0]                           # D2H read of this step's result (synchronises)
-        energies.append(float(d[PL.DIAG_KE] + d[PL.DIAG_PE_MESH] * N / L_BOX))
-    barrier()
-    e2e_s = time.perf_counter() - t0
-    if world > 1:
-        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t[0])
-    e2e_value = N * args.steps / e2e_s
+    e2e_rep_s, energies = [], []
+    for _ in range(reps):
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            eng.step_mesh_ptr(ext_host.data_ptr(), 1)        # H2D copy of this step's input inside the call
+            d = eng.get_diag()[0]                           # D2H read of this step's result (synchronises)
+            energies.append(float(d[PL.DIAG_KE] + d[PL.DIAG_PE_MESH] * N / L_BOX))
+        barrier()
+        e2e_rep_s.append(max_over_ranks((time.perf_counter() - t0) * 1e3) * 1e-3)
+    e2e_value = N * args.steps / float(np.mean(e2e_rep_s))
 
     # ---- for context: what a step costs when the caller insists on round-tripping the whole particle state through
-    #      host memory every step (pinned buffers, PCIe).  This is why the env state is device-resident.
+    #      host memory every step (pinned buffers, PCIe) -- what every reference runner does with sim.x / sim.v /
+    #      get_state() (run_wo_oc.py:116-122).  This is why the env state is device-resident.
     roundtrip = None
     if not args.no_roundtrip and world == 1:
         Nr = 50_000_000
@@ -318,83 +463,180 @@ def run_gpu_arm(args):
         er.close()
         del xh, vh
 
-    # ---- roofline: the dominant kernel (kick + drift + deposit pass, stages 1-3) timed alone with CUDA events
-    stages = (1, 2, 3, 4)                               # kick, kick, final (+ stage 0 of the next step), finalize
+    # ---- roofline: every pass of the step timed alone with CUDA events on the launching stream
+    stages = (1, 2, 3, 4)                               # stage 1, stage 2, stage 3 (+ stage 0 of the next step), finalize
+    stage_bytes = (32.0, 24.0, 32.0)                    # algorithmic bytes per particle per launch, float64
     stage_ms = np.zeros(len(stages))
-    reps = max(2, min(args.steps, 10))
-    evs = [[(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in stages] for _ in range(reps)]
+    sreps = max(2, min(args.steps, 10))
+    evs = [[(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in stages] for _ in range(sreps)]
     eng.set_stage_actuation(None, None)
     barrier()
-    for r in range(reps):
+    for r in range(sreps):
         for k, st in enumerate(stages):
             evs[r][k][0].record()
             eng.run_stage(st)
             evs[r][k][1].record()
     barrier()
-    for r in range(reps):
+    for r in range(sreps):
         for k in range(len(stages)):
-            stage_ms[k] += evs[r][k][0].elapsed_time(evs[r][k][1]) / reps
-    kick_ms = float(np.mean(stage_ms[0:2]))
-    alg_bytes = 32.0 * N_local                          # read x,v + write x,v, float64 (DESIGN.md "Roofline")
-    achieved = alg_bytes / (kick_ms * 1e-3) / 1e9
-    traffic, traffic_src = None, None
-    try:                                                # DRAM bytes of the same kernel from the committed ncu capture
-        with open(os.path.join(ROOT, "profiles", "traffic_r01.json")) as f:
-            tj = json.load(f)
-        traffic, traffic_src = tj["traffic_bytes_per_particle"] * N_local, tj["source"]
+            stage_ms[k] += evs[r][k][0].elapsed_time(evs[r][k][1]) / sreps
+    names = ["push_stream_kernel<MODE_KICK0> (stage 1: stage-0 drift redone on load, kick, drift, deposit; 32 B)",
+             "push_stream_kernel<MODE_KICK> (stage 2: kick, drift, deposit; stores v only; 24 B)",
+             "push_stream_kernel<MODE_FINAL> (stage 3: stage-2 drift redone on load, kick, drift, wrap, state deposit + "
+             "stage-0 deposit of the next step; 32 B)"]
+    traffic = {}
+    try:                                                # DRAM bytes per particle per launch from the committed ncu capture
+        with open(os.path.join(ROOT, "profiles", "traffic_r02.json")) as f:
+            traffic = json.load(f)
     except Exception:
         pass
-    roofline = {"bound": "hbm", "kernel": "push_stream_kernel<MODE_KICK> (2 of the 3 passes of a step)", "achieved": achieved,
-                "peak": hbm_peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / hbm_peak,
-                "traffic": traffic, "traffic_source": traffic_src,
-                "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": kick_ms,
-                "stage_ms": [float(s) for s in stage_ms],
-                "stage_names": ["kick (32 B)", "kick (32 B)", "final + next stage-0 deposit (32 B)", "field finalize"],
-                "bytes_per_particle_step": 96,
-                "step_frac_of_hbm": (96.0 * N_local / (float(stage_ms.sum()) * 1e-3) / 1e9) / hbm_peak}
+    kernels = []
+    for k in range(3):
+        ach = stage_bytes[k] * N_local / (stage_ms[k] * 1e-3) / 1e9
+        tr = traffic.get("bytes_per_particle", [None, None, None])[k]
+        kernels.append({"kernel": names[k], "kernel_ms": float(stage_ms[k]), "share_of_step": float(stage_ms[k] / stage_ms.sum()),
+                        "algorithmic_bytes_per_launch": stage_bytes[k] * N_local, "achieved": ach, "frac": ach / hbm_peak,
+                        "traffic": (tr * N_local if tr is not None else None)})
+    top = int(np.argmax(stage_ms[:3]))
+    roofline = {"bound": "hbm", "kernel": kernels[top]["kernel"], "achieved": kernels[top]["achieved"], "peak": hbm_peak,
+                "peak_source": peak_src, "unit": "GB/s", "frac": kernels[top]["frac"], "traffic": kernels[top]["traffic"],
+                "traffic_source": traffic.get("source"),
+                "algorithmic_bytes_per_launch": kernels[top]["algorithmic_bytes_per_launch"],
+                "kernel_ms": kernels[top]["kernel_ms"], "kernels": kernels, "finalize_ms": float(stage_ms[3]),
+                "bytes_per_particle_step": BYTES_PER_PARTICLE_STEP,
+                # the whole step against the same peak, from the ONE driver-checked number (ms_per_step)
+                "step_frac_of_hbm": (BYTES_PER_PARTICLE_STEP * N_local / (ms_per_step * 1e-3) / 1e9) / hbm_peak,
+                "note": "dominant = the pass with the largest share of the step; stages timed alone with CUDA events"}
     flags = eng.error_flags()
 
-    # ---- CPU baseline beside it (rank 0, N=1 only)
+    # ---- CPU baseline beside it (rank 0, N=1 only): the reference itself when this box has it
+    kind, ref = cpu_kind()
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        v1, slow, _ = cpu_baseline(2_000_000, 16, 1)
-        cpu = {"value": v1, "unit": UNIT, "cores": 1, "kind": "port",
-               "sample": "oracle port (faithful restatement of the reference's numpy path: 8 deposits + 8 periodic "
-                         "solves per step), one env of 2e6 particles, N_mesh=4096, 16 steps, %.1f s; the reference is "
-                         "single-threaded and cannot hold 1e9 particles" % slow}
+        n_s, k_s = 2_000_000, 3
+        pool = CpuPool(kind, 1, n_s, N_MESH, ref)
+        try:
+            sec = pool.run("step", k_s)
+        finally:
+            pool.close()
+        cpu = {"value": n_s * k_s / sec, "unit": UNIT, "cores": 1, "kind": kind,
+               "sample": sample_text(kind, 1, n_s, N_MESH, "%d steps after one warm-up step, %.1f s" % (k_s, sec))}
 
     # ---- batched-env companion number (BASELINE configs[3]); env-sharded, no communication
     batched = None
     if not args.no_batched:
+        def run_batched(B_total, lo, hi, T=10, breps=60):
+            bp = pic_b200.Engine(5000, 250, L_BOX, 0.05, n_envs=hi - lo, mode="resident", deposit="split32", max_mode=3,
+                                 device=local)
+            act = pic_b200.E_field(L_BOX, 250, 3)
+            bp.set_actuator_basis(act.basis_cos, act.basis_sin)
+            bp.sample_state("bump-on-tail", seed=7, n_global=5000, env_offset=lo)
+            coeffs = torch.rand(T, hi - lo, 6, dtype=torch.float64, device=dev) * 2 - 1
+            for _ in range(10):
+                bp.step_coeffs_device(coeffs.data_ptr(), T)
+            barrier()
+            b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            with ClockSampler(local) as bclk:
+                b0.record()
+                for _ in range(breps):                          # 600 env steps per env: long enough for sustained clocks
+                    bp.step_coeffs_device(coeffs.data_ptr(), T)
+                b1.record()
+                barrier()
+            bms = max_over_ranks(b0.elapsed_time(b1)) / (breps * T)
+            out = {"env_steps_per_s": B_total / (bms * 1e-3), "particle_steps_per_s": B_total * 5000 / (bms * 1e-3),
+                   "ms_per_batched_step": bms, "envs_per_gpu": hi - lo, "launch": bp.launch_info(), "clocks": bclk.summary(),
+                   "error_flags": int(bp.error_flags())}
+            bp.close()
+            return out
+
         B = 4096
         lo, hi = pic_b200.shard_range(B, rank, world)
-        bp = pic_b200.Engine(5000, 250, L_BOX, 0.05, n_envs=hi - lo, mode="resident", deposit="split32", max_mode=3,
-                             device=local)
-        act = pic_b200.E_field(L_BOX, 250, 3)
-        bp.set_actuator_basis(act.basis_cos, act.basis_sin)
-        bp.sample_state("bump-on-tail", seed=7, n_global=5000, env_offset=lo)
-        T = 10
-        coeffs = torch.rand(T, hi - lo, 6, dtype=torch.float64, device=dev) * 2 - 1
-        for _ in range(10):
-            bp.step_coeffs_device(coeffs.data_ptr(), T)
-        barrier()
-        reps = 60                                           # 600 env steps per env: long enough for sustained clocks
-        b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        with ClockSampler(local) as bclk:
-            b0.record()
-            for _ in range(reps):
-                bp.step_coeffs_device(coeffs.data_ptr(), T)
-            b1.record()
-            barrier()
-        bms = max_over_ranks(b0.elapsed_time(b1)) / (reps * T)
-        binfo = bp.launch_info()
-        batched = {"workload": "4096 envs x (N=5000, N_mesh=250, dt=0.05, 6 actuator coefficients per env per step)",
-                   "env_steps_per_s": B / (bms * 1e-3), "particle_steps_per_s": B * 5000 / (bms * 1e-3),
-                   "ms_per_batched_step": bms, "hbm_frac": (32.0 * 5000 * (hi - lo) / (bms * 1e-3) / 1e9) / hbm_peak,
-                   "launch": binfo, "clocks": bclk.summary(),
-                   "note": "one CTA per env, particle state in shared memory; bound by instruction issue / shared "
-                           "atomics (and the SM clock under the power cap), not HBM"}
-        bp.close()
+        strong = run_batched(B, lo, hi)
+        weak = run_batched(B * world, B * rank, B * (rank + 1)) if world > 1 else strong
+        batched = {"workload": "4096 envs x (N=5000, N_mesh=250, dt=0.05, 6 actuator coefficients per env per step), "
+                               "env-sharded over the GPUs (strong scaling: 4096 envs in total)",
+                   **strong,
+                   "hbm_frac": (32.0 * 5000 * (hi - lo) / (strong["ms_per_batched_step"] * 1e-3) / 1e9) / hbm_peak,
+                   "weak": {"workload": "4096 envs PER GPU (%d in total)" % (B * world),
+                            "env_steps_per_s": weak["env_steps_per_s"], "ms_per_batched_step": weak["ms_per_batched_step"]},
+                   "note": "one CTA (or CTA pair) per env, particle state in shared memory; bound by instruction issue / "
+                           "shared atomics (and the SM clock), not HBM"}
+        if rank == 0 and world == 1 and not args.no_cpu:
+            # the reference has no batching -> one reference env per process
+            procs = host_procs(5000, 250)
+            k_b = 100
+            p1 = CpuPool(kind, 1, 5000, 250, ref)
+            try:
+                s1 = p1.run("step", k_b)
+            finally:
+                p1.close()
+            pa = CpuPool(kind, procs, 5000, 250, ref)
+            try:
+                pa.run("step", 10)
+                sa = pa.run("step", k_b)
+            finally:
+                pa.close()
+            batched["cpu_baseline"] = {"unit": "env-steps/s", "kind": kind, "single_core": k_b / s1,
+                                       "all_core": procs * k_b / sa, "cores": procs,
+                                       "sample": "%s, one env (N=5000, N_mesh=250) per process, %d steps each"
+                                                 % ("reference PIC.update_state" if kind == "reference" else "oracle port", k_b)}
+
+    # ---- BASELINE configs 1-3: ONE small env (N=5000, N_mesh=250) through the reference-facing PIC class
+    single = None
+    if rank == 0 and world == 1 and not args.no_single:
+        from pic_b200.dist import BumpOnTail
+        np.random.seed(42)
+        d5 = BumpOnTail(a=0.2, v0=3.0, sigma=1.0, n_samples=5000, L=50.0)
+        s5 = pic_b200.PIC(N=5000, N_mesh=250, n0=1.0, L=50.0, dt=0.1, tmin=0.0, tmax=50.0, gamma=5.0, A=0.1, n_mode=2,
+                          interpol="CIC", init_dist=d5, device=local)
+        n_it = 2000
+        for _ in range(100):
+            s5.update_state(None)
+        s5.engine.sync()
+        t0 = time.perf_counter()
+        for _ in range(n_it):
+            s5.update_state(None)
+        s5.engine.sync()
+        us_update = (time.perf_counter() - t0) / n_it * 1e6
+        t0 = time.perf_counter()
+        for _ in range(n_it):                            # run_wo_oc.py:111-122 without the host-side Reward calls
+            s5.update_state(None)
+            s5.get_energy(); s5.get_electric_energy()
+            s5.x.copy(); s5.v.copy()
+            s5.get_state()
+        us_body = (time.perf_counter() - t0) / n_it * 1e6
+        s5.engine.step_mesh(None, 500)
+        s5.engine.sync()
+        t0 = time.perf_counter()
+        s5.engine.step_mesh(None, 5000)
+        s5.engine.sync()
+        us_dev = (time.perf_counter() - t0) / 5000 * 1e6
+        single = {"workload": "BASELINE configs 1-3: one env, N=5000, N_mesh=250, dt=0.1 (run_wo_oc.py / run_ddpg.py defaults)",
+                  "update_state_us": us_update, "run_wo_oc_loop_body_us": us_body, "device_only_us_per_step": us_dev,
+                  "particle_steps_per_s_device_only": 5000 / (us_dev * 1e-6), "launch": s5.engine.launch_info(),
+                  "api": "pic_b200.PIC.update_state / get_energy / get_electric_energy / .x / .v / get_state (host copies "
+                         "of the 80 KB state every iteration, as the runner does)"}
+        if not args.no_cpu:
+            pc = CpuPool(kind, 1, 5000, 250, ref)
+            try:
+                su = pc.run("step", 200)
+                sb = pc.run("body", 200)
+            finally:
+                pc.close()
+            single["cpu_baseline"] = {"kind": kind, "cores": 1, "update_state_us": su / 200 * 1e6,
+                                      "run_wo_oc_loop_body_us": sb / 200 * 1e6}
+        # mid-size single envs (streaming kernels, fixed per-pass cost visible): us per env step
+        mids = []
+        for Nm, Mm in ((1_000_000, 1024), (10_000_000, 4096)):
+            em = pic_b200.Engine(Nm, Mm, L_BOX, min(0.05, 2 / np.sqrt(Nm / L_BOX)), device=local)
+            em.sample_state("bump-on-tail", seed=3)
+            em.step_mesh_device(None, 50); em.sync()
+            ks = 500 if Nm <= 1_000_000 else 100
+            t0 = time.perf_counter(); em.step_mesh_device(None, ks); em.sync()
+            us = (time.perf_counter() - t0) / ks * 1e6
+            mids.append({"n_particles": Nm, "n_mesh": Mm, "us_per_step": us, "particle_steps_per_s": Nm / (us * 1e-6)})
+            em.close()
+        single["mid_size"] = mids
 
     # ---- the separate float32 mode (own tolerance: tests/test_gpu_f32.py), same workload, device-timed
     fp32 = None
@@ -414,8 +656,8 @@ def run_gpu_arm(args):
         f1.record()
         barrier()
         fms = max_over_ranks(f0.elapsed_time(f1)) / args.steps
-        fp32 = {"value": N / (fms * 1e-3), "unit": UNIT, "ms_per_step": fms, "bytes_per_particle_step": 48,
-                "step_frac_of_hbm": (48.0 * s32.N_local / (fms * 1e-3) / 1e9) / hbm_peak,
+        fp32 = {"value": N / (fms * 1e-3), "unit": UNIT, "ms_per_step": fms, "bytes_per_particle_step": BYTES_PER_PARTICLE_STEP // 2,
+                "step_frac_of_hbm": (BYTES_PER_PARTICLE_STEP / 2 * s32.N_local / (fms * 1e-3) / 1e9) / hbm_peak,
                 "tolerance": "per step |dx| <= 2e-5, |dv| <= 1e-5, PE rel 1e-4 vs the float64 reference; indices "
                              "bit-exact vs the float32 restatement (tests/test_gpu_f32.py)",
                 "error_flags": int(s32.engine.error_flags())}
@@ -431,15 +673,21 @@ def run_gpu_arm(args):
                        "n_particles": N, "n_mesh": N_MESH, "L": L_BOX, "dt": sim_dt, "parallelism": "particle-shard x%d" % world,
                        "collective": sim_collective,
                        "l2_policy": "inputs (16 B x %.3g particles per rank) exceed the 126 MB L2" % N_local,
-                       "launch": info, "extra_untimed_warmup_steps": settle_steps},
+                       "launch": info, "extra_untimed_warmup_steps": settle_steps,
+                       "timed_region": "exactly %d steps between barriers, measured %d time(s) back to back; ms_per_step and "
+                                       "value are the mean" % (args.steps, reps),
+                       "timed_region_ms": [float(m) for m in rep_ms],
+                       "parity": parity},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": N_MESH * 8, "d2h_bytes_per_step": diag_bytes,
                     "api": "pic_step_mesh(host E_external) + pic_get_diag per step (what PIC.update_state + "
-                           "PIC.get_energy do); particle state stays resident on the device"},
+                           "PIC.get_energy do); the particle state stays resident on the device -- see e2e_state_roundtrip "
+                           "for a caller that pulls x, v every step"},
             "gpu_launches": int(launches),
             "roofline": roofline,
             "cpu_baseline": cpu,
             "batched": batched,
+            "single_env": single,
             "e2e_state_roundtrip": roundtrip,
             "fp32_mode": fp32,
             "error_flags": int(flags),
@@ -458,14 +706,15 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--particles", type=float, default=N_FULL)
-    ap.add_argument("--deposit", default="split32")
-    ap.add_argument("--threads", type=int, default=1024)
-    ap.add_argument("--unroll", type=int, default=2)
+    ap.add_argument("--deposit", default="auto")
+    ap.add_argument("--threads", type=int, default=0)
+    ap.add_argument("--unroll", type=int, default=0)
     ap.add_argument("--ctas", type=int, default=0)
     ap.add_argument("--collective", default="nccl", choices=["fused", "nccl"],
                     help="density exchange of the particle-sharded mode: fused peer-memory exchange or ncclAllReduce")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-batched", action="store_true")
+    ap.add_argument("--no-single", action="store_true")
     ap.add_argument("--no-roundtrip", action="store_true")
     ap.add_argument("--no-fp32", action="store_true")
     args = ap.parse_args()

@@ -357,7 +357,7 @@ int run_stage(pic_handle* h, int stage, const double* ext, const double* coeffs,
         case 1: mode = MODE_KICK0; a.c_pre = h->cs[0]; a.rho_in = h->rho[0]; a.rho_out = h->rho[1]; a.rho_zero = h->rho[3];
                 reduce = h->rho[1]; break;
         case 2: mode = MODE_KICK; a.rho_in = h->rho[1]; a.rho_out = h->rho[2]; a.rho_zero = h->rho[0]; reduce = h->rho[2]; break;
-        case 3: mode = MODE_FINAL; a.rho_in = h->rho[2]; a.rho_out = h->rho[3]; a.rho_next = h->rho[0];
+        case 3: mode = MODE_FINAL; a.c_pre = h->cs[2]; a.rho_in = h->rho[2]; a.rho_out = h->rho[3]; a.rho_next = h->rho[0];
                 a.rho_zero = h->rho[1]; reduce = h->rho[3]; reduce_count = 2 * sz; break;
         default: return fail(h, PIC_EINVAL, "stage must be -1..4");
     }
@@ -519,6 +519,14 @@ int pic_create(const pic_config* cfg, pic_handle** out) {
     mc.M = h->M; mc.L = cfg->L; mc.dx = cfg->L / cfg->n_mesh; mc.inv_dx = 1.0 / mc.dx; mc.n0 = cfg->n0; mc.dt = cfg->dt;
     mc.dx2 = mc.dx * mc.dx; mc.inv2dx = 1.0 / (2.0 * mc.dx);
     mc.scale = cfg->n0 * cfg->L / (double)h->Ntotal / mc.dx;
+    h->dep = cfg->deposit == PIC_DEPOSIT_CAS64 ? DEP_CAS64 : DEP_SPLIT32;     // auto: native 32-bit atomics
+    if (h->f32) h->dep = DEP_SPLIT32;
+    int mode = cfg->mode;
+    // resident = the whole env (particles + mesh tables) fits the shared memory of one CTA
+    const size_t res512 = h->f32 ? resident_smem_bytes<float>(h->M, 512, h->N, h->ip) : resident_smem_bytes<double>(h->M, 512, h->N, h->ip);
+    const size_t res1024 = h->f32 ? resident_smem_bytes<float>(h->M, 1024, h->N, h->ip) : resident_smem_bytes<double>(h->M, 1024, h->N, h->ip);
+    if (mode == PIC_MODE_AUTO) mode = (long long)res1024 <= (long long)h->max_smem ? PIC_MODE_RESIDENT : PIC_MODE_STREAMING;
+    h->resident = mode == PIC_MODE_RESIDENT;
     int k = cfg->fixed_bits;
     if (k <= 0) {                                         // headroom: 8x the mean per-cell weight sum below 2^62
         double per_cell = (double)h->Ntotal / h->M;
@@ -533,14 +541,6 @@ int pic_create(const pic_config* cfg, pic_handle** out) {
     mc.idx_thr = (double)h->M * (h->f32 ? ldexp(1.0, -20) : ldexp(1.0, -49));
     mc.range_floor = h->ip == IP_TSC ? -(1LL << 61) : -(mc.fix_one << 2);
 
-    h->dep = cfg->deposit == PIC_DEPOSIT_CAS64 ? DEP_CAS64 : DEP_SPLIT32;     // auto: native 32-bit atomics
-    if (h->f32) h->dep = DEP_SPLIT32;
-    int mode = cfg->mode;
-    // resident = the whole env (particles + mesh tables) fits the shared memory of one CTA
-    const size_t res512 = h->f32 ? resident_smem_bytes<float>(h->M, 512, h->N, h->ip) : resident_smem_bytes<double>(h->M, 512, h->N, h->ip);
-    const size_t res1024 = h->f32 ? resident_smem_bytes<float>(h->M, 1024, h->N, h->ip) : resident_smem_bytes<double>(h->M, 1024, h->N, h->ip);
-    if (mode == PIC_MODE_AUTO) mode = (long long)res1024 <= (long long)h->max_smem ? PIC_MODE_RESIDENT : PIC_MODE_STREAMING;
-    h->resident = mode == PIC_MODE_RESIDENT;
     if (h->resident) {
         if ((long long)res1024 > (long long)h->max_smem) {
             delete h;

@@ -91,6 +91,15 @@ template <> struct RT<double> {
         ok = __double2hiint(t) == 0x43380000;
         return __dsub_rn(t, MAGIC);
     }
+    // floor(x * a) for 0 <= x * a < 2^32 by ONE fused multiply-add rounded down against the magic constant (the exact
+    // product plus 2^52+2^51 rounds down to an integer + magic); the integer sits in the low mantissa word.
+    // `hi_ok`: the high word is the magic's, i.e. 0 <= floor < 2^32 and the input was finite.
+    static __device__ __forceinline__ int floor_mul_magic(double x, double a, bool& hi_ok, double& t) {
+        t = __fma_rd(x, a, 6755399441055744.0);
+        hi_ok = __double2hiint(t) == 0x43380000;
+        return __double2loint(t);
+    }
+    static __device__ __forceinline__ double unmagic(double t) { return __dsub_rn(t, 6755399441055744.0); }
 };
 
 template <> struct RT<float> {
@@ -120,6 +129,12 @@ template <> struct RT<float> {
         ok = (__float_as_int(t) >> 22) == (0x4B400000 >> 22);
         return __fsub_rn(t, MAGIC);
     }
+    static __device__ __forceinline__ int floor_mul_magic(float x, float a, bool& hi_ok, float& t) {   // 0 <= floor < 2^22
+        t = __fmaf_rd(x, a, 12582912.0f);
+        hi_ok = (__float_as_int(t) >> 22) == (0x4B400000 >> 22);
+        return __float_as_int(t) - 0x4B400000;
+    }
+    static __device__ __forceinline__ float unmagic(float t) { return __fsub_rn(t, 12582912.0f); }
 };
 
 // llrint(w * 2^k) for |w * 2^k| < 2^51 without a conversion instruction: one fused multiply-add against the magic
@@ -155,7 +170,7 @@ struct MeshConst {
 
 template <typename R> struct PartConst {   // per-particle constants in the particle precision
     R L, twoL, dx, inv_dx, dt, idx_thr;
-    R half_m_thr;          // 0.5 - idx_thr
+    R inv_lo, inv_hi;      // (1/dx) (1 -+ eps), eps = idx_thr / N_mesh: the bracket of fast_cell
 };
 
 template <typename R>
@@ -163,7 +178,9 @@ __host__ __device__ inline PartConst<R> make_part_const(const MeshConst& m) {
     PartConst<R> c;
     c.L = (R)m.L; c.twoL = (R)(2.0 * m.L); c.dx = (R)m.dx; c.inv_dx = (R)1 / c.dx; c.dt = (R)m.dt;
     c.idx_thr = (R)m.idx_thr;
-    c.half_m_thr = (R)0.5 - c.idx_thr;
+    const R eps = (R)(m.idx_thr / (double)m.M);
+    c.inv_lo = c.inv_dx * ((R)1 - eps);
+    c.inv_hi = c.inv_dx * ((R)1 + eps);
     return c;
 }
 
@@ -252,18 +269,8 @@ __device__ __forceinline__ Cell cell_weights(R xw, const PartConst<R>& c, int M,
 //                 The cell density in fixed point is then  cnt[j] 2^k - S[j] + S[j-1]  -- three atomics per
 //                 particle instead of four and no wrap cell.
 // Both give the identical integer density (tests/test_gpu_parity.py::test_bitwise_reproducibility_across_kernels).
-//   DEP_PACK2   : TWO native 32-bit atomics per particle (large-N streaming mode, where the six / three atomics of
-//                 DEP_SPLIT32 make the LSU data pipe the binding unit).  Needs weights of at most 32 bits
-//                 (fixed_bits <= 31).  Word lo[il] += W_r with the old value returned; word hi[il] += 2^16 + carry:
-//                 the particle count lives in the upper half of hi, the carries of the low word (the bits 32.. of the
-//                 64-bit sum) in the lower half.  Both fields hold fewer than 2^16 = 65536 particles per cell, per CTA
-//                 and per flush: the kernel flushes often enough for 16x the mean density and CHECKS -- the counts it
-//                 reads back must add up to the particles it deposited, else ERR_DENSITY_RANGE (a field overflow loses
-//                 a carry out of bit 31, so the sum comes out short: the check is exact, never silent).
 constexpr int DEP_CAS64 = 0;
 constexpr int DEP_SPLIT32 = 1;
-constexpr int DEP_PACK2 = 2;
-constexpr int PACK2_MAX_BITS = 31;
 
 template <int DEP> struct Hist;
 
@@ -291,21 +298,26 @@ template <> struct Hist<DEP_CAS64> {
 
 // native 32-bit shared atomics by address in the shared window (inline PTX: keeps ptxas from wrapping constant
 // increments in its own MATCH.ANY-based warp aggregation, and needs no generic-to-shared conversion per access)
+#ifdef PIC_ATOM_NOCLOBBER      // experiment: let the compiler interleave the particles of a thread across the atomics
+#define PIC_ATOM_CLOBBER
+#else
+#define PIC_ATOM_CLOBBER : "memory"
+#endif
 __device__ __forceinline__ void red_shared_u32(unsigned addr, unsigned v) {
-    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(addr), "r"(v) PIC_ATOM_CLOBBER);
 }
 __device__ __forceinline__ unsigned atom_shared_u32(unsigned addr, unsigned v) {
     unsigned old;
-    asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(addr), "r"(v) : "memory");
+    asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(addr), "r"(v) PIC_ATOM_CLOBBER);
     return old;
 }
 // the same at a constant byte offset from addr (folded into the instruction's immediate)
 template <int OFF> __device__ __forceinline__ void red_shared_u32_at(unsigned addr, unsigned v) {
-    asm volatile("red.shared.add.u32 [%0+%2], %1;" ::"r"(addr), "r"(v), "n"(OFF) : "memory");
+    asm volatile("red.shared.add.u32 [%0+%2], %1;" ::"r"(addr), "r"(v), "n"(OFF) PIC_ATOM_CLOBBER);
 }
 template <int OFF> __device__ __forceinline__ unsigned atom_shared_u32_at(unsigned addr, unsigned v) {
     unsigned old;
-    asm volatile("atom.shared.add.u32 %0, [%1+%3], %2;" : "=r"(old) : "r"(addr), "r"(v), "n"(OFF) : "memory");
+    asm volatile("atom.shared.add.u32 %0, [%1+%3], %2;" : "=r"(old) : "r"(addr), "r"(v), "n"(OFF) PIC_ATOM_CLOBBER);
     return old;
 }
 
@@ -338,40 +350,6 @@ template <> struct Hist<DEP_SPLIT32> {
     }
     __device__ __forceinline__ unsigned long long get(int j, long long one) const {
         return (unsigned long long)w[3 * j] * (unsigned long long)one - S(j) + S(j == 0 ? M - 1 : j - 1);
-    }
-};
-
-// Layout: lo[0..M) then hi[0..M) (stride of one word: random cells spread over all 32 banks; cell-interleaved
-// (lo, hi) pairs would put every lo in an even bank and double the conflicts of each atomic instruction).
-template <> struct Hist<DEP_PACK2> {
-    unsigned* w;
-    unsigned lo_a, hi_off;               // lo[] as a shared-window byte address; byte distance from lo[j] to hi[j]
-    int M;
-    static __host__ __device__ constexpr size_t bytes(int M) { return (size_t)M * 8 + 8; }
-    __device__ __forceinline__ void init(void* base, int M_) {
-        M = M_; w = (unsigned*)base;
-        lo_a = (unsigned)__cvta_generic_to_shared(w);
-        hi_off = 4u * (unsigned)M_;
-    }
-    __device__ __forceinline__ void zero(int tid, int nthreads) {
-        for (int j = tid; j < 2 * M; j += nthreads) w[j] = 0u;
-    }
-    __device__ __forceinline__ void deposit_group(int il, unsigned long long S, unsigned count, long long) {
-        const unsigned wl = (unsigned)S, wh = (unsigned)(S >> 32), cell = lo_a + 4u * (unsigned)il;
-        const unsigned old = atom_shared_u32(cell, wl);
-        red_shared_u32(cell + hi_off, (count << 16) + wh + ((old + wl) < old ? 1u : 0u));
-    }
-    __device__ __forceinline__ void deposit(int il, long long Wr, long long) {      // Wr <= 2^31: no high word
-        const unsigned wl = (unsigned)Wr, cell = lo_a + 4u * (unsigned)il;
-        const unsigned old = atom_shared_u32(cell, wl);
-        red_shared_u32(cell + hi_off, 0x10000u + ((old + wl) < old ? 1u : 0u));
-    }
-    __device__ __forceinline__ unsigned cnt(int j) const { return w[M + j] >> 16; }
-    __device__ __forceinline__ unsigned long long S(int j) const {
-        return ((unsigned long long)(w[M + j] & 0xFFFFu) << 32) | (unsigned long long)w[j];
-    }
-    __device__ __forceinline__ unsigned long long get(int j, long long one) const {
-        return (unsigned long long)cnt(j) * (unsigned long long)one - S(j) + S(j == 0 ? M - 1 : j - 1);
     }
 };
 
@@ -628,12 +606,19 @@ __device__ __forceinline__ R drift(R x, R v, R cc, const PartConst<R>& c) {
 // the full-semantics code in a cold block.  Same bits either way.
 template <typename R>
 __device__ __forceinline__ bool fast_cell(R xw, const PartConst<R>& c, int M, int& il, R& f) {
-    R q = RT<R>::mul(xw, c.inv_dx);
-    bool ok;
-    f = RT<R>::floor_magic(q, il, ok);
-    const R frac = RT<R>::sub(q, f);                 // exact, in [0, 1)
-    // frac in (thr, 1 - thr)  <=>  |frac - 1/2| < 1/2 - thr  (the rounding of either side is far inside the margin)
-    return !ok | !(RT<R>::abs(RT<R>::sub(frac, (R)0.5)) < c.half_m_thr) | ((unsigned)il >= (unsigned)M);
+    // Bracket instead of threshold: floor(x a_lo) and floor(x a_hi) with a_lo/hi = (1/dx)(1 -+ eps) are two fused
+    // multiply-adds (round-down, against the magic constant).  eps = 2^-49 (2^-20 in float32) is 8x the relative
+    // distance between the correctly rounded quotient x/dx and x (1/dx), so when both floors agree every real number
+    // in between -- x/dx as IEEE division rounds it included -- has that floor: il == floor(x/dx), bit for bit.  They
+    // disagree only within eps of a cell edge (redone exactly on the careful path).  Three fp64-pipe instructions
+    // (2 DFMA + the subtraction that turns the integer back into a double) where multiply, magic add, two
+    // subtractions, an add and a compare were needed to measure the distance to the nearest integer.
+    bool ok_lo, ok_hi;
+    R t_lo, t_hi;
+    il = RT<R>::floor_mul_magic(xw, c.inv_lo, ok_lo, t_lo);
+    const int ih = RT<R>::floor_mul_magic(xw, c.inv_hi, ok_hi, t_hi);
+    f = RT<R>::unmagic(t_lo);
+    return !ok_lo | !ok_hi | (il != ih) | ((unsigned)il >= (unsigned)M);
 }
 
 // the three TSC weights from the in-cell distance d = (x - m dx)/dx, formulas followed literally (interpolate.py:28-32)
@@ -754,12 +739,30 @@ __device__ __forceinline__ void deposit_full_warp(H& hist, int il, long long Wa,
     }
 }
 
+// Aggregation hint.  Warp-aggregating the deposit only pays when the particles are cell-sorted (every lane of a warp in
+// the same cell, where 32 same-address atomics would serialise); for particles in random order the uniformity vote is
+// pure overhead -- 4-5 instructions per deposit, 4 % of the streaming passes.  Sortedness is a property of the particle
+// ORDER, so one probe per tile is enough: the first particle of a tile votes (PROBE) and its verdict `agg` (warp-
+// uniform) decides whether the other deposits of the tile take the aggregated route (which re-checks per particle,
+// so the hint can only cost time, never correctness) or go straight to their own atomics.
+template <int IP, bool PROBE, typename H>
+__device__ __forceinline__ void deposit_hinted(H& hist, int il, long long Wa, long long Wb, long long one, bool& agg) {
+#ifdef PIC_NO_VOTE
+    deposit_one<IP>(hist, il, Wa, Wb, one);
+#else
+    if (PROBE) agg = __all_sync(0xffffffffu, il == __shfl_sync(0xffffffffu, il, 0));
+    if (agg) deposit_full_warp<IP>(hist, il, Wa, Wb, one);
+    else deposit_one<IP>(hist, il, Wa, Wb, one);
+#endif
+}
+
 // One sub-stage for one particle: fast path, careful fallback, deposit.  x, v are updated in place.
-// FULL_WARP: the caller guarantees that all 32 lanes of the warp execute this call (enables the aggregated deposit).
-template <typename R, int IP, bool KICK, bool MOVE, bool EXACT_W, bool FULL_WARP, typename H>
+// FULL_WARP: the caller guarantees that all 32 lanes of the warp execute this call (enables the aggregated deposit,
+// steered by the per-tile hint `agg`; PROBE: this call refreshes the hint).
+template <typename R, int IP, bool KICK, bool MOVE, bool EXACT_W, bool FULL_WARP, typename H, bool PROBE = false>
 __device__ __forceinline__ void particle_substage(R& x, R& v, H& hist, const typename PairT<R>::type* __restrict__ E_s,
                                                   R cc, R dd, const PartConst<R>& c, const MeshConst& mc,
-                                                  bool wrap_state, unsigned& err) {
+                                                  bool wrap_state, unsigned& err, bool* agg = nullptr) {
     R xn, vn; int il; long long Wa, Wb;
     const bool slow = particle_fast<R, IP, KICK, MOVE, EXACT_W>(x, v, xn, vn, il, Wa, Wb, E_s, cc, dd, c, mc);
     if (__builtin_expect(slow, 0)) {
@@ -767,10 +770,12 @@ __device__ __forceinline__ void particle_substage(R& x, R& v, H& hist, const typ
     } else {
         x = xn; v = vn;                                   // inside [0, L): wrapped == unwrapped
     }
-    // (the warp-uniformity test costs ~5 instructions per particle even when it never fires; measured with it removed
-    //  the kernels are 4-5 % SLOWER -- the vote also reconverges the warp after the cold branch above)
-    if (FULL_WARP) deposit_full_warp<IP>(hist, il, Wa, Wb, mc.fix_one);
-    else deposit_one<IP>(hist, il, Wa, Wb, mc.fix_one);
+    if (FULL_WARP) {
+        __syncwarp();                                     // reconverge after the cold branch before the warp-wide part
+        deposit_hinted<IP, PROBE>(hist, il, Wa, Wb, mc.fix_one, *agg);
+    } else {
+        deposit_one<IP>(hist, il, Wa, Wb, mc.fix_one);
+    }
 }
 
 // Stage 0 of the NEXT env step, done while the particle is still in registers: the first Yoshida sub-stage has d = 0
@@ -781,7 +786,7 @@ __device__ __forceinline__ void particle_substage(R& x, R& v, H& hist, const typ
 // This removes one whole pass over the particles from every env step: 96 instead of 120 bytes per particle-step.
 template <typename R, int IP, bool EXACT_W, bool FULL_WARP, typename H>
 __device__ __forceinline__ void next_stage0(R x_state, R v, H& hist_next, R c0, const PartConst<R>& c, const MeshConst& mc,
-                                            unsigned& err) {
+                                            unsigned& err, bool* agg = nullptr) {
     const R x1 = RT<R>::add(x_state, RT<R>::mul(RT<R>::mul(c0, v), c.dt));
     int il; R f; long long Wa, Wb;
     const bool slow = fast_cell<R>(x1, c, mc.M, il, f);
@@ -791,8 +796,18 @@ __device__ __forceinline__ void next_stage0(R x_state, R v, H& hist_next, R c0, 
         il = cell_index<R>(xw, c, mc.M, f, err);
         deposit_weights<R, IP, EXACT_W>(xw, f, c, mc, Wa, Wb);
     }
-    if (FULL_WARP) deposit_full_warp<IP>(hist_next, il, Wa, Wb, mc.fix_one);
-    else deposit_one<IP>(hist_next, il, Wa, Wb, mc.fix_one);
+    if (FULL_WARP) {
+        __syncwarp();
+        deposit_hinted<IP, false>(hist_next, il, Wa, Wb, mc.fix_one, *agg);
+    } else {
+        deposit_one<IP>(hist_next, il, Wa, Wb, mc.fix_one);
+    }
+}
+
+// One thread asks the L2 to fetch a contiguous range ahead of the loads that will consume it (UBLKPF.L2): no registers,
+// no shared memory, one instruction per range.  p 16-byte aligned, bytes a multiple of 16.
+__device__ __forceinline__ void prefetch_l2_bulk(const void* p, unsigned bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
 
 // streaming loads / stores (no reuse: keep the particle stream out of L1, evict-first in L2)
