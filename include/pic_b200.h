@@ -195,7 +195,11 @@ int pic_set_stage_actuation(pic_handle* h, const double* E_ext_dev, const double
 /* --- tuning / introspection ---------------------------------------------------------------------------------- */
 int pic_get_launch_info(pic_handle* h, int32_t* mode, int32_t* threads, int32_t* per_thread, int32_t* grid_x,
                         int32_t* smem_bytes, int32_t* fixed_bits, int32_t* deposit);
-int pic_set_tuning(pic_handle* h, int32_t threads, int32_t unroll_or_ppt, int32_t ctas_per_sm);
+/* streaming mode: threads per CTA, 16-byte vectors in flight per thread, CTAs per SM (0 = as many as fit);
+ * resident mode: threads per CTA, CTAs PER ENV (1 = one CTA per env; 2, 4, 8 = the env spread over a thread-block
+ * cluster whose CTAs exchange their histograms through distributed shared memory), third argument unused.
+ * pic_get_launch_info reports the same quantity in *per_thread.  0 / negative = keep. */
+int pic_set_tuning(pic_handle* h, int32_t threads, int32_t unroll_or_cluster, int32_t ctas_per_sm);
 int64_t pic_kernel_launch_count(const pic_handle* h);        /* kernels enqueued by this handle so far */
 
 #if defined(__GNUC__)

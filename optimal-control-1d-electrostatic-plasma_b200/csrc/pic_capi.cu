@@ -73,6 +73,7 @@ struct pic_handle {
 
     // tuning
     int threads = 256, per_thread = 2, ctas_per_sm = 0, grid_x = 1, occ = 1;
+    int cluster = 1;                                // resident mode: CTAs per env (thread-block cluster over DSMEM)
     size_t smem = 0;
 
     // device buffers
@@ -137,10 +138,16 @@ const void* stream_kernel(const pic_handle* h, int mode) {
                   : stream_kernel_f64(h->threads, h->per_thread, mode, h->dep, h->exact_w);
 }
 const void* resident_kernel(const pic_handle* h) {
+    if (h->cluster > 1)
+        return (h->dep == DEP_SPLIT32 && !h->exact_w) ? cluster_kernel(h->f32, h->threads, h->cluster, h->ip) : nullptr;
     if (h->ip == IP_TSC) return resident_kernel_tsc(h->threads);
     return h->f32 ? resident_kernel_f32(h->threads, h->dep, h->exact_w) : resident_kernel_f64(h->threads, h->dep, h->exact_w);
 }
+long long cluster_slice(const pic_handle* h) { return (h->N + h->cluster - 1) / h->cluster; }
 size_t smem_for(const pic_handle* h) {
+    if (h->resident && h->cluster > 1)
+        return h->f32 ? cluster_smem_bytes<float>(h->M, h->threads, cluster_slice(h), h->cluster, h->ip)
+                      : cluster_smem_bytes<double>(h->M, h->threads, cluster_slice(h), h->cluster, h->ip);
     if (h->resident)
         return h->f32 ? resident_smem_bytes<float>(h->M, h->threads, h->N, h->ip)
                       : resident_smem_bytes<double>(h->M, h->threads, h->N, h->ip);
@@ -151,13 +158,16 @@ size_t smem_for(const pic_handle* h) {
 int configure_launch(pic_handle* h) {
     h->smem = smem_for(h);
     if ((int)h->smem > h->max_smem)
-        return fail(h, PIC_EUNSUPPORTED, "n_mesh too large for the shared-memory mesh tables (" +
+        return fail(h, PIC_EUNSUPPORTED, h->resident ? "env does not fit the shared memory of its CTA(s) (" + std::to_string(h->smem) +
+                    " B needed per CTA, " + std::to_string(h->max_smem) + " B available)"
+                    : "n_mesh too large for the shared-memory mesh tables (" +
                     std::to_string(h->smem) + " B needed, " + std::to_string(h->max_smem) + " B available)");
     if (h->resident) {
         const void* k = resident_kernel(h);
-        if (!k) return fail(h, PIC_EUNSUPPORTED, "no resident kernel variant for threads=" + std::to_string(h->threads));
+        if (!k) return fail(h, PIC_EUNSUPPORTED, "no resident kernel variant for threads=" + std::to_string(h->threads) +
+                            " cluster=" + std::to_string(h->cluster) + " (clusters: split32 deposit, exact_weights=0)");
         CK(h, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
-        h->grid_x = h->n_envs;
+        h->grid_x = h->n_envs * h->cluster;
         return PIC_OK;
     }
     int occ_min = 1 << 30;
@@ -408,13 +418,26 @@ int launch_resident(pic_handle* h, int n_steps, const double* ext, const double*
     for (int i = 0; i < 4; ++i) { a.c[i] = h->cs[i]; a.d[i] = h->ds[i]; }
     a.n_out = h->n; a.E_out = h->E; a.diag = h->diag; a.trace = n_steps > 0 ? h->trace : nullptr;
     a.rho_out = h->rho[3]; a.err = h->err;
-    a.lay = h->f32 ? smem_offsets<float>(h->M, h->threads, true, h->ip, false, h->N)
-                   : smem_offsets<double>(h->M, h->threads, true, h->ip, false, h->N);
+    const bool cl = h->cluster > 1;                  // cluster mode: two histograms, the CTA's particle slice
+    const long long n_res = cl ? cluster_slice(h) : h->N;
+    a.lay = h->f32 ? smem_offsets<float>(h->M, h->threads, true, h->ip, cl, n_res)
+                   : smem_offsets<double>(h->M, h->threads, true, h->ip, cl, n_res);
     a.rw = h->rw; a.tw_cos = h->tw_cos; a.tw_sin = h->tw_sin; a.n_modes = h->n_modes;
     a.modes = h->n_modes > 0 ? h->modes : nullptr;
     a.mode_trace = (h->n_modes > 0 && n_steps > 0) ? h->mode_trace : nullptr;
     void* args[] = {&a};
-    CK(h, cudaLaunchKernel(resident_kernel(h), dim3(h->n_envs), dim3(h->threads), args, h->smem, h->stream));
+    if (cl) {
+        cudaLaunchConfig_t lc{};
+        lc.gridDim = dim3(h->n_envs * h->cluster); lc.blockDim = dim3(h->threads);
+        lc.dynamicSmemBytes = h->smem; lc.stream = h->stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = h->cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        lc.attrs = at; lc.numAttrs = 1;
+        CK(h, cudaLaunchKernelExC(&lc, resident_kernel(h), args));
+    } else {
+        CK(h, cudaLaunchKernel(resident_kernel(h), dim3(h->n_envs), dim3(h->threads), args, h->smem, h->stream));
+    }
     h->launches++;
     if (a.mode_trace)            // the state's modes = the last row of the per-step record
         CK(h, cudaMemcpyAsync(h->modes, h->mode_trace + (size_t)(n_steps - 1) * h->n_envs * 2 * h->n_modes,
@@ -527,6 +550,7 @@ int pic_create(const pic_config* cfg, pic_handle** out) {
     const size_t res1024 = h->f32 ? resident_smem_bytes<float>(h->M, 1024, h->N, h->ip) : resident_smem_bytes<double>(h->M, 1024, h->N, h->ip);
     if (mode == PIC_MODE_AUTO) mode = (long long)res1024 <= (long long)h->max_smem ? PIC_MODE_RESIDENT : PIC_MODE_STREAMING;
     h->resident = mode == PIC_MODE_RESIDENT;
+
     int k = cfg->fixed_bits;
     if (k <= 0) {                                         // headroom: 8x the mean per-cell weight sum below 2^62
         double per_cell = (double)h->Ntotal / h->M;
@@ -542,22 +566,34 @@ int pic_create(const pic_config* cfg, pic_handle** out) {
     mc.range_floor = h->ip == IP_TSC ? -(1LL << 61) : -(mc.fix_one << 2);
 
     if (h->resident) {
-        if ((long long)res1024 > (long long)h->max_smem) {
+        // CTAs per env: one if the env fits one CTA's shared memory, else the smallest thread-block cluster that holds it
+        // (each CTA keeps a slice of the particles; histograms meet through distributed shared memory)
+        h->threads = 1024;
+        for (h->cluster = 1; h->cluster <= 8 && (long long)smem_for(h) > (long long)h->max_smem; h->cluster *= 2) {}
+        if (h->cluster > 8 || (h->cluster > 1 && (h->dep != DEP_SPLIT32 || h->exact_w))) {
             delete h;
             return fail(nullptr, PIC_EUNSUPPORTED, "n_particles too large for resident mode (env does not fit in shared memory)");
         }
-        // as many envs per SM as fit side by side, so that one env's field solves overlap the others' particle loops
-        // (measured best in every case tried): four 256-thread CTAs, else two of 512 threads, else one of 1024
-        const size_t res256 = h->f32 ? resident_smem_bytes<float>(h->M, 256, h->N, h->ip) : resident_smem_bytes<double>(h->M, 256, h->N, h->ip);
         const size_t per_sm = (size_t)h->max_smem + 1024;          // every CTA reserves 1 KB on top of its request
-        h->threads = 2 * (res512 + 1024) <= per_sm ? 512 : 1024;
-        if (h->n_envs <= h->sm_count) {
-            // every env has an SM to itself: nothing to overlap, the step latency decides (measured: 1024 threads
-            // win from ~4000 particles per env, 512 below)
-            h->threads = h->N >= 4096 ? 1024 : 512;
-        } else if (4 * (res256 + 1024) <= per_sm) {
-            h->threads = 256;
-            if (!resident_kernel(h)) h->threads = 512;             // variant not compiled (exact_weights)
+        if (h->cluster == 1) {
+            // as many envs per SM as fit side by side, so that one env's field solves overlap the others' particle loops
+            // (measured best in every case tried): four 256-thread CTAs, else two of 512 threads, else one of 1024
+            const size_t res256 = h->f32 ? resident_smem_bytes<float>(h->M, 256, h->N, h->ip) : resident_smem_bytes<double>(h->M, 256, h->N, h->ip);
+            h->threads = 2 * (res512 + 1024) <= per_sm ? 512 : 1024;
+            if (h->n_envs <= h->sm_count) {
+                // every env has an SM to itself: nothing to overlap, the step latency decides (measured: 1024 threads
+                // win from ~4000 particles per env, 512 below)
+                h->threads = h->N >= 4096 ? 1024 : 512;
+            } else if (4 * (res256 + 1024) <= per_sm) {
+                h->threads = 256;
+                if (!resident_kernel(h)) h->threads = 512;             // variant not compiled (exact_weights)
+            }
+        } else {
+            for (int t : {256, 512}) {                                 // most CTAs per SM that fit
+                h->threads = t;
+                if ((1024 / t) * (smem_for(h) + 1024) <= per_sm && resident_kernel(h)) break;
+                h->threads = 1024;
+            }
         }
         h->per_thread = 0;
     } else {
@@ -618,11 +654,13 @@ int pic_set_tuning(pic_handle* h, int32_t threads, int32_t per_thread, int32_t c
     if (!h) return PIC_EINVAL;
     int t0 = h->threads, p0 = h->per_thread, c0 = h->ctas_per_sm;
     if (threads > 0) h->threads = threads;
+    const int cl0 = h->cluster;
     if (per_thread > 0 && !h->resident) h->per_thread = per_thread;
+    if (per_thread > 0 && h->resident) h->cluster = per_thread;          // resident mode: CTAs per env (1, 2, 4, 8)
     if (ctas_per_sm >= 0) h->ctas_per_sm = ctas_per_sm;
     cudaStreamSynchronize(h->stream);
     int rc = configure_launch(h);
-    if (rc) { h->threads = t0; h->per_thread = p0; h->ctas_per_sm = c0; configure_launch(h); }
+    if (rc) { h->threads = t0; h->per_thread = p0; h->ctas_per_sm = c0; h->cluster = cl0; configure_launch(h); }
     return rc;
 }
 
@@ -631,7 +669,7 @@ int pic_get_launch_info(pic_handle* h, int32_t* mode, int32_t* threads, int32_t*
     if (!h) return PIC_EINVAL;
     if (mode) *mode = h->resident ? PIC_MODE_RESIDENT : PIC_MODE_STREAMING;
     if (threads) *threads = h->threads;
-    if (per_thread) *per_thread = h->per_thread;
+    if (per_thread) *per_thread = h->resident ? h->cluster : h->per_thread;
     if (grid_x) *grid_x = h->grid_x;
     if (smem_bytes) *smem_bytes = (int32_t)h->smem;
     if (fixed_bits) *fixed_bits = h->fixed_bits;

@@ -655,6 +655,226 @@ __global__ void __launch_bounds__(THREADS, THREADS <= 512 ? 1024 / THREADS : 1) 
     if (err) atomicOr(a.err, err);
 }
 
+// ----------------------------------------------------------------- resident, one env over a CTA cluster
+// The same env step with the env spread over CL CTAs of a thread-block cluster (CL SMs, or CL slots of the same SMs):
+// CTA r keeps the r-th slice of the particles in its shared memory and deposits into its own histogram; the field
+// solve of every sub-stage reads ALL the cluster's histograms through distributed shared memory (each CTA solves the
+// whole mesh redundantly -- the mesh is tiny -- so nothing has to be sent back), and the per-CTA kinetic sums are
+// exchanged the same way.  Why:
+//   * finer scheduling units.  With one CTA per env two 512-thread CTAs share an SM, and a batch that does not fill a
+//     whole number of waves (512 envs on 2 x 148 slots = 1.73 waves) pays for 2; half-env CTAs of 256 threads run four
+//     to an SM, the last wave is 3/4 full instead of 1/2, and an SM with three co-resident CTAs loses far less
+//     throughput than one with a single CTA of two;
+//   * envs that do not fit ONE CTA's shared memory (N > ~13 000 particles at float64; the SAC shape N = 10 000,
+//     N_mesh = 500 fits only one CTA per SM) stay in the resident kernel -- one launch per call, the state never leaves
+//     the chip -- instead of falling back to three streaming launches per env step.
+// Histograms are double-buffered: sub-stage s deposits into buffer s & 1 and the other one -- last read by the peers
+// during the solve of sub-stage s - 1, which they have left before arriving at this sub-stage's cluster barrier -- is
+// cleared meanwhile.  That makes ONE cluster barrier per sub-stage enough (4 per env step).
+// Integer densities: x, v, fields are bit-identical to the one-CTA kernel; only the kinetic sums (float) differ in
+// their last bits because they are added up in a different order.
+template <typename H, int CL> struct ClusterRho {
+    H h[CL];                       // every rank's histogram of the current buffer (generic pointers into peer smem)
+    long long one;
+    __device__ __forceinline__ unsigned long long operator()(int j) const {
+        unsigned long long s = 0;
+#pragma unroll
+        for (int r = 0; r < CL; ++r) s += h[r].get(j, one);
+        return s;
+    }
+};
+
+__device__ __forceinline__ unsigned cluster_ctarank() {
+    unsigned r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {       // barrier.cluster with release / acquire semantics
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// generic address of `p` (a shared-memory object of this CTA) in the shared memory of cluster rank r
+template <typename T> __device__ __forceinline__ T* map_to_rank(T* p, unsigned r) {
+    unsigned long long out;
+    asm volatile("mapa.u64 %0, %1, %2;" : "=l"(out) : "l"((unsigned long long)p), "r"(r));
+    return (T*)out;
+}
+
+template <typename R>
+__host__ __device__ constexpr size_t cluster_smem_bytes(int M, int threads, long long n_slice, int cl, int ip = IP_CIC) {
+    // gather table + two histograms + D_s + scratch + particle slice + E_ext of the step + per-warp kinetic partials
+    return smem_plan_bytes<R>(M, threads, true, ip, true) + (size_t)((n_slice + 1) / 2 * 2) * 2 * sizeof(R) + (size_t)M * 8 +
+           (size_t)(threads / 32) * 2 * 8;
+}
+
+template <typename R, int THREADS, int CL, bool EXACT_W, int IP = IP_CIC>
+__global__ void __launch_bounds__(THREADS, THREADS <= 512 ? 1024 / THREADS : 1) env_step_cluster_kernel(const ResidentArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int NW = THREADS / 32;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, M = a.mc.M;
+    const unsigned crank = cluster_ctarank();
+    const int env = blockIdx.x / CL;
+    const int n_lo = (int)(a.N * crank / CL), n_hi = (int)(a.N * (crank + 1) / CL), N = n_hi - n_lo;   // this CTA's slice
+    SmemLayout<R> sm(smem_raw, a.lay);
+    R* x_s = (R*)(smem_raw + a.lay.x);
+    R* v_s = (R*)(smem_raw + a.lay.v);
+    double* ext_s = (double*)(smem_raw + a.lay.ext);
+    double* part_s = ext_s + M;                               // [NW][2] per-warp sum v^2, sum v of the final sub-stage
+    using H = typename HistSel<DEP_SPLIT32, IP>::type;
+    // Two histogram buffers; sub-stage s of an env step uses buffer s & 1 (four sub-stages per step: every step starts
+    // on buffer 0), so the buffer is a compile-time constant everywhere below and everything stays in registers.
+    H hist0, hist1;
+    hist0.init(sm.hist, M); hist1.init(sm.hist2, M);
+    ClusterRho<H, CL> rho0, rho1;
+    rho0.one = rho1.one = a.mc.fix_one;
+#pragma unroll
+    for (int r = 0; r < CL; ++r) {
+        rho0.h[r] = hist0; rho0.h[r].w = map_to_rank(hist0.w, (unsigned)r);
+        rho1.h[r] = hist1; rho1.h[r].w = map_to_rank(hist1.w, (unsigned)r);
+    }
+    const PartConst<R> pc = make_part_const<R>(a.mc);
+    R* xe = (R*)a.x + (size_t)env * a.ld + n_lo;
+    R* ve = (R*)a.v + (size_t)env * a.ld + n_lo;
+    for (int i = tid; i < N; i += THREADS) { x_s[i] = xe[i]; v_s[i] = ve[i]; }
+    hist0.zero(tid, THREADS); hist1.zero(tid, THREADS);
+    __syncthreads();
+    unsigned err = 0;
+    const bool lead = crank == 0;                             // rank 0 writes the env's outputs
+    double* n_out = a.n_out + (size_t)env * M;
+    double* E_out = a.E_out + (size_t)env * M;
+    const ExtSrc none{nullptr, nullptr, nullptr, nullptr, 0};
+    constexpr int FT = FieldShape<THREADS>::FT;
+    auto clear = [&](H& h) {                                  // called by the threads block_field leaves idle
+        if (FT == THREADS) h.zero(tid, THREADS);
+        else h.zero(tid - FT, THREADS - FT);
+    };
+    // per-warp kinetic partials -> shared memory (before the cluster barrier); summed over ranks and warps in a fixed
+    // order by warp 0 of every CTA after it, so that all CTAs of the cluster hold the same doubles
+    auto publish_kinetic = [&](double s2, double s1) {
+        s2 = warp_sum(s2); s1 = warp_sum(s1);
+        if (lane == 0) { part_s[2 * warp] = s2; part_s[2 * warp + 1] = s1; }
+    };
+    auto gather_kinetic = [&](double& s2, double& s1) {       // valid in warp 0
+        s2 = 0.0; s1 = 0.0;
+        if (warp == 0) {
+            for (int k = lane; k < CL * NW; k += 32) {
+                const double* p = map_to_rank(part_s, (unsigned)(k / NW)) + 2 * (k % NW);
+                s2 += p[0]; s1 += p[1];
+            }
+            s2 = warp_sum(s2); s1 = warp_sum(s1);
+        }
+    };
+    double pe_pre = 0.0;
+    if (tid == 0 && a.n_steps > 0) pe_pre = a.diag[(size_t)env * DIAG_N + DIAG_PE_MESH];
+    auto write_diag = [&](const FieldTotals& t, double s2, double s1, int step, double input_e) {
+        if (tid == 0 && lead) {
+            double rec[DIAG_N];
+            rec[DIAG_KE] = 0.5 * s2; rec[DIAG_PE_MESH] = 0.5 * t.e2 * a.mc.dx; rec[DIAG_SUM_V] = s1; rec[DIAG_SUM_E2] = t.e2;
+            rec[DIAG_REWARD] = 0.0; rec[DIAG_INPUT_E] = 0.0;
+            if (step >= 0) {
+                rec[DIAG_INPUT_E] = input_e;
+                rec[DIAG_REWARD] = reward_of(a.rw, pe_pre, rec[DIAG_INPUT_E]);
+                pe_pre = rec[DIAG_PE_MESH];
+            }
+            double* d = a.diag + (size_t)env * DIAG_N;
+#pragma unroll
+            for (int k = 0; k < DIAG_N; ++k) d[k] = rec[k];
+            if (a.trace && step >= 0) {
+                double* tr = a.trace + ((size_t)step * (gridDim.x / CL) + env) * DIAG_N;
+#pragma unroll
+                for (int k = 0; k < DIAG_N; ++k) tr[k] = rec[k];
+            }
+        }
+    };
+    auto dump_rho = [&](const ClusterRho<H, CL>& rho) {
+        if (a.rho_out && lead) for (int j = tid; j < M; j += THREADS) a.rho_out[(size_t)env * M + j] = rho(j);
+    };
+    // one kick/drift sub-stage into histogram `hc` (summed over the cluster by `rc`), clearing the other buffer `ho`
+    auto kick_stage = [&](H& hc, const ClusterRho<H, CL>& rc, H& ho, R cc, R dd, const ExtSrc& ext) {
+#pragma unroll 2
+        for (int i = tid; i < N; i += THREADS) {
+            R x = x_s[i], v = v_s[i];
+            particle_substage<R, IP, true, true, EXACT_W, false>(x, v, hc, sm.E_s, cc, dd, pc, a.mc, false, err);
+            x_s[i] = x; v_s[i] = v;
+        }
+        cluster_sync_all();
+        block_field<R, THREADS, false>(rc, sm.E_s, sm.D_s, sm.red, a.mc, ext, nullptr, nullptr, 0.0, 0.0, [&] { clear(ho); });
+    };
+
+    if (a.n_steps == 0) {                                            // initial state: wrap + deposit + field (buffer 0)
+        double s2 = 0.0, s1 = 0.0;
+        for (int i = tid; i < N; i += THREADS) {
+            R x = x_s[i], v = v_s[i];
+            particle_substage<R, IP, false, false, EXACT_W, false>(x, v, hist0, sm.E_s, (R)0, (R)0, pc, a.mc, true, err);
+            x_s[i] = x;
+            s2 += (double)v * (double)v; s1 += (double)v;
+        }
+        publish_kinetic(s2, s1);
+        cluster_sync_all();
+        dump_rho(rho0);
+        gather_kinetic(s2, s1);
+        const ModeOut mo{a.tw_cos, a.tw_sin, (a.modes && lead) ? a.modes + (size_t)env * 2 * a.n_modes : nullptr, a.n_modes};
+        const FieldTotals t = block_field<R, THREADS>(rho0, sm.E_s, sm.D_s, sm.red, a.mc, none, lead ? n_out : nullptr,
+                                                      lead ? E_out : nullptr, 0.0, 0.0, [&] { clear(hist1); }, mo, a.err);
+        write_diag(t, s2, s1, -1, 0.0);
+    }
+
+    for (int step = 0; step < a.n_steps; ++step) {
+        ActuatorArgs act = a.act;
+        if (act.coeffs) act.coeffs += (size_t)step * a.coeff_step_stride;
+        if (act.ext) act.ext += (size_t)step * a.ext_step_stride;
+        const ExtSrc ext_g = stage_ext(act, env, M);
+        const bool last = step == a.n_steps - 1;
+        double input_e = 0.0;
+        if (tid == 0 && ext_g.coeff) input_e = input_energy(ext_g.coeff, 2 * a.act.m, a.rw.L);
+        ExtSrc ext = none;
+        if (ext_g.any()) {                                           // E_external of the step on the mesh, once (pic.py:131-137)
+            for (int j = tid; j < M; j += THREADS) ext_s[j] = ext_g.at(j);
+            ext.ext = ext_s;
+        }
+        {                                                            // stage 0: drift only (integration.py:71); buffer 0
+            const R cc = (R)a.c[0];
+#pragma unroll 2
+            for (int i = tid; i < N; i += THREADS) {
+                R x = x_s[i], v = v_s[i];
+                particle_substage<R, IP, false, true, EXACT_W, false>(x, v, hist0, sm.E_s, cc, (R)0, pc, a.mc, false, err);
+                x_s[i] = x;
+            }
+            cluster_sync_all();
+            block_field<R, THREADS, false>(rho0, sm.E_s, sm.D_s, sm.red, a.mc, ext, nullptr, nullptr, 0.0, 0.0, [&] { clear(hist1); });
+        }
+        kick_stage(hist1, rho1, hist0, (R)a.c[1], (R)a.d[1], ext);   // stage 1: kick + drift; buffer 1
+        kick_stage(hist0, rho0, hist1, (R)a.c[2], (R)a.d[2], ext);   // stage 2; buffer 0
+        {                                                            // stage 3: kick + drift + state wrap + kinetic sums; buffer 1
+            const R cc = (R)a.c[3], dd = (R)a.d[3];
+            double s2 = 0.0, s1 = 0.0;
+#pragma unroll 2
+            for (int i = tid; i < N; i += THREADS) {
+                R x = x_s[i], v = v_s[i];
+                particle_substage<R, IP, true, true, EXACT_W, false>(x, v, hist1, sm.E_s, cc, dd, pc, a.mc, true, err);
+                x_s[i] = x; v_s[i] = v;
+                s2 += (double)v * (double)v; s1 += (double)v;
+            }
+            publish_kinetic(s2, s1);
+            cluster_sync_all();
+            if (last) dump_rho(rho1);
+            gather_kinetic(s2, s1);
+            double* mout = nullptr;
+            if (a.n_modes > 0 && lead) {
+                if (a.mode_trace) mout = a.mode_trace + ((size_t)step * (gridDim.x / CL) + env) * 2 * a.n_modes;
+                else if (last && a.modes) mout = a.modes + (size_t)env * 2 * a.n_modes;
+            }
+            const ModeOut mo{a.tw_cos, a.tw_sin, mout, a.n_modes};
+            const FieldTotals t = block_field<R, THREADS>(rho1, sm.E_s, sm.D_s, sm.red, a.mc, none,
+                                                          (last && lead) ? n_out : nullptr, (last && lead) ? E_out : nullptr,
+                                                          0.0, 0.0, [&] { clear(hist0); }, mo, a.err);
+            write_diag(t, s2, s1, step, input_e);
+        }
+    }
+    for (int i = tid; i < N; i += THREADS) { xe[i] = x_s[i]; ve[i] = v_s[i]; }
+    if (err) atomicOr(a.err, err);
+    cluster_sync_all();                      // no CTA leaves while a peer may still be reading its shared memory
+}
+
 // ------------------------------------------------------------- small helpers
 template <typename T, typename U>
 __global__ void convert_kernel(const T* __restrict__ in, U* __restrict__ out, long long n) {

@@ -63,3 +63,15 @@ def test_external_field_enters_linearly_in_the_first_kick():
     d1, d2 = out[1] - out[0], out[2] - out[0]
     assert np.abs(d1).max() > 1e-6                            # the control did something
     assert np.abs(d2 - 2 * d1).max() < 1e-6 * np.abs(d1).max()
+
+
+def test_bench_parity_side_check_constant():
+    """bench.py prints `config.parity` at every GPU count: a fixed 5-step run (4e6 particles, device sampler with a
+    sharding-independent Philox counter) whose fixed-point state density is hashed.  The integer density makes the
+    hash independent of the number of GPUs; this pins the value the 1/2/4/8-GPU bench lines must all carry."""
+    import bench
+    p = bench.parity_side_check(0, 1, 0)
+    assert p["fixed_bits"] == 49
+    assert p["rho_crc"] == "4748b7b8c1adb0c1", p
+    assert p["pe_mesh"] == "0.0007774569269651889", p
+    assert abs(float(p["sum_v"]) - 2.0018312970e+06) < 1e-3
