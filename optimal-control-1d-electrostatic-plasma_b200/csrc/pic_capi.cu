@@ -190,8 +190,8 @@ int configure_launch(pic_handle* h) {
     h->grid_x = (int)want;
     if (h->partial) { cudaFree(h->partial); h->partial = nullptr; }
     CK(h, cudaMalloc(&h->partial, sizeof(double) * 2 * (size_t)h->grid_x * h->n_envs));
-    const void* kf = (const void*)&field_finalize_kernel<256>;
-    CK(h, cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_plan_bytes<double>(h->M, 256, false)));
+    const void* kf = (const void*)&field_finalize_kernel<1024>;
+    CK(h, cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_plan_bytes<double>(h->M, 1024, false)));
     return PIC_OK;
 }
 
@@ -342,8 +342,8 @@ int run_stage(pic_handle* h, int stage, const double* ext, const double* coeffs,
         const bool nccl_sharded = h->world > 1 && !h->fused;
         f.rho_reduced = h->rho[3]; f.err = h->err; f.trace_row = nccl_sharded ? nullptr : trace_row;
         void* args[] = {&f};
-        CK(h, cudaLaunchKernel((const void*)&field_finalize_kernel<256>, dim3(h->n_envs), dim3(256), args,
-                               smem_plan_bytes<double>(h->M, 256, false), h->stream));
+        CK(h, cudaLaunchKernel((const void*)&field_finalize_kernel<1024>, dim3(h->n_envs), dim3(1024), args,
+                               smem_plan_bytes<double>(h->M, 1024, false), h->stream));
         h->launches++;
         if (nccl_sharded) {
             int r = nccl_api().allreduce(h->vsum, h->vsum, 2 * (size_t)h->n_envs, kNcclFloat64, kNcclSum, h->comm, h->stream);
@@ -548,8 +548,15 @@ int pic_create(const pic_config* cfg, pic_handle** out) {
     // resident = the whole env (particles + mesh tables) fits the shared memory of one CTA
     const size_t res512 = h->f32 ? resident_smem_bytes<float>(h->M, 512, h->N, h->ip) : resident_smem_bytes<double>(h->M, 512, h->N, h->ip);
     const size_t res1024 = h->f32 ? resident_smem_bytes<float>(h->M, 1024, h->N, h->ip) : resident_smem_bytes<double>(h->M, 1024, h->N, h->ip);
-    if (mode == PIC_MODE_AUTO) mode = (long long)res1024 <= (long long)h->max_smem ? PIC_MODE_RESIDENT : PIC_MODE_STREAMING;
+    // resident = the whole env (particles + mesh tables) fits the shared memory of one CTA; its field solve is the
+    // small-mesh instance (block_field), so N_mesh <= 1024
+    if (mode == PIC_MODE_AUTO)
+        mode = ((long long)res1024 <= (long long)h->max_smem && h->M <= FIELD_SMALL_MESH) ? PIC_MODE_RESIDENT : PIC_MODE_STREAMING;
     h->resident = mode == PIC_MODE_RESIDENT;
+    if (h->resident && h->M > FIELD_SMALL_MESH) {
+        delete h;
+        return fail(nullptr, PIC_EUNSUPPORTED, "resident mode needs n_mesh <= " + std::to_string(FIELD_SMALL_MESH) + " (use streaming mode)");
+    }
 
     int k = cfg->fixed_bits;
     if (k <= 0) {                                         // headroom: 8x the mean per-cell weight sum below 2^62
@@ -564,6 +571,8 @@ int pic_create(const pic_config* cfg, pic_handle** out) {
     mc.fix_scale = ldexp(1.0, k); mc.inv_fix = ldexp(1.0, -k); mc.fix_one = 1LL << k;
     mc.idx_thr = (double)h->M * (h->f32 ? ldexp(1.0, -20) : ldexp(1.0, -49));
     mc.range_floor = h->ip == IP_TSC ? -(1LL << 61) : -(mc.fix_one << 2);
+    mc.field_g = (h->M + 32 * FIELD_VWARPS - 1) / (32 * FIELD_VWARPS);
+    mc.field_nvw = ((h->M + mc.field_g - 1) / mc.field_g + 31) / 32;
 
     if (h->resident) {
         // CTAs per env: one if the env fits one CTA's shared memory, else the smallest thread-block cluster that holds it

@@ -163,6 +163,7 @@ struct MeshConst {
     long long fix_one;     // 2^k as an integer: what one particle deposits in total
     double idx_thr;        // |q - rint(q)| below this => redo the cell index with IEEE division
     double dt;
+    int field_g, field_nvw; // field solve: cells per chunk (virtual lane) = ceil(N_mesh / 1024), virtual warps in use
     long long range_floor; // a cell sum below this has wrapped past 2^63 (ERR_DENSITY_RANGE).  CIC sums are never
                            // negative: -4 * 2^k; TSC's middle weight goes down to -0.25 per particle, so a clumped cell
                            // is legitimately negative: -2^61, far below anything the 8x headroom rule admits
@@ -442,15 +443,21 @@ struct ExtSrc {
 // which is the reference's Thomas/Sherman-Morrison solve of laplacian @ phi = b followed by -grad @ phi
 // (src/env/util.py:99-100) without forming phi.
 //
-// Block-cooperative with TWO block barriers (A after the per-thread prefix sums, C before the result is used).
-// The first FIELD_THREADS (<= 256) threads own contiguous runs of cells; each warp publishes two numbers -- its sum
-// of b and its share of sum_j S_j = sum_i b_i (M - i), a weighted sum that does not depend on the scan, so its
-// shuffles overlap the scan's -- from which every field thread derives its own offset, the grand total and
-// sum_j S_j without further communication (S_{j-1} of a thread's first cell is its exclusive offset, so D_{j-1}
-// never comes from a neighbour).  The other threads meanwhile run `idle_work` (the
-// resident kernel clears the histogram there).  Every thread must call this.
+// Block-cooperative with TWO block barriers (A after the chunk prefix sums, C before the result is used).  Two
+// instances, picked by the size of the MESH (see block_field below):
 //
-//   rho      : M fixed-point cell sums (functor; global or shared memory)
+// Large meshes (block_field_body).  The floating-point sums are organised over VIRTUAL lanes, not over the threads that
+// happen to run them, so that every launch shape produces the same bits: the mesh is cut into 1024 chunks of
+// g = ceil(N_mesh / 1024) consecutive cells (four at 4096); 32 consecutive chunks form a virtual warp.  Within a chunk
+// the cells are added left to right, within a virtual warp the chunk sums are scanned with the shuffle tree, across
+// virtual warps the totals are added in order.  A field warp of the CTA takes the virtual warps w, w + NWF, ... one
+// after the other: with 1024 threads every lane owns one chunk, with 256 four.
+// Each virtual warp publishes two numbers -- its sum of b and its share of sum_j S_j = sum_i b_i (M - i), a weighted
+// sum that does not depend on the scan -- from which every field thread derives its offsets, the grand total and
+// sum_j S_j without further communication (S_{j-1} of a chunk's first cell is its exclusive offset, so D_{j-1} never
+// comes from a neighbour).  Every thread must call this.
+//
+//   rho      : M fixed-point cell sums (functor; global, shared or distributed shared memory)
 //   E_s      : shared, M pairs (E_j + ext_j, E_{j+1 mod M} + ext_{j+1 mod M}) for the gather
 //   D_s      : shared scratch, M doubles;  red: shared scratch, field_scratch_doubles(THREADS) doubles
 //   ext      : external field source added to what particles see (util.py:102-103)
@@ -461,13 +468,16 @@ struct ExtSrc {
 // only needed for the next kick): the three block sums and their shuffles are skipped, the result is zeros.
 struct FieldTotals { double e2, s1, s2; };
 
+constexpr int FIELD_VWARPS = 32;                                  // virtual warps (1024 virtual lanes) at most
 template <int THREADS> struct FieldShape {
-    static constexpr int FT = THREADS < 256 ? THREADS : 256;     // field threads
+    static constexpr int FT = THREADS < 256 ? THREADS : 256;     // default number of field threads
     static constexpr int NWF = FT / 32, NW = THREADS / 32;
 };
-template <int THREADS>
-__host__ __device__ constexpr int field_scratch_doubles_t() { return (3 + 2 * MAX_MODES) * FieldShape<THREADS>::NWF + 3 * FieldShape<THREADS>::NW; }
-__host__ __device__ constexpr int field_scratch_doubles(int threads) { return (3 + 2 * MAX_MODES) * ((threads < 256 ? threads : 256) / 32) + 3 * (threads / 32); }
+// scratch: [3 x FIELD_VWARPS] scan triples | [FIELD_VWARPS] sum E^2 per virtual warp | [2 x NW] kinetic partials |
+//          [2 MAX_MODES x NW] mode partials
+__host__ __device__ constexpr int field_scratch_doubles(int threads) {
+    return 4 * FIELD_VWARPS + (2 + 2 * MAX_MODES) * (threads / 32);
+}
 
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
@@ -475,12 +485,154 @@ __device__ __forceinline__ double warp_sum(double v) {
     return v;
 }
 
-template <typename R, int THREADS, bool TOTALS = true, typename RhoLoad, typename IdleWork>
-__device__ __forceinline__ FieldTotals block_field(RhoLoad rho, typename PairT<R>::type* E_s, double* D_s, double* red,
-                                                   const MeshConst& mc, const ExtSrc& ext, double* __restrict__ n_out,
-                                                   double* __restrict__ E_out, double x1, double x2,
-                                                   IdleWork idle_work, const ModeOut modes = ModeOut{nullptr, nullptr, nullptr, 0},
-                                                   unsigned* range_err = nullptr) {
+// FT_: number of field threads (a multiple of 32, >= 32).  The resident kernels keep the default (<= 256); the
+// streaming prologue and the finalize kernel have nothing else to do and use every thread: at N_mesh = 4096 a lane's
+// chain of loads, int64 -> double conversions and dependent adds is then 4 cells long instead of 16, which was most of
+// the fixed cost of a pass (12 of 20 us).
+template <typename R, int THREADS, bool TOTALS, int FT_, int ROUNDS, typename RhoLoad, typename IdleWork>
+__device__ __forceinline__ FieldTotals block_field_body(RhoLoad rho, typename PairT<R>::type* E_s, double* D_s, double* red,
+                                                        const MeshConst& mc, const ExtSrc& ext, double* __restrict__ n_out,
+                                                        double* __restrict__ E_out, double x1, double x2,
+                                                        IdleWork idle_work, const ModeOut modes, unsigned* range_err) {
+    constexpr int FT = FT_, NWF = FT_ / 32, NW = FieldShape<THREADS>::NW;   // ROUNDS: virtual warps per field warp, at most
+    const int M = mc.M, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const bool field_thread = tid < FT;
+    const int g = mc.field_g, nvw = mc.field_nvw;                     // cells per chunk (virtual lane), virtual warps in use
+    double* red_e2 = red + 3 * FIELD_VWARPS;                          // [FIELD_VWARPS]
+    double* red_kin = red_e2 + FIELD_VWARPS;                          // [NW][2]
+    double* red_mode = red_kin + 2 * NW;                              // [NW][2 * MAX_MODES]
+    const bool has_ext = ext.any();
+    const bool want_modes = modes.out != nullptr;
+
+    double excl[ROUNDS];
+    if (field_thread) {
+        bool wrapped = false;
+#pragma unroll
+        for (int r = 0; r < ROUNDS; ++r) {
+            const int vw = w + r * NWF;                               // warp-uniform
+            excl[r] = 0.0;
+            if (vw < nvw) {
+                const int j0 = (vw * 32 + lane) * g, j1 = min(M, j0 + g);
+                double run = 0.0, ws = 0.0;
+                for (int j = j0; j < j1; ++j) {
+                    const long long rj = (long long)rho(j);
+                    wrapped |= rj < mc.range_floor;                   // wrapped past 2^63
+                    // rn intrinsics / explicit fma throughout: this function is inlined into every kernel flavour, and
+                    // ptxas must not be free to contract a multiply-add in one of them and not in another
+                    const double nj = __dmul_rn(__dmul_rn((double)rj, mc.inv_fix), mc.scale);
+                    if (n_out) n_out[j] = nj;
+                    const double b = __dsub_rn(nj, mc.n0);
+                    run = __dadd_rn(run, b);
+                    D_s[j] = run;                                     // inclusive prefix inside the chunk
+                    ws = __fma_rn(b, (double)(M - j), ws);            // b_j enters S_j, S_{j+1}, ..., S_{M-1}
+                }
+                double inc = run;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    double t = __shfl_up_sync(0xffffffffu, inc, o);
+                    if (lane >= o) inc = __dadd_rn(inc, t);
+                }
+                excl[r] = __dsub_rn(inc, run);
+                const double a = warp_sum(ws);
+                const double wt = __shfl_sync(0xffffffffu, inc, 31);
+                if (lane == 0) { red[3 * vw] = wt; red[3 * vw + 1] = a; }
+            }
+        }
+        if (range_err && wrapped) atomicOr(range_err, ERR_DENSITY_RANGE);
+    }
+    __syncthreads();                                   // (A) triples published; all reads of rho are done
+
+    double kin1 = x1, kin2 = x2;
+    if (field_thread) {
+        double total = 0.0, sumS = 0.0, myoff[ROUNDS];
+#pragma unroll
+        for (int r = 0; r < ROUNDS; ++r) myoff[r] = 0.0;
+        for (int k = 0; k < nvw; ++k) {
+#pragma unroll
+            for (int r = 0; r < ROUNDS; ++r) if (k == w + r * NWF) myoff[r] = total;
+            sumS = __dadd_rn(sumS, red[3 * k + 1]);
+            total = __dadd_rn(total, red[3 * k]);
+        }
+        const double meanS = sumS / (double)M;
+        const double dx2 = mc.dx2, inv2dx = mc.inv2dx;
+#pragma unroll
+        for (int r = 0; r < ROUNDS; ++r) {
+            const int vw = w + r * NWF;
+            if (vw < nvw) {
+                const int j0 = (vw * 32 + lane) * g, j1 = min(M, j0 + g);
+                const double off = __dadd_rn(myoff[r], excl[r]);
+                double prevS = j0 == 0 ? total : off;  // S_{j0-1}; periodic: S_{-1} = S_{M-1} = total
+                double e2 = 0.0;
+                for (int j = j0; j < j1; ++j) {
+                    const int jm = j == 0 ? M - 1 : j - 1;
+                    const double S = __dadd_rn(D_s[j], off);
+                    const double E = __dmul_rn(-__dadd_rn(__dmul_rn(dx2, __dsub_rn(S, meanS)), __dmul_rn(dx2, __dsub_rn(prevS, meanS))), inv2dx);
+                    prevS = S;
+                    if (E_out) E_out[j] = E;
+                    if (TOTALS) e2 = __fma_rn(E, E, e2);
+                    if (want_modes) D_s[j] = E;         // S_j is dead from here on; keep E_j for the read-out below
+                    const double Et = has_ext ? __dadd_rn(E, ext.at(j)) : E;
+                    E_s[j].x = (R)Et;
+                    E_s[jm].y = (R)Et;
+                }
+                if (TOTALS) {                           // sum E^2 per VIRTUAL warp: the same tree in every flavour
+                    e2 = warp_sum(e2);
+                    if (lane == 0) red_e2[vw] = e2;
+                }
+            }
+        }
+        if (want_modes) {                               // cold: one mode at a time keeps the register footprint small
+            for (int k = 0; k < modes.m; ++k) {
+                double re = 0.0, im = 0.0;
+                for (int r = 0; r < ROUNDS; ++r) {
+                    const int vw = w + r * NWF;
+                    if (vw < nvw) {
+                        const int j0 = (vw * 32 + lane) * g, j1 = min(M, j0 + g);
+                        for (int j = j0; j < j1; ++j) {
+                            re = __fma_rn(D_s[j], modes.tw_cos[j * modes.m + k], re);
+                            im = __fma_rn(-D_s[j], modes.tw_sin[j * modes.m + k], im);
+                        }
+                    }
+                }
+                re = warp_sum(re); im = warp_sum(im);
+                if (lane == 0) { red_mode[w * 2 * MAX_MODES + k] = re; red_mode[w * 2 * MAX_MODES + MAX_MODES + k] = im; }
+            }
+        }
+    } else {
+        idle_work();
+    }
+    if (FT == THREADS) idle_work();                    // no spare threads: everyone does it after its share
+    if (TOTALS) {
+        kin1 = warp_sum(kin1); kin2 = warp_sum(kin2);
+        if (lane == 0) { red_kin[2 * w] = kin1; red_kin[2 * w + 1] = kin2; }
+    }
+    __syncthreads();                                   // (C) gather table, idle work and partial sums complete
+
+    FieldTotals t{0.0, 0.0, 0.0};
+    if (TOTALS && w == 0) {
+        t.e2 = warp_sum(lane < nvw ? red_e2[lane] : 0.0);
+        t.s1 = warp_sum(lane < NW ? red_kin[2 * lane] : 0.0);
+        t.s2 = warp_sum(lane < NW ? red_kin[2 * lane + 1] : 0.0);
+        if (want_modes && lane < 2 * modes.m) {         // lane < m: Re_{lane+1}; m <= lane < 2m: Im_{lane-m+1}
+            const int k = lane < modes.m ? lane : lane - modes.m;
+            const int slot = lane < modes.m ? k : MAX_MODES + k;
+            double acc = 0.0;
+#pragma unroll
+            for (int ww = 0; ww < NWF; ++ww) acc += red_mode[ww * 2 * MAX_MODES + slot];
+            modes.out[lane] = acc / (double)M * 2.0;
+        }
+    }
+    return t;
+}
+
+// Small meshes (N_mesh <= FIELD_SMALL_MESH): 256 field threads own contiguous runs of ceil(N_mesh / 256) <= 4 cells.
+// Same structure as the large-mesh body with the chunk = one thread's run and ONE virtual warp per field warp, written
+// out straight-line: this is what the resident kernels run four times per env step (a third of their time).
+template <typename R, int THREADS, bool TOTALS, typename RhoLoad, typename IdleWork>
+__device__ __forceinline__ FieldTotals block_field_small(RhoLoad rho, typename PairT<R>::type* E_s, double* D_s, double* red,
+                                                         const MeshConst& mc, const ExtSrc& ext, double* __restrict__ n_out,
+                                                         double* __restrict__ E_out, double x1, double x2,
+                                                         IdleWork idle_work, const ModeOut modes, unsigned* range_err) {
     constexpr int FT = FieldShape<THREADS>::FT, NWF = FieldShape<THREADS>::NWF, NW = FieldShape<THREADS>::NW;
     const int M = mc.M, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const bool field_thread = tid < FT;
@@ -491,6 +643,9 @@ __device__ __forceinline__ FieldTotals block_field(RhoLoad rho, typename PairT<R
     const bool has_ext = ext.any();
     const bool want_modes = modes.out != nullptr;
 
+    // rn intrinsics / explicit fma on everything that reaches E: this function is inlined into every kernel flavour, and
+    // ptxas must not be free to contract a multiply-add in one of them and not in another (the flavours promise
+    // identical bits)
     double run = 0.0, excl = 0.0, ext0 = 0.0;
     if (field_thread) {
         if (has_ext && j0 < j1) ext0 = ext.at(j0);     // global loads: in flight across the scan and barrier (A)
@@ -498,20 +653,20 @@ __device__ __forceinline__ FieldTotals block_field(RhoLoad rho, typename PairT<R
         for (int j = j0; j < j1; ++j) {
             const long long rj = (long long)rho(j);
             if (range_err && rj < mc.range_floor) atomicOr(range_err, ERR_DENSITY_RANGE);   // wrapped past 2^63
-            double nj = (double)rj * mc.inv_fix * mc.scale;
+            const double nj = __dmul_rn(__dmul_rn((double)rj, mc.inv_fix), mc.scale);
             if (n_out) n_out[j] = nj;
-            const double b = nj - mc.n0;
-            run += b;
+            const double b = __dsub_rn(nj, mc.n0);
+            run = __dadd_rn(run, b);
             D_s[j] = run;                              // inclusive prefix inside this thread's run of cells
-            ws += b * (double)(M - j);                 // b_j enters S_j, S_{j+1}, ..., S_{M-1}
+            ws = __fma_rn(b, (double)(M - j), ws);     // b_j enters S_j, S_{j+1}, ..., S_{M-1}
         }
         double inc = run;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             double t = __shfl_up_sync(0xffffffffu, inc, o);
-            if (lane >= o) inc += t;
+            if (lane >= o) inc = __dadd_rn(inc, t);
         }
-        excl = inc - run;
+        excl = __dsub_rn(inc, run);
         const double a = warp_sum(ws);
         const double wt = __shfl_sync(0xffffffffu, inc, 31);
         if (lane == 0) { red[3 * w] = wt; red[3 * w + 1] = a; }
@@ -524,22 +679,22 @@ __device__ __forceinline__ FieldTotals block_field(RhoLoad rho, typename PairT<R
 #pragma unroll
         for (int k = 0; k < NWF; ++k) {
             if (k == w) myoff = total;
-            sumS += red[3 * k + 1];
-            total += red[3 * k];
+            sumS = __dadd_rn(sumS, red[3 * k + 1]);
+            total = __dadd_rn(total, red[3 * k]);
         }
         const double meanS = sumS / (double)M;
-        const double off = myoff + excl;
+        const double off = __dadd_rn(myoff, excl);
         const double dx2 = mc.dx2, inv2dx = mc.inv2dx;
         double prevS = j0 == 0 ? total : off;          // S_{j0-1}; periodic: S_{-1} = S_{M-1} = total
         for (int j = j0; j < j1; ++j) {
             const int jm = j == 0 ? M - 1 : j - 1;
-            const double S = D_s[j] + off;
-            const double E = -(dx2 * (S - meanS) + dx2 * (prevS - meanS)) * inv2dx;
+            const double S = __dadd_rn(D_s[j], off);
+            const double E = __dmul_rn(-__dadd_rn(__dmul_rn(dx2, __dsub_rn(S, meanS)), __dmul_rn(dx2, __dsub_rn(prevS, meanS))), inv2dx);
             prevS = S;
             if (E_out) E_out[j] = E;
-            if (TOTALS) e2 += E * E;
+            if (TOTALS) e2 = __fma_rn(E, E, e2);
             if (want_modes) D_s[j] = E;                 // S_j is dead from here on; keep E_j for the read-out below
-            const double Et = has_ext ? E + (j == j0 ? ext0 : ext.at(j)) : E;
+            const double Et = has_ext ? __dadd_rn(E, j == j0 ? ext0 : ext.at(j)) : E;
             E_s[j].x = (R)Et;
             E_s[jm].y = (R)Et;
         }
@@ -547,8 +702,8 @@ __device__ __forceinline__ FieldTotals block_field(RhoLoad rho, typename PairT<R
             for (int k = 0; k < modes.m; ++k) {
                 double re = 0.0, im = 0.0;
                 for (int j = j0; j < j1; ++j) {
-                    re += D_s[j] * modes.tw_cos[j * modes.m + k];
-                    im -= D_s[j] * modes.tw_sin[j * modes.m + k];
+                    re = __fma_rn(D_s[j], modes.tw_cos[j * modes.m + k], re);
+                    im = __fma_rn(-D_s[j], modes.tw_sin[j * modes.m + k], im);
                 }
                 re = warp_sum(re); im = warp_sum(im);
                 if (lane == 0) { red3[w * 2 * MAX_MODES + k] = re; red3[w * 2 * MAX_MODES + MAX_MODES + k] = im; }
@@ -579,6 +734,27 @@ __device__ __forceinline__ FieldTotals block_field(RhoLoad rho, typename PairT<R
         }
     }
     return t;
+}
+
+// The field solve.  LARGE_OK = false (resident and cluster kernels: N_mesh <= FIELD_SMALL_MESH is a precondition that
+// pic_create enforces) compiles the small-mesh instance only; the streaming prologue and the finalize kernel take any
+// mesh and pick by size (CTA-uniform branch).  Both instances order their sums by the MESH, never by the launch shape:
+// 256 runs of <= 4 cells up to 1024 cells, 1024 chunks of ceil(N_mesh / 1024) cells above -- so every kernel flavour,
+// thread count and GPU count builds the identical field from the identical integer density.
+constexpr int FIELD_SMALL_MESH = 1024;
+template <typename R, int THREADS, bool TOTALS = true, bool LARGE_OK = false, typename RhoLoad, typename IdleWork>
+__device__ __forceinline__ FieldTotals block_field(RhoLoad rho, typename PairT<R>::type* E_s, double* D_s, double* red,
+                                                   const MeshConst& mc, const ExtSrc& ext, double* __restrict__ n_out,
+                                                   double* __restrict__ E_out, double x1, double x2,
+                                                   IdleWork idle_work, const ModeOut modes = ModeOut{nullptr, nullptr, nullptr, 0},
+                                                   unsigned* range_err = nullptr) {
+    if constexpr (LARGE_OK) {
+        constexpr int ROUNDS = (FIELD_VWARPS + THREADS / 32 - 1) / (THREADS / 32);
+        if (mc.M > FIELD_SMALL_MESH)
+            return block_field_body<R, THREADS, TOTALS, THREADS, ROUNDS>(rho, E_s, D_s, red, mc, ext, n_out, E_out, x1, x2,
+                                                                        idle_work, modes, range_err);
+    }
+    return block_field_small<R, THREADS, TOTALS>(rho, E_s, D_s, red, mc, ext, n_out, E_out, x1, x2, idle_work, modes, range_err);
 }
 
 // ------------------------------------------------------------------- push step

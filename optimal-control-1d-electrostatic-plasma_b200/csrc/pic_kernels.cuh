@@ -226,10 +226,10 @@ __global__ void __launch_bounds__(THREADS) push_stream_kernel(const StreamArgs a
         if (fused) {
             dead = comm_wait(a.comm, a.comm.seq_in, a.err);
             PeerSumRho rho{comm_in_slots(a.comm, a.comm.seq_in), a.comm.slot_len, a.comm.world};
-            block_field<R, THREADS, false>(rho, sm.E_s, sm.D_s, sm.red, a.mc, ext, nullptr, nullptr, 0.0, 0.0, [] {});
+            block_field<R, THREADS, false, true>(rho, sm.E_s, sm.D_s, sm.red, a.mc, ext, nullptr, nullptr, 0.0, 0.0, [] {});
         } else {
             GlobalRho rho{a.rho_in + (size_t)env * M};
-            block_field<R, THREADS, false>(rho, sm.E_s, sm.D_s, sm.red, a.mc, ext, nullptr, nullptr, 0.0, 0.0, [] {});
+            block_field<R, THREADS, false, true>(rho, sm.E_s, sm.D_s, sm.red, a.mc, ext, nullptr, nullptr, 0.0, 0.0, [] {});
         }
     }
     hist.zero(tid, THREADS);
@@ -454,14 +454,14 @@ __global__ void __launch_bounds__(THREADS) field_finalize_kernel(const FinalizeA
             }
         }
         for (int j = tid; j < M; j += THREADS) a.rho_reduced[j] = rho(j);
-        t = block_field<double, THREADS>(rho, sm.E_s, sm.D_s, sm.red, a.mc, none, a.n_out, a.E_out, s2, s1, [] {}, mo, a.err);
+        t = block_field<double, THREADS, true, true>(rho, sm.E_s, sm.D_s, sm.red, a.mc, none, a.n_out, a.E_out, s2, s1, [] {}, mo, a.err);
     } else {
         GlobalRho rho{a.rho + (size_t)env * M};
         if (a.partial) {
             const double* p = a.partial + (size_t)env * a.n_partial * 2;
             for (int i = tid; i < a.n_partial; i += THREADS) { s2 += p[2 * i]; s1 += p[2 * i + 1]; }
         }
-        t = block_field<double, THREADS>(rho, sm.E_s, sm.D_s, sm.red, a.mc, none,
+        t = block_field<double, THREADS, true, true>(rho, sm.E_s, sm.D_s, sm.red, a.mc, none,
                                          a.n_out + (size_t)env * M, a.E_out + (size_t)env * M, s2, s1, [] {}, mo, a.err);
     }
     if (a.rho_zero) for (int j = tid; j < M; j += THREADS) a.rho_zero[(size_t)env * M + j] = 0ull;

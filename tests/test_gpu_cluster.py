@@ -58,7 +58,7 @@ def test_cluster_env_is_bit_identical_to_one_cta_env(shape):
 @pytest.mark.parametrize("N,M", [(4999, 250), (3, 5), (257, 31)])
 def test_cluster_ragged_sizes(N, M):
     B, steps = 3, 3
-    m = 3 if M > 6 else 2                                      # spectral read-out needs n_modes < N_mesh / 2
+    m = 3 if M > 6 else 1                                      # spectral read-out needs n_modes < N_mesh // 2
     rng = np.random.RandomState(N)
     x = rng.uniform(0, 50.0, (B, N)); v = rng.normal(size=(B, N))
     coeffs = rng.uniform(-1, 1, (steps, B, 2 * m))

@@ -446,8 +446,13 @@ def test_error_behaviour():
         Engine(1000, 16, 10.0, 0.1, precision="f32", interpol="TSC")
     assert e.value.code == -8
     with pytest.raises(PicError) as e:
-        Engine(50_000, 16, 10.0, 0.1, mode="resident")            # does not fit one CTA's shared memory
+        Engine(5_000_000, 16, 10.0, 0.01, mode="resident")        # does not fit the shared memory of even an 8-CTA cluster
     assert e.value.code == -8
+    with pytest.raises(PicError) as e:
+        Engine(1000, 2048, 10.0, 0.1, mode="resident")            # resident field solve is the small-mesh instance
+    assert e.value.code == -8 and "n_mesh" in str(e.value)
+    big = Engine(50_000, 16, 10.0, 0.1, mode="resident")          # one CTA is too small: spread over a cluster
+    assert big.launch_info()["per_thread"] == 4
     with pytest.raises(PicError) as e:
         Engine(100_000, 20000, 10.0, 0.1, mode="streaming")       # mesh tables exceed shared memory
     assert e.value.code == -8 and "n_mesh too large" in str(e.value)
