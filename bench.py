@@ -529,42 +529,61 @@ def run_gpu_arm(args):
     # ---- batched-env companion number (BASELINE configs[3]); env-sharded, no communication
     batched = None
     if not args.no_batched:
-        def run_batched(B_total, lo, hi, T=10, breps=60):
-            bp = pic_b200.Engine(5000, 250, L_BOX, 0.05, n_envs=hi - lo, mode="resident", deposit="split32", max_mode=3,
-                                 device=local)
+        def run_batched(B_total, lo, hi, T=10, breps=60, groups=2):
+            # the rank's envs as `groups` handles on their own streams (what BatchedPIC does): the launches of one group
+            # fill the CTA slots the other group's last wave leaves empty
+            G = max(1, min(groups, hi - lo))
             act = pic_b200.E_field(L_BOX, 250, 3)
-            bp.set_actuator_basis(act.basis_cos, act.basis_sin)
-            bp.sample_state("bump-on-tail", seed=7, n_global=5000, env_offset=lo)
-            coeffs = torch.rand(T, hi - lo, 6, dtype=torch.float64, device=dev) * 2 - 1
+            engs, coeffs, streams = [], [], []
+            for g in range(G):
+                glo, ghi = pic_b200.shard_range(hi - lo, g, G)
+                bp = pic_b200.Engine(5000, 250, L_BOX, 0.05, n_envs=ghi - glo, mode="resident", deposit="split32", max_mode=3,
+                                     device=local, stream="own" if G > 1 else None)
+                bp.set_actuator_basis(act.basis_cos, act.basis_sin)
+                bp.sample_state("bump-on-tail", seed=7, n_global=5000, env_offset=lo + glo)
+                engs.append(bp)
+                coeffs.append(torch.rand(T, ghi - glo, 6, dtype=torch.float64, device=dev) * 2 - 1)
+                streams.append(torch.cuda.ExternalStream(bp.stream_ptr(), device=dev) if G > 1 else torch.cuda.current_stream())
+            torch.cuda.synchronize()
             for _ in range(10):
-                bp.step_coeffs_device(coeffs.data_ptr(), T)
+                for bp, c in zip(engs, coeffs):
+                    bp.step_coeffs_device(c.data_ptr(), T)
             barrier()
-            b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            b0 = torch.cuda.Event(enable_timing=True)
+            ends = [torch.cuda.Event(enable_timing=True) for _ in range(G)]
             with ClockSampler(local) as bclk:
-                b0.record()
+                b0.record(streams[0])                           # every stream is idle here (barrier above)
                 for _ in range(breps):                          # 600 env steps per env: long enough for sustained clocks
-                    bp.step_coeffs_device(coeffs.data_ptr(), T)
-                b1.record()
+                    for bp, c in zip(engs, coeffs):
+                        bp.step_coeffs_device(c.data_ptr(), T)
+                for e, st in zip(ends, streams):
+                    e.record(st)
                 barrier()
-            bms = max_over_ranks(b0.elapsed_time(b1)) / (breps * T)
+            bms = max_over_ranks(max(b0.elapsed_time(e) for e in ends)) / (breps * T)
             out = {"env_steps_per_s": B_total / (bms * 1e-3), "particle_steps_per_s": B_total * 5000 / (bms * 1e-3),
-                   "ms_per_batched_step": bms, "envs_per_gpu": hi - lo, "launch": bp.launch_info(), "clocks": bclk.summary(),
-                   "error_flags": int(bp.error_flags())}
-            bp.close()
+                   "ms_per_batched_step": bms, "envs_per_gpu": hi - lo, "groups": G, "launch": engs[0].launch_info(),
+                   "clocks": bclk.summary(), "error_flags": int(max(bp.error_flags() for bp in engs))}
+            for bp in engs:
+                bp.close()
             return out
 
         B = 4096
         lo, hi = pic_b200.shard_range(B, rank, world)
         strong = run_batched(B, lo, hi)
+        one_group = run_batched(B, lo, hi, groups=1)
         weak = run_batched(B * world, B * rank, B * (rank + 1)) if world > 1 else strong
         batched = {"workload": "4096 envs x (N=5000, N_mesh=250, dt=0.05, 6 actuator coefficients per env per step), "
                                "env-sharded over the GPUs (strong scaling: 4096 envs in total)",
                    **strong,
                    "hbm_frac": (32.0 * 5000 * (hi - lo) / (strong["ms_per_batched_step"] * 1e-3) / 1e9) / hbm_peak,
+                   "single_group": {"env_steps_per_s": one_group["env_steps_per_s"],
+                                    "ms_per_batched_step": one_group["ms_per_batched_step"],
+                                    "note": "the same envs as ONE launch per call: the last wave of 2 x 148 CTA slots "
+                                            "is partly empty unless envs-per-GPU is a multiple of 296"},
                    "weak": {"workload": "4096 envs PER GPU (%d in total)" % (B * world),
                             "env_steps_per_s": weak["env_steps_per_s"], "ms_per_batched_step": weak["ms_per_batched_step"]},
-                   "note": "one CTA (or CTA pair) per env, particle state in shared memory; bound by instruction issue / "
-                           "shared atomics (and the SM clock), not HBM"}
+                   "note": "one CTA per env, particle state in shared memory, two env groups on two streams; bound by "
+                           "instruction issue / shared atomics (and the SM clock), not HBM"}
         if rank == 0 and world == 1 and not args.no_cpu:
             # the reference has no batching -> one reference env per process
             procs = host_procs(5000, 250)

@@ -46,6 +46,7 @@ enum { PIC_DIAG_KE = 0,        /* 0.5*sum(v^2)            src/env/util.py:144   
        PIC_DIAG_N = 6 };
 
 typedef struct pic_handle pic_handle;
+#define PIC_STREAM_OWN ((void*)(intptr_t)-1)
 
 /* Mirrors the keyword set of PIC.__init__ (src/env/pic.py:13-27, as passed at run_wo_oc.py:79-92) that the step
  * itself needs, plus the batching / sharding / device knobs the reference does not have. */
@@ -64,7 +65,8 @@ typedef struct pic_config {
     int32_t exact_weights;      /* 1 => CIC weights with IEEE division as interpolate.py:11-12 (slower)        */
     int32_t device;             /* CUDA device ordinal                                                         */
     int32_t max_mode;           /* actuator modes m (src/control/actuator.py:5); 0 => mesh-vector actuation only */
-    void*   stream;             /* cudaStream_t to enqueue on; NULL => the legacy default stream               */
+    void*   stream;             /* cudaStream_t to enqueue on; NULL => the legacy default stream;
+                                 * PIC_STREAM_OWN => the handle creates (and destroys) a non-blocking stream of its own */
     int32_t interpolation;      /* PIC_INTERP_CIC | PIC_INTERP_TSC (float64 + split32 deposit only)            */
 } pic_config;
 
@@ -76,6 +78,7 @@ int pic_create(const pic_config* cfg, pic_handle** out);                /* PIC._
 int pic_destroy(pic_handle* h);
 const char* pic_last_error(const pic_handle* h);
 int pic_set_stream(pic_handle* h, void* cuda_stream);
+int pic_get_stream(pic_handle* h, void** cuda_stream);     /* the stream the handle enqueues on (e.g. to record events) */
 
 /* --- state -------------------------------------------------------------------------------------------------- */
 /* PIC.initialize after sampling (pic.py:66-77): takes x, v (host float64, [n_envs][n_particles]), wraps x in

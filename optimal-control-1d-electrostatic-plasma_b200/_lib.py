@@ -52,6 +52,7 @@ SIGNATURES = {
     "pic_destroy": (C.c_int, [_H]),
     "pic_last_error": (C.c_char_p, [_H]),
     "pic_set_stream": (C.c_int, [_H, C.c_void_p]),
+    "pic_get_stream": (C.c_int, [_H, C.POINTER(C.c_void_p)]),
     "pic_set_state": (C.c_int, [_H, C.c_void_p, C.c_void_p]),
     "pic_set_state_device": (C.c_int, [_H, C.c_void_p, C.c_void_p]),
     "pic_sample_state": (C.c_int, [_H, C.c_int32, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int32,

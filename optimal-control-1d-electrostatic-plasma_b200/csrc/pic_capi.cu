@@ -64,6 +64,7 @@ struct pic_handle {
     pic_config cfg{};
     int device = 0, sm_count = 0, max_smem = 0;
     cudaStream_t stream = nullptr;
+    bool own_stream = false;                        // cfg.stream == PIC_STREAM_OWN: created (non-blocking) and destroyed here
     MeshConst mc{};
     long long N = 0, ld = 0, Ntotal = 0;
     int M = 0, n_envs = 1, esize = 8, fixed_bits = 0, dep = DEP_CAS64;
@@ -115,6 +116,11 @@ struct pic_handle {
 };
 
 namespace {
+
+void drop_handle(pic_handle* h) {                    // pic_create bailing out before any device buffer exists
+    if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
 
 int fail(pic_handle* h, int code, const std::string& msg) {
     if (h) h->last_error = msg; else g_create_error = msg;
@@ -522,7 +528,12 @@ int pic_create(const pic_config* cfg, pic_handle** out) {
     if (prop.major < 10) { delete h; return fail(nullptr, PIC_ENODEVICE, "device is not sm_100 class (built for sm_100a only)"); }
     h->sm_count = prop.multiProcessorCount;
     h->max_smem = (int)prop.sharedMemPerBlockOptin;
-    h->stream = (cudaStream_t)cfg->stream;
+    if (cfg->stream == PIC_STREAM_OWN) {
+        if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return fail(nullptr, PIC_ECUDA, "cudaStreamCreate failed"); }
+        h->own_stream = true;
+    } else {
+        h->stream = (cudaStream_t)cfg->stream;
+    }
     h->N = cfg->n_particles;
     h->Ntotal = cfg->n_particles_total > 0 ? cfg->n_particles_total : cfg->n_particles;
     h->M = cfg->n_mesh; h->n_envs = cfg->n_envs;
@@ -530,7 +541,7 @@ int pic_create(const pic_config* cfg, pic_handle** out) {
     h->exact_w = cfg->exact_weights != 0;
     h->ip = cfg->interpolation == PIC_INTERP_TSC ? IP_TSC : IP_CIC;
     if (h->ip == IP_TSC && (cfg->precision == PIC_F32 || cfg->deposit == PIC_DEPOSIT_CAS64 || h->exact_w)) {
-        delete h;
+        drop_handle(h);
         return fail(nullptr, PIC_EUNSUPPORTED, "TSC interpolation is built for float64 with the split32 deposit only");
     }
     h->m = cfg->max_mode > 0 ? cfg->max_mode : 0;
@@ -554,7 +565,7 @@ int pic_create(const pic_config* cfg, pic_handle** out) {
         mode = ((long long)res1024 <= (long long)h->max_smem && h->M <= FIELD_SMALL_MESH) ? PIC_MODE_RESIDENT : PIC_MODE_STREAMING;
     h->resident = mode == PIC_MODE_RESIDENT;
     if (h->resident && h->M > FIELD_SMALL_MESH) {
-        delete h;
+        drop_handle(h);
         return fail(nullptr, PIC_EUNSUPPORTED, "resident mode needs n_mesh <= " + std::to_string(FIELD_SMALL_MESH) + " (use streaming mode)");
     }
 
@@ -566,7 +577,7 @@ int pic_create(const pic_config* cfg, pic_handle** out) {
         if (k > 50) k = 50;
         if (k < 20) k = 20;
     }
-    if (k > 50) { delete h; return fail(nullptr, PIC_EINVAL, "fixed_bits must be <= 50"); }
+    if (k > 50) { drop_handle(h); return fail(nullptr, PIC_EINVAL, "fixed_bits must be <= 50"); }
     h->fixed_bits = k;
     mc.fix_scale = ldexp(1.0, k); mc.inv_fix = ldexp(1.0, -k); mc.fix_one = 1LL << k;
     mc.idx_thr = (double)h->M * (h->f32 ? ldexp(1.0, -20) : ldexp(1.0, -49));
@@ -580,7 +591,7 @@ int pic_create(const pic_config* cfg, pic_handle** out) {
         h->threads = 1024;
         for (h->cluster = 1; h->cluster <= 8 && (long long)smem_for(h) > (long long)h->max_smem; h->cluster *= 2) {}
         if (h->cluster > 8 || (h->cluster > 1 && (h->dep != DEP_SPLIT32 || h->exact_w))) {
-            delete h;
+            drop_handle(h);
             return fail(nullptr, PIC_EUNSUPPORTED, "n_particles too large for resident mode (env does not fit in shared memory)");
         }
         const size_t per_sm = (size_t)h->max_smem + 1024;          // every CTA reserves 1 KB on top of its request
@@ -648,6 +659,7 @@ int pic_destroy(pic_handle* h) {
                     h->ext, h->coeffs, h->bcos, h->bsin, h->trace, h->stage64, h->err, h->tw_cos, h->tw_sin, h->modes,
                     h->mode_trace, h->ph_counts, h->ph_feq, h->ph_kl, h->ticket};
     for (void* b : bufs) if (b) cudaFree(b);
+    if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
     delete h;
     return PIC_OK;
 }
@@ -655,7 +667,14 @@ int pic_destroy(pic_handle* h) {
 int pic_set_stream(pic_handle* h, void* s) {
     if (!h) return PIC_EINVAL;
     cudaStreamSynchronize(h->stream);
+    if (h->own_stream && h->stream) { cudaStreamDestroy(h->stream); h->own_stream = false; }
     h->stream = (cudaStream_t)s;
+    return PIC_OK;
+}
+
+int pic_get_stream(pic_handle* h, void** out) {
+    if (!h || !out) return PIC_EINVAL;
+    *out = (void*)h->stream;
     return PIC_OK;
 }
 

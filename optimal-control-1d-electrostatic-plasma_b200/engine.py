@@ -41,7 +41,8 @@ class Engine:
         self._h = C.c_void_p()
         cfg = L.PicConfig(int(n_particles), int(n_particles_total), int(n_mesh), int(n_envs), float(n0), float(L_box),
                           float(dt), _PREC[precision], _MODE[mode], _DEP[deposit], int(fixed_bits),
-                          int(bool(exact_weights)), int(device), int(max_mode), C.c_void_p(stream or 0),
+                          int(bool(exact_weights)), int(device), int(max_mode),
+                          C.c_void_p(-1 if stream == "own" else (stream or 0)),     # "own": PIC_STREAM_OWN
                           {"CIC": L.PIC_INTERP_CIC, "TSC": L.PIC_INTERP_TSC}[interpol])
         self.interpol = interpol
         rc = self._lib.pic_create(C.byref(cfg), C.byref(self._h))
@@ -226,6 +227,12 @@ class Engine:
 
     def sync(self):
         self._ck(self._lib.pic_sync(self._h))
+
+    def stream_ptr(self):
+        """cudaStream_t (as int) the handle enqueues on; wrap with torch.cuda.ExternalStream to record events on it."""
+        p = C.c_void_p()
+        self._ck(self._lib.pic_get_stream(self._h, C.byref(p)))
+        return int(p.value or 0)
 
     def set_stream(self, stream_ptr):
         self._ck(self._lib.pic_set_stream(self._h, C.c_void_p(stream_ptr or 0)))

@@ -100,3 +100,33 @@ def test_batched_reset_and_observe():
     out_w = whole.step(np.zeros((B, 6)), n_steps=3)
     assert out_w["reward"].shape == (3, B) and np.all(out_w["reward"] <= 2.0)
     assert np.allclose(obs["diag"][:, 1].cpu().numpy(), out_w["pe_mesh"][-1])
+
+
+def test_batched_env_groups_change_nothing_but_the_schedule():
+    """BatchedPIC splits its envs into groups on separate streams (so that one group's launches fill the CTA slots the
+    other's last wave leaves empty): every env must come out bit-identical to the single-group batch."""
+    from pic_b200 import BatchedPIC
+    B, N = 70, 2000
+    rng = np.random.RandomState(3)
+    acts = rng.uniform(-1, 1, size=(5, B, 6))
+    outs = []
+    for groups in (1, 2, 3):
+        bp = BatchedPIC(B, N=N, N_mesh=128, L=50.0, dt=0.05, max_mode=3, groups=groups)
+        assert bp.groups == groups and len(bp.engines) == groups
+        bp.enable_modes()
+        bp.reset("two-stream", seed=9)
+        r = bp.step(acts, n_steps=5)
+        r2 = bp.step(None, n_steps=2)
+        outs.append((bp.get_state(), r["pe_mesh"], r["reward"], r["modes"], r2["ke"]))
+        obs = bp.observe()
+        if groups == 1:
+            assert obs["x"].shape == (B, N) and bp.engine is bp.engines[0]
+        else:
+            assert [o["x"].shape[0] for o in obs] == [hi - lo for lo, hi in bp.group_bounds()]
+            with pytest.raises(AttributeError):
+                bp.engine
+        bp.close()
+    for o in outs[1:]:
+        for a, b in zip(outs[0], o):
+            assert np.array_equal(a, b)
+    assert BatchedPIC(64, N=100, N_mesh=16, dt=0.01).groups == 2 and BatchedPIC(63, N=100, N_mesh=16, dt=0.01).groups == 1
