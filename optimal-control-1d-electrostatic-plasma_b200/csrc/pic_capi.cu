@@ -66,6 +66,7 @@ struct pic_handle {
     cudaStream_t stream = nullptr;
     bool own_stream = false;                        // cfg.stream == PIC_STREAM_OWN: created (non-blocking) and destroyed here
     MeshConst mc{};
+    PartConsts pcs{};
     long long N = 0, ld = 0, Ntotal = 0;
     int M = 0, n_envs = 1, esize = 8, fixed_bits = 0, dep = DEP_CAS64;
     bool f32 = false, exact_w = false, resident = false;
@@ -361,7 +362,7 @@ int run_stage(pic_handle* h, int stage, const double* ext, const double* coeffs,
     }
     if (stage == 0) return PIC_OK;      // stage 0 (pure drift): deposited ahead of time by stage 3 / init, redone by stage 1
     StreamArgs a{};
-    a.mc = h->mc; a.x = h->x; a.v = h->v; a.N = h->N; a.ld = h->ld;
+    a.mc = h->mc; a.pcs = h->pcs; a.x = h->x; a.v = h->v; a.N = h->N; a.ld = h->ld;
     a.act.ext = ext; a.act.coeffs = coeffs; a.act.bcos = h->bcos; a.act.bsin = h->bsin; a.act.m = h->m;
     a.partial = h->partial; a.err = h->err; a.c_next = h->cs[0];
     const size_t sz = (size_t)h->M * h->n_envs;
@@ -418,7 +419,7 @@ int ensure_trace(pic_handle* h, int n_steps) {
 
 int launch_resident(pic_handle* h, int n_steps, const double* ext, const double* coeffs) {
     ResidentArgs a{};
-    a.mc = h->mc; a.x = h->x; a.v = h->v; a.N = h->N; a.ld = h->ld; a.n_steps = n_steps;
+    a.mc = h->mc; a.pcs = h->pcs; a.x = h->x; a.v = h->v; a.N = h->N; a.ld = h->ld; a.n_steps = n_steps;
     a.act.ext = ext; a.act.coeffs = coeffs; a.act.bcos = h->bcos; a.act.bsin = h->bsin; a.act.m = h->m;
     a.coeff_step_stride = (long long)h->n_envs * 2 * h->m; a.ext_step_stride = 0;
     for (int i = 0; i < 4; ++i) { a.c[i] = h->cs[i]; a.d[i] = h->ds[i]; }
@@ -582,6 +583,7 @@ int pic_create(const pic_config* cfg, pic_handle** out) {
     mc.fix_scale = ldexp(1.0, k); mc.inv_fix = ldexp(1.0, -k); mc.fix_one = 1LL << k;
     mc.idx_thr = (double)h->M * (h->f32 ? ldexp(1.0, -20) : ldexp(1.0, -49));
     mc.range_floor = h->ip == IP_TSC ? -(1LL << 61) : -(mc.fix_one << 2);
+    h->pcs.d = make_part_const<double>(mc); h->pcs.f = make_part_const<float>(mc);
     mc.field_g = (h->M + 32 * FIELD_VWARPS - 1) / (32 * FIELD_VWARPS);
     mc.field_nvw = ((h->M + mc.field_g - 1) / mc.field_g + 31) / 32;
 

@@ -185,6 +185,15 @@ __host__ __device__ inline PartConst<R> make_part_const(const MeshConst& m) {
     return c;
 }
 
+// Both precisions side by side, computed once on the HOST and passed inside the kernel arguments: the hot loops then
+// read these constants straight from the constant bank (fp64 instructions take a constant-bank operand) instead of
+// holding ~14 registers of loop invariants that every kernel would otherwise recompute at its start -- the streaming
+// and resident kernels live at the 64-register limit.
+struct PartConsts { PartConst<double> d; PartConst<float> f; };
+template <typename R> __device__ __forceinline__ const PartConst<R>& part_const(const PartConsts& p);
+template <> __device__ __forceinline__ const PartConst<double>& part_const<double>(const PartConsts& p) { return p.d; }
+template <> __device__ __forceinline__ const PartConst<float>& part_const<float>(const PartConsts& p) { return p.f; }
+
 // ---------------------------------------------------------------- wrap / cell
 // np.mod(np.mod(x, L), L): util.py:51 followed by interpolate.py:6 (and pic.py:139 for the state itself).
 // np.mod = fmod, then +L when the remainder is non-zero and negative.  For |x| < 2L every branch below is the

@@ -120,6 +120,7 @@ struct ActuatorArgs {
 
 struct StreamArgs {
     MeshConst mc;
+    PartConsts pcs;                    // per-particle constants of both precisions (host-computed)
     void* x;                           // [n_envs][ld] particle positions (R): read and written in place
     void* v;                           // [n_envs][ld] particle velocities (R)
     long long N, ld;
@@ -217,7 +218,11 @@ __global__ void __launch_bounds__(THREADS) push_stream_kernel(const StreamArgs a
     using H = typename HistSel<DEP, IP>::type;
     H hist; hist.init(sm.hist, M);
     H hist_next; hist_next.init(sm.hist2, M);
+    #ifdef PIC_DEVICE_PARTCONST                          // experiment: recompute the constants in registers (round-1 behaviour)
     const PartConst<R> pc = make_part_const<R>(a.mc);
+#else
+    const PartConst<R>& pc = part_const<R>(a.pcs);
+#endif
 
     const bool fused = a.comm.world > 1;
     bool dead = false;                                  // fused exchange timed out: leave the particle state untouched
@@ -488,6 +493,7 @@ __global__ void __launch_bounds__(THREADS) field_finalize_kernel(const FinalizeA
 // ----------------------------------------------------------------- resident
 struct ResidentArgs {
     MeshConst mc;
+    PartConsts pcs;                    // per-particle constants of both precisions (host-computed)
     RewardConst rw;
     const double* tw_cos; const double* tw_sin; int n_modes;   // spectral read-out tables or nullptr
     double* modes;                     // [n_envs][2 n_modes] after the last step, or nullptr
@@ -529,7 +535,11 @@ __global__ void __launch_bounds__(THREADS, THREADS <= 512 ? 1024 / THREADS : 1) 
     double* ext_s = (double*)(smem_raw + a.lay.ext);
     using H = typename HistSel<DEP, IP>::type;
     H hist; hist.init(sm.hist, M);
+    #ifdef PIC_DEVICE_PARTCONST                          // experiment: recompute the constants in registers (round-1 behaviour)
     const PartConst<R> pc = make_part_const<R>(a.mc);
+#else
+    const PartConst<R>& pc = part_const<R>(a.pcs);
+#endif
     R* xe = (R*)a.x + (size_t)env * a.ld;
     R* ve = (R*)a.v + (size_t)env * a.ld;
     for (int i = tid; i < N; i += THREADS) { x_s[i] = xe[i]; v_s[i] = ve[i]; }
@@ -731,7 +741,11 @@ __global__ void __launch_bounds__(THREADS, THREADS <= 512 ? 1024 / THREADS : 1) 
         rho0.h[r] = hist0; rho0.h[r].w = map_to_rank(hist0.w, (unsigned)r);
         rho1.h[r] = hist1; rho1.h[r].w = map_to_rank(hist1.w, (unsigned)r);
     }
+    #ifdef PIC_DEVICE_PARTCONST                          // experiment: recompute the constants in registers (round-1 behaviour)
     const PartConst<R> pc = make_part_const<R>(a.mc);
+#else
+    const PartConst<R>& pc = part_const<R>(a.pcs);
+#endif
     R* xe = (R*)a.x + (size_t)env * a.ld + n_lo;
     R* ve = (R*)a.v + (size_t)env * a.ld + n_lo;
     for (int i = tid; i < N; i += THREADS) { x_s[i] = xe[i]; v_s[i] = ve[i]; }

@@ -66,7 +66,7 @@ for dep in a.deps.split(","):
         e0.record()
         for i in range(a.steps):
             eng.step_mesh_device(None, 1)
-            if hdev is not None and i % 4 == 3:
+            if hdev is not None and i == a.steps - 1:
                 torch.cuda.current_stream().synchronize() if False else None
                 clk.append((pynvml.nvmlDeviceGetClockInfo(hdev, pynvml.NVML_CLOCK_SM), pynvml.nvmlDeviceGetPowerUsage(hdev) / 1000.0))
         e1.record(); torch.cuda.synchronize()
