@@ -204,6 +204,21 @@ int configure_launch(pic_handle* h) {
 
 int comm_slot_len(const pic_handle* h) { return 2 * h->M * h->n_envs + 2 * h->n_envs; }
 
+// launch with programmatic stream serialization (see griddep_wait in pic_device.cuh)
+cudaError_t launch_pdl(const void* kernel, dim3 grid, dim3 block, void** args, size_t smem, cudaStream_t stream) {
+#ifdef PIC_NO_PDL
+    return cudaLaunchKernel(kernel, grid, block, args, smem, stream);
+#else
+    cudaLaunchConfig_t lc{};
+    lc.gridDim = grid; lc.blockDim = block; lc.dynamicSmemBytes = smem; lc.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    lc.attrs = at; lc.numAttrs = 1;
+    return cudaLaunchKernelExC(&lc, kernel, args);
+#endif
+}
+
 void fill_comm(const pic_handle* h, CommArgs& c, unsigned long long seq_in, int in_offset, unsigned long long seq_out,
                const unsigned long long* out_src, int out_words) {
     c.world = h->fused ? h->world : 1; c.rank = h->rank; c.slot_len = comm_slot_len(h);
@@ -349,8 +364,8 @@ int run_stage(pic_handle* h, int stage, const double* ext, const double* coeffs,
         const bool nccl_sharded = h->world > 1 && !h->fused;
         f.rho_reduced = h->rho[3]; f.err = h->err; f.trace_row = nccl_sharded ? nullptr : trace_row;
         void* args[] = {&f};
-        CK(h, cudaLaunchKernel((const void*)&field_finalize_kernel<1024>, dim3(h->n_envs), dim3(1024), args,
-                               smem_plan_bytes<double>(h->M, 1024, false), h->stream));
+        CK(h, launch_pdl((const void*)&field_finalize_kernel<1024>, dim3(h->n_envs), dim3(1024), args,
+                         smem_plan_bytes<double>(h->M, 1024, false), h->stream));
         h->launches++;
         if (nccl_sharded) {
             int r = nccl_api().allreduce(h->vsum, h->vsum, 2 * (size_t)h->n_envs, kNcclFloat64, kNcclSum, h->comm, h->stream);
@@ -391,7 +406,7 @@ int run_stage(pic_handle* h, int stage, const double* ext, const double* coeffs,
         fill_comm(h, a.comm, 0, 0, 0, nullptr, 0);
     }
     void* args[] = {&a};
-    CK(h, cudaLaunchKernel(stream_kernel(h, mode), dim3(h->grid_x, h->n_envs), dim3(h->threads), args, h->smem, h->stream));
+    CK(h, launch_pdl(stream_kernel(h, mode), dim3(h->grid_x, h->n_envs), dim3(h->threads), args, h->smem, h->stream));
     h->launches++;
     return allreduce_u64(h, reduce, reduce_count);     // S and W0 are adjacent: one all-reduce covers both
 }

@@ -995,6 +995,12 @@ __device__ __forceinline__ void prefetch_l2_bulk(const void* p, unsigned bytes) 
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
 
+// Programmatic dependent launch: the kernels of a streaming step are launched with the programmatic-serialization
+// attribute, so the next kernel's CTAs may be scheduled (and run whatever precedes their own wait) while this grid is
+// still draining; `griddep_wait` returns once every grid this one depends on has completed and its writes are visible.
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // streaming loads / stores (no reuse: keep the particle stream out of L1, evict-first in L2)
 #ifndef PIC_LD_FLAVOR
 #define PIC_LD_FLAVOR 0

@@ -223,6 +223,10 @@ __global__ void __launch_bounds__(THREADS) push_stream_kernel(const StreamArgs a
 #else
     const PartConst<R>& pc = part_const<R>(a.pcs);
 #endif
+#ifndef PIC_NO_PDL
+    griddep_launch_dependents();                        // the next kernel of the step may start launching behind this one
+    griddep_wait();                                     // ... and this one touches memory only after its predecessors are done
+#endif
 
     const bool fused = a.comm.world > 1;
     bool dead = false;                                  // fused exchange timed out: leave the particle state untouched
@@ -441,6 +445,10 @@ template <int THREADS>
 __global__ void __launch_bounds__(THREADS) field_finalize_kernel(const FinalizeArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int env = blockIdx.x, M = a.mc.M, tid = threadIdx.x;
+#ifndef PIC_NO_PDL
+    griddep_launch_dependents();
+    griddep_wait();
+#endif
     SmemLayout<double> sm(smem_raw, M, false);
     const ExtSrc none{nullptr, nullptr, nullptr, nullptr, 0};
     const ModeOut mo{a.tw_cos, a.tw_sin, a.modes ? a.modes + (size_t)env * 2 * a.n_modes : nullptr, a.n_modes};
