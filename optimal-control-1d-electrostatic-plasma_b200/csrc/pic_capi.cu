@@ -577,8 +577,18 @@ int pic_create(const pic_config* cfg, pic_handle** out) {
     const size_t res1024 = h->f32 ? resident_smem_bytes<float>(h->M, 1024, h->N, h->ip) : resident_smem_bytes<double>(h->M, 1024, h->N, h->ip);
     // resident = the whole env (particles + mesh tables) fits the shared memory of one CTA; its field solve is the
     // small-mesh instance (block_field), so N_mesh <= 1024
-    if (mode == PIC_MODE_AUTO)
+    if (mode == PIC_MODE_AUTO) {
         mode = ((long long)res1024 <= (long long)h->max_smem && h->M <= FIELD_SMALL_MESH) ? PIC_MODE_RESIDENT : PIC_MODE_STREAMING;
+        // an env that needs a CTA PAIR (up to ~26 000 particles at float64) still runs resident when the batch fills the
+        // GPU: measured 49 vs 45 G particle-steps/s for 1024 envs x 20 000 particles; larger clusters lose to the streaming
+        // kernels (22 vs 46 G for 256 x 40 000) and are only used on request
+        if (mode == PIC_MODE_STREAMING && h->M <= FIELD_SMALL_MESH && h->n_envs >= h->sm_count &&
+            cfg->deposit != PIC_DEPOSIT_CAS64 && !h->exact_w) {
+            const size_t pair = h->f32 ? cluster_smem_bytes<float>(h->M, 1024, (h->N + 1) / 2, 2, h->ip)
+                                       : cluster_smem_bytes<double>(h->M, 1024, (h->N + 1) / 2, 2, h->ip);
+            if ((long long)pair <= (long long)h->max_smem) mode = PIC_MODE_RESIDENT;
+        }
+    }
     h->resident = mode == PIC_MODE_RESIDENT;
     if (h->resident && h->M > FIELD_SMALL_MESH) {
         drop_handle(h);

@@ -8,8 +8,8 @@ const void* cluster_kernel(bool f32, int threads, int cl, int ip) {
     PIC_C_CASE(double, 256, 2, pic::IP_CIC) PIC_C_CASE(double, 512, 2, pic::IP_CIC) PIC_C_CASE(double, 1024, 2, pic::IP_CIC)
     PIC_C_CASE(double, 256, 4, pic::IP_CIC) PIC_C_CASE(double, 512, 4, pic::IP_CIC) PIC_C_CASE(double, 1024, 4, pic::IP_CIC)
     PIC_C_CASE(double, 1024, 8, pic::IP_CIC)
-    PIC_C_CASE(float, 256, 2, pic::IP_CIC) PIC_C_CASE(float, 512, 2, pic::IP_CIC)
-    PIC_C_CASE(double, 256, 2, pic::IP_TSC) PIC_C_CASE(double, 512, 2, pic::IP_TSC)
+    PIC_C_CASE(float, 256, 2, pic::IP_CIC) PIC_C_CASE(float, 512, 2, pic::IP_CIC) PIC_C_CASE(float, 1024, 2, pic::IP_CIC)
+    PIC_C_CASE(double, 256, 2, pic::IP_TSC) PIC_C_CASE(double, 512, 2, pic::IP_TSC) PIC_C_CASE(double, 1024, 2, pic::IP_TSC)
     return nullptr;
 }
 }  // namespace pic

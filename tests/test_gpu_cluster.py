@@ -95,3 +95,21 @@ def test_env_too_large_for_one_cta_runs_resident_in_a_cluster():
         o = O.step(xo, vo, p, O.actuator_field(bc, bs, coeffs[t, 0, :5], coeffs[t, 0, 5:]))
         xo, vo = o["x"], o["v"]
     assert np.abs(clu["x"][0] - xo).max() < 1e-11 and np.abs(clu["v"][0] - vo).max() < 1e-11
+
+
+def test_auto_mode_uses_a_cta_pair_for_large_batches_of_mid_size_envs():
+    """20 000-particle envs do not fit one CTA; a batch that fills the GPU runs them resident as CTA pairs (measured
+    faster than the streaming kernels), a handful of them streams."""
+    import pic_b200
+    many = pic_b200.Engine(20_000, 250, 50.0, 0.02, n_envs=160)
+    assert many.launch_info()["mode"] == "resident" and many.launch_info()["per_thread"] == 2
+    few = pic_b200.Engine(20_000, 250, 50.0, 0.02, n_envs=4)
+    assert few.launch_info()["mode"] == "streaming"
+    tsc = pic_b200.Engine(20_000, 250, 50.0, 0.02, n_envs=160, interpol="TSC")
+    assert tsc.launch_info()["mode"] == "resident"
+    rng = np.random.RandomState(2)
+    x = rng.uniform(0, 50.0, (160, 20_000)); v = rng.normal(size=(160, 20_000))
+    many.set_state(x, v); many.step_mesh(None, 2)
+    s = pic_b200.Engine(20_000, 250, 50.0, 0.02, n_envs=160, mode="streaming")
+    s.set_state(x, v); s.step_mesh(None, 2)
+    assert np.array_equal(many.get_state()[0], s.get_state()[0]) and many.error_flags() == 0
