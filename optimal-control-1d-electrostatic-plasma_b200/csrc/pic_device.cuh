@@ -350,7 +350,9 @@ template <> struct Hist<DEP_SPLIT32> {
         const unsigned wl = (unsigned)S, wh = (unsigned)(S >> 32), cell = w_a + 12u * (unsigned)il;
         const unsigned old = atom_shared_u32_at<4>(cell, wl);
         red_shared_u32_at<0>(cell, count);
-        red_shared_u32_at<8>(cell, wh + ((old + wl) < old ? 1u : 0u));
+        unsigned hi_add;                               // wh + carry-out of (old + wl): one add with carry-out, one with carry-in
+        asm("{\n\t.reg .u32 t;\n\tadd.cc.u32 t, %1, %2;\n\taddc.u32 %0, %3, 0;\n\t}" : "=r"(hi_add) : "r"(old), "r"(wl), "r"(wh));
+        red_shared_u32_at<8>(cell, hi_add);
     }
     __device__ __forceinline__ void deposit(int il, long long Wr, long long one) {
         deposit_group(il, (unsigned long long)Wr, 1u, one);
@@ -798,12 +800,15 @@ __device__ __forceinline__ bool fast_cell(R xw, const PartConst<R>& c, int M, in
     // disagree only within eps of a cell edge (redone exactly on the careful path).  Three fp64-pipe instructions
     // (2 DFMA + the subtraction that turns the integer back into a double) where multiply, magic add, two
     // subtractions, an add and a compare were needed to measure the distance to the nearest integer.
+    // (The high word of the upper product needs no test of its own: with the lower product in range, the upper one is
+    //  at most a few units above it, so equal low words mean equal values.  NaN, infinities, negative and huge x all
+    //  fail the test of the lower product.)
     bool ok_lo, ok_hi;
     R t_lo, t_hi;
     il = RT<R>::floor_mul_magic(xw, c.inv_lo, ok_lo, t_lo);
     const int ih = RT<R>::floor_mul_magic(xw, c.inv_hi, ok_hi, t_hi);
     f = RT<R>::unmagic(t_lo);
-    return !ok_lo | !ok_hi | (il != ih) | ((unsigned)il >= (unsigned)M);
+    return !ok_lo | (il != ih) | ((unsigned)il >= (unsigned)M);
 }
 
 // the three TSC weights from the in-cell distance d = (x - m dx)/dx, formulas followed literally (interpolate.py:28-32)
@@ -861,7 +866,7 @@ __device__ __forceinline__ bool particle_fast(R x, R v, R& xn, R& vn, int& il_de
     if (KICK) {
         int il; R f;
         slow = fast_cell<R>(x, c, mc.M, il, f);
-        il = (unsigned)il < (unsigned)mc.M ? il : 0;            // keep the gather address legal on the slow path
+        il = (int)min((unsigned)il, (unsigned)(mc.M - 1));      // keep the gather address legal on the slow path
         R Ep = gather_field<R, IP, EXACT_W>(x, il, f, E_s, c, mc.M);
         vn = RT<R>::add(v, RT<R>::mul(RT<R>::mul(dd, -Ep), c.dt));
     }
