@@ -111,6 +111,9 @@ struct pic_handle {
     unsigned long long* cflags[COMM_MAX_WORLD] = {};
     unsigned long long seq = 0, seq_state = 0;       // last exchange issued; the exchange holding the state density
     unsigned* ticket = nullptr;
+    // finalize of step t overlapped with the first pass of step t+1 inside a multi-step call (single GPU)
+    cudaStream_t fin_stream = nullptr;
+    cudaEvent_t ev_pass_done = nullptr, ev_fin_done = nullptr;
 
     long long launches = 0;
     std::string last_error;
@@ -352,9 +355,14 @@ __global__ void kl_kernel(const unsigned* __restrict__ counts, const double* __r
     if (threadIdx.x == 0) kl[env] = acc * dxdv;
 }
 
-// one streaming sub-stage: stage 0..3 = Yoshida stages, 4 = finalize, -1 = init deposit
-int run_stage(pic_handle* h, int stage, const double* ext, const double* coeffs, double* trace_row) {
+// one streaming sub-stage: stage 0..3 = Yoshida stages, 4 = finalize, -1 = init deposit.
+// overlap (single GPU, inside a multi-step call): the finalize of a step runs on `fin_on` beside the first pass of the
+// next step; that pass then must not clear the state density the finalize is reading -- the stage-2 pass, which is
+// launched after the finalize has been waited for, clears it instead.
+int run_stage(pic_handle* h, int stage, const double* ext, const double* coeffs, double* trace_row, bool overlap = false,
+              cudaStream_t fin_on = nullptr) {
     if (stage == 4) {
+        cudaStream_t fs = fin_on ? fin_on : h->stream;
         FinalizeArgs f{};
         f.mc = h->mc; f.rho = h->rho[3]; f.rho_zero = h->rho[2]; f.n_out = h->n; f.E_out = h->E; f.diag = h->diag;
         f.partial = h->partial; f.vsum = h->vsum; f.n_partial = h->grid_x;
@@ -365,7 +373,7 @@ int run_stage(pic_handle* h, int stage, const double* ext, const double* coeffs,
         f.rho_reduced = h->rho[3]; f.err = h->err; f.trace_row = nccl_sharded ? nullptr : trace_row;
         void* args[] = {&f};
         CK(h, launch_pdl((const void*)&field_finalize_kernel<1024>, dim3(h->n_envs), dim3(1024), args,
-                         smem_plan_bytes<double>(h->M, 1024, false), h->stream));
+                         smem_plan_bytes<double>(h->M, 1024, false), fs));
         h->launches++;
         if (nccl_sharded) {
             int r = nccl_api().allreduce(h->vsum, h->vsum, 2 * (size_t)h->n_envs, kNcclFloat64, kNcclSum, h->comm, h->stream);
@@ -386,9 +394,10 @@ int run_stage(pic_handle* h, int stage, const double* ext, const double* coeffs,
     switch (stage) {
         case -1: mode = MODE_INIT; a.rho_out = h->rho[3]; a.rho_next = h->rho[0]; a.c = 0; a.d = 0;
                  reduce = h->rho[3]; reduce_count = 2 * sz; break;
-        case 1: mode = MODE_KICK0; a.c_pre = h->cs[0]; a.rho_in = h->rho[0]; a.rho_out = h->rho[1]; a.rho_zero = h->rho[3];
-                reduce = h->rho[1]; break;
-        case 2: mode = MODE_KICK; a.rho_in = h->rho[1]; a.rho_out = h->rho[2]; a.rho_zero = h->rho[0]; reduce = h->rho[2]; break;
+        case 1: mode = MODE_KICK0; a.c_pre = h->cs[0]; a.rho_in = h->rho[0]; a.rho_out = h->rho[1];
+                a.rho_zero = overlap ? nullptr : h->rho[3]; reduce = h->rho[1]; break;
+        case 2: mode = MODE_KICK; a.rho_in = h->rho[1]; a.rho_out = h->rho[2]; a.rho_zero = h->rho[0];
+                a.rho_zero2 = overlap ? h->rho[3] : nullptr; reduce = h->rho[2]; break;
         case 3: mode = MODE_FINAL; a.c_pre = h->cs[2]; a.rho_in = h->rho[2]; a.rho_out = h->rho[3]; a.rho_next = h->rho[0];
                 a.rho_zero = h->rho[1]; reduce = h->rho[3]; reduce_count = 2 * sz; break;
         default: return fail(h, PIC_EINVAL, "stage must be -1..4");
@@ -475,13 +484,30 @@ int step_device(pic_handle* h, const double* ext, const double* coeffs, int n_st
     int rc = ensure_trace(h, n_steps);
     if (rc) return rc;
     if (h->resident) return launch_resident(h, n_steps, ext, coeffs);
+    // Single GPU, several steps in one call: the finalize of step s (one CTA: state density -> field, energies,
+    // reward) runs on a side stream beside the first pass of step s + 1, which needs nothing it produces.  The side
+    // stream is joined before the stage-2 pass (which clears the buffers the finalize read / cleared) and at the end of
+    // the call, so nothing outside this function ever sees it.
+    const bool overlap = h->world <= 1 && !h->fused && n_steps > 1 && h->fin_stream != nullptr;
+    bool pending = false;
     for (int s = 0; s < n_steps; ++s) {
         const double* cf = coeffs ? coeffs + (size_t)s * h->n_envs * 2 * h->m : nullptr;
-        for (int st = 1; st < 4; ++st) if ((rc = run_stage(h, st, ext, cf, nullptr))) return rc;
-        if ((rc = run_stage(h, 4, nullptr, cf, h->trace + (size_t)s * h->n_envs * DIAG_N))) return rc;
+        double* row = h->trace + (size_t)s * h->n_envs * DIAG_N;
+        if ((rc = run_stage(h, 1, ext, cf, nullptr, overlap))) return rc;
+        if (pending) { CK(h, cudaStreamWaitEvent(h->stream, h->ev_fin_done, 0)); pending = false; }
+        if ((rc = run_stage(h, 2, ext, cf, nullptr, overlap))) return rc;
+        if ((rc = run_stage(h, 3, ext, cf, nullptr, overlap))) return rc;
+        const bool side = overlap && s < n_steps - 1;
+        cudaStream_t fs = side ? h->fin_stream : h->stream;
+        if (side) {
+            CK(h, cudaEventRecord(h->ev_pass_done, h->stream));
+            CK(h, cudaStreamWaitEvent(h->fin_stream, h->ev_pass_done, 0));
+        }
+        if ((rc = run_stage(h, 4, nullptr, cf, row, overlap, fs))) return rc;
         if (h->n_modes > 0)
             CK(h, cudaMemcpyAsync(h->mode_trace + (size_t)s * h->n_envs * 2 * h->n_modes, h->modes,
-                                  sizeof(double) * (size_t)h->n_envs * 2 * h->n_modes, cudaMemcpyDeviceToDevice, h->stream));
+                                  sizeof(double) * (size_t)h->n_envs * 2 * h->n_modes, cudaMemcpyDeviceToDevice, fs));
+        if (side) { CK(h, cudaEventRecord(h->ev_fin_done, h->fin_stream)); pending = true; }
     }
     return PIC_OK;
 }
@@ -671,6 +697,14 @@ int pic_create(const pic_config* cfg, pic_handle** out) {
     cudaMemsetAsync(h->err, 0, sizeof(unsigned), h->stream);
     if (cudaMalloc(&h->ticket, sizeof(unsigned)) != cudaSuccess) { pic_destroy(h); return fail(nullptr, PIC_ENOMEM, "cudaMalloc"); }
     cudaMemsetAsync(h->ticket, 0, sizeof(unsigned), h->stream);
+    if (!h->resident) {                              // side stream of the overlapped finalize (step_device)
+        if (cudaStreamCreateWithFlags(&h->fin_stream, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&h->ev_pass_done, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&h->ev_fin_done, cudaEventDisableTiming) != cudaSuccess) {
+            pic_destroy(h);
+            return fail(nullptr, PIC_ECUDA, "cudaStreamCreate / cudaEventCreate failed");
+        }
+    }
     int rc = configure_launch(h);
     if (rc) { g_create_error = h->last_error; pic_destroy(h); return rc; }
     *out = h;
@@ -686,6 +720,9 @@ int pic_destroy(pic_handle* h) {
                     h->ext, h->coeffs, h->bcos, h->bsin, h->trace, h->stage64, h->err, h->tw_cos, h->tw_sin, h->modes,
                     h->mode_trace, h->ph_counts, h->ph_feq, h->ph_kl, h->ticket};
     for (void* b : bufs) if (b) cudaFree(b);
+    if (h->fin_stream) { cudaStreamSynchronize(h->fin_stream); cudaStreamDestroy(h->fin_stream); }
+    if (h->ev_pass_done) cudaEventDestroy(h->ev_pass_done);
+    if (h->ev_fin_done) cudaEventDestroy(h->ev_fin_done);
     if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
     delete h;
     return PIC_OK;

@@ -128,6 +128,7 @@ struct StreamArgs {
     unsigned long long* rho_out;       // [n_envs][M] must be zero on entry
     unsigned long long* rho_next;      // MODE_FINAL / MODE_INIT: density of x1 (must be zero on entry)
     unsigned long long* rho_zero;      // [n_envs][M] or nullptr: cleared for a later sub-stage
+    unsigned long long* rho_zero2;     // a second buffer to clear (overlapped finalize: see step_device), or nullptr
     ActuatorArgs act;
     double c, d;
     double c_next;                     // c0 of the Yoshida scheme (MODE_FINAL / MODE_INIT: stage 0 of the next step)
@@ -246,6 +247,10 @@ __global__ void __launch_bounds__(THREADS) push_stream_kernel(const StreamArgs a
     __syncthreads();
     if (a.rho_zero) {
         unsigned long long* z = a.rho_zero + (size_t)env * M;
+        for (int j = blockIdx.x * THREADS + tid; j < M; j += gridDim.x * THREADS) z[j] = 0ull;
+    }
+    if (a.rho_zero2) {
+        unsigned long long* z = a.rho_zero2 + (size_t)env * M;
         for (int j = blockIdx.x * THREADS + tid; j < M; j += gridDim.x * THREADS) z[j] = 0ull;
     }
 
