@@ -217,8 +217,8 @@ def run_reference_arm(args):
     if rank != 0:
         return
     kind, ref = cpu_kind()
-    n_sample = 2_000_000
-    procs = host_procs(n_sample, N_MESH)
+    n_sample = int(float(os.environ.get("PIC_BENCH_CPU_SAMPLE", "2e6")))      # (tests shrink it)
+    procs = host_procs(n_sample, N_MESH, int(os.environ["PIC_BENCH_CPU_PROCS"]) if "PIC_BENCH_CPU_PROCS" in os.environ else None)
     pool = CpuPool(kind, procs, n_sample, N_MESH, ref)
     try:
         for _ in range(max(1, args.warmup)):
