@@ -26,7 +26,7 @@ extern "C" {
 #pragma GCC visibility push(default)   /* the library is built with -fvisibility=hidden; these are its exports */
 #endif
 
-#define PIC_B200_ABI_VERSION 2
+#define PIC_B200_ABI_VERSION 3
 
 enum { PIC_OK = 0, PIC_EINVAL = -1, PIC_ENODEVICE = -2, PIC_ECUDA = -3, PIC_ENOMEM = -4, PIC_ESTATE = -5,
        PIC_ENUMERIC = -6, PIC_ENCCL = -7, PIC_EUNSUPPORTED = -8 };
@@ -203,6 +203,19 @@ int pic_get_launch_info(pic_handle* h, int32_t* mode, int32_t* threads, int32_t*
  * cluster whose CTAs exchange their histograms through distributed shared memory), third argument unused.
  * pic_get_launch_info reports the same quantity in *per_thread.  0 / negative = keep. */
 int pic_set_tuning(pic_handle* h, int32_t threads, int32_t unroll_or_cluster, int32_t ctas_per_sm);
+/* streaming mode: where the kick's field gather (util.py:106) reads the mesh field from.  PIC_GATHER_SHARED: every CTA
+ * rebuilds the field in its prologue and gathers from shared memory.  PIC_GATHER_TEXTURE: the field is solved once per
+ * sub-stage by a one-CTA launch and gathered through the texture pipe (off the LSU pipe that the deposit's shared
+ * atomics saturate).  PIC_GATHER_TEXTURE_STAGES(mask): texture for the Yoshida stages whose bit is set (bit 0: stage
+ * 1, bit 1: stage 2, bit 2: stage 3), shared for the others.  Identical bits whatever the route.  PIC_GATHER_AUTO
+ * (default): texture where it was measured faster (stage 3 of large envs).  pic_get_gather reports the route in
+ * effect (SHARED, TEXTURE or TEXTURE_STAGES(mask)). */
+#define PIC_GATHER_AUTO 0
+#define PIC_GATHER_SHARED 1
+#define PIC_GATHER_TEXTURE 2
+#define PIC_GATHER_TEXTURE_STAGES(mask) (0x10 | ((mask) & 0x7))
+int pic_set_gather(pic_handle* h, int32_t route);
+int pic_get_gather(pic_handle* h, int32_t* route);
 int64_t pic_kernel_launch_count(const pic_handle* h);        /* kernels enqueued by this handle so far */
 
 #if defined(__GNUC__)

@@ -92,6 +92,8 @@ SIGNATURES = {
     "pic_set_stage_actuation": (C.c_int, [_H, C.c_void_p, C.c_void_p]),
     "pic_get_launch_info": (C.c_int, [_H] + [C.POINTER(C.c_int32)] * 7),
     "pic_set_tuning": (C.c_int, [_H, C.c_int32, C.c_int32, C.c_int32]),
+    "pic_set_gather": (C.c_int, [_H, C.c_int32]),
+    "pic_get_gather": (C.c_int, [_H, C.POINTER(C.c_int32)]),
     "pic_kernel_launch_count": (C.c_int64, [_H]),
 }
 

@@ -115,6 +115,20 @@ struct pic_handle {
     cudaStream_t fin_stream = nullptr;
     cudaEvent_t ev_pass_done = nullptr, ev_fin_done = nullptr;
 
+    // gather route of the streaming kernels: shared-memory table rebuilt in every CTA's prologue, or one global table per
+    // sub-stage (written by field_table_kernel) read through the texture pipe
+    int gather_req = PIC_GATHER_AUTO;               // what the caller asked for
+    bool texg = false;                              // what is in effect: any stage on the texture route ...
+    bool tex_stage[3] = {false, false, false};      // ... and which (Yoshida stages 1, 2, 3)
+    void* table[3] = {nullptr, nullptr, nullptr};   // [n_envs][M] pairs, one per kick stage (1, 2, 3)
+    cudaTextureObject_t table_tex[3] = {0, 0, 0};
+    size_t smem_tex[3] = {0, 0, 0};                 // dynamic shared memory of the TEXG kernel of stage 1, 2, 3
+    // Large meshes (TSC at 4096 cells): the two-histogram kernels (stage 3, init) do not fit next to a shared-memory
+    // gather table.  They then run their table-less instances -- stage 3 on the texture route whatever was asked for,
+    // the init deposit (which gathers nothing) with the table-less layout -- and h->smem is the one-histogram plan.
+    bool tableless = false;
+    size_t smem_init = 0;
+
     long long launches = 0;
     std::string last_error;
 };
@@ -165,8 +179,90 @@ size_t smem_for(const pic_handle* h) {
                   : smem_plan_bytes<double>(h->M, h->threads, false, h->ip, true);    // stage-3 / init kernels
 }
 
+const int kStageMode[3] = {MODE_KICK0, MODE_KICK, MODE_FINAL};     // Yoshida stages 1, 2, 3
+
+// Gather route of the streaming kernels (see TexTable in pic_device.cuh), chosen per Yoshida stage.  AUTO takes the
+// texture route where it was measured faster (N = 1e9, 4096 cells): the stage-3 pass, whose two deposits + gather
+// saturate the LSU data pipe (6.03 -> 5.52 ms under the power cap); not the stage-1 pass, which is bound by HBM alone and
+// loses (5.31 -> 6.35 ms: the texture fetches queue behind the pass's own outstanding global loads), nor stage 2 (equal
+// under the cap, slower at boost clocks).  Conditions: split32 deposit, default launch shape, no fused peer exchange
+// (whose prologue consumes the peers' slots), and enough particles per launch that the extra one-CTA field launch per
+// pass does not show (kTexMinParticles).
+constexpr long long kTexMinParticles = 1ll << 22;
+constexpr int kTexAutoStages = 0x4;                 // bit s-1: stage s
+int configure_gather(pic_handle* h) {
+    h->texg = false;
+    for (int i = 0; i < 3; ++i) h->tex_stage[i] = false;
+    if (h->resident) return PIC_OK;
+    if (h->tableless) {
+        const void* ki = stream_kernel_tex(h->f32, h->threads, h->per_thread, MODE_INIT, h->ip);
+        CK(h, cudaFuncSetAttribute(ki, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_init));
+    }
+    if (h->gather_req == PIC_GATHER_SHARED && !h->tableless) return PIC_OK;
+    int mask = h->gather_req == PIC_GATHER_AUTO ? kTexAutoStages
+             : h->gather_req == PIC_GATHER_TEXTURE ? 0x7
+             : h->gather_req == PIC_GATHER_SHARED ? 0 : (h->gather_req & 0x7);
+    if (h->tableless) mask |= 0x4;
+    bool have = h->dep == DEP_SPLIT32 && !h->exact_w && !h->fused;
+    for (int i = 0; i < 3 && have; ++i) have = stream_kernel_tex(h->f32, h->threads, h->per_thread, kStageMode[i], h->ip) != nullptr;
+    if (!have) {
+        if (h->tableless)
+            return fail(h, PIC_EUNSUPPORTED, "n_mesh too large for the shared-memory mesh tables of this configuration "
+                                             "(the table-less texture route needs the 1024 x 2 shape and no fused peer exchange)");
+        if (h->gather_req != PIC_GATHER_AUTO && h->gather_req != PIC_GATHER_SHARED)
+            return fail(h, PIC_EUNSUPPORTED, "gather = texture needs streaming mode, the split32 deposit, exact_weights = 0, "
+                                             "the 1024 x 2 launch shape and no fused peer exchange");
+        return PIC_OK;
+    }
+    if (h->gather_req == PIC_GATHER_AUTO && !h->tableless) {
+        // measured: float64 CIC gains from ~1e6 particles up; float32 (an 8-byte gather is cheap on the LSU pipe) loses
+        if (h->f32 || h->N * (long long)h->n_envs < kTexMinParticles) return PIC_OK;
+    }
+    const size_t pair = h->f32 ? sizeof(float2) : sizeof(double2);
+    cudaDeviceProp prop;
+    CK(h, cudaGetDeviceProperties(&prop, h->device));
+    for (int i = 0; i < 3; ++i) {
+        if (!h->table[i]) {
+            CK(h, cudaMalloc(&h->table[i], pair * (size_t)h->M * h->n_envs));
+            cudaResourceDesc rd{};
+            rd.resType = cudaResourceTypeLinear;
+            rd.res.linear.devPtr = h->table[i];
+            rd.res.linear.desc = h->f32 ? cudaCreateChannelDesc<float2>() : cudaCreateChannelDesc<int4>();
+            rd.res.linear.sizeInBytes = pair * (size_t)h->M * h->n_envs;
+            cudaTextureDesc td{};
+            td.readMode = cudaReadModeElementType;
+            CK(h, cudaCreateTextureObject(&h->table_tex[i], &rd, &td, nullptr));
+        }
+        const bool second = kStageMode[i] == MODE_FINAL;
+        h->smem_tex[i] = h->f32 ? smem_plan_bytes<float>(h->M, h->threads, false, h->ip, second, false)
+                                : smem_plan_bytes<double>(h->M, h->threads, false, h->ip, second, false);
+        const void* k = stream_kernel_tex(h->f32, h->threads, h->per_thread, kStageMode[i], h->ip);
+        CK(h, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_tex[i]));
+        // the smallest shared-memory carve-out that holds the CTA: everything else of the SM's 256 KB is L1 for the table
+        int pct = (int)(((h->smem_tex[i] + 1024) * 100 + prop.sharedMemPerMultiprocessor - 1) / prop.sharedMemPerMultiprocessor);
+        if (pct > 100) pct = 100;
+        CK(h, cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+    }
+    const void* kt = field_table_kernel_for(h->f32);
+    CK(h, cudaFuncSetAttribute(kt, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)(h->f32 ? smem_plan_bytes<float>(h->M, 1024, false) : smem_plan_bytes<double>(h->M, 1024, false))));
+    for (int i = 0; i < 3; ++i) h->tex_stage[i] = (mask >> i) & 1;
+    h->texg = mask != 0;
+    return PIC_OK;
+}
+
 int configure_launch(pic_handle* h) {
     h->smem = smem_for(h);
+    h->tableless = false;
+    if (!h->resident && (int)h->smem > h->max_smem) {
+        const size_t one = h->f32 ? smem_plan_bytes<float>(h->M, h->threads, false, h->ip, false) : smem_plan_bytes<double>(h->M, h->threads, false, h->ip, false);
+        const size_t two_tl = h->f32 ? smem_plan_bytes<float>(h->M, h->threads, false, h->ip, true, false) : smem_plan_bytes<double>(h->M, h->threads, false, h->ip, true, false);
+        if ((int)one <= h->max_smem && (int)two_tl <= h->max_smem && h->dep == DEP_SPLIT32 && !h->exact_w &&
+            stream_kernel_tex(h->f32, h->threads, h->per_thread, MODE_FINAL, h->ip) &&
+            stream_kernel_tex(h->f32, h->threads, h->per_thread, MODE_INIT, h->ip)) {
+            h->tableless = true; h->smem = one; h->smem_init = two_tl;
+        }
+    }
     if ((int)h->smem > h->max_smem)
         return fail(h, PIC_EUNSUPPORTED, h->resident ? "env does not fit the shared memory of its CTA(s) (" + std::to_string(h->smem) +
                     " B needed per CTA, " + std::to_string(h->max_smem) + " B available)"
@@ -182,6 +278,7 @@ int configure_launch(pic_handle* h) {
     }
     int occ_min = 1 << 30;
     for (int mode = MODE_KICK; mode <= MODE_KICK0; ++mode) {
+        if (h->tableless && (mode == MODE_FINAL || mode == MODE_INIT)) continue;
         const void* k = stream_kernel(h, mode);
         if (!k) return fail(h, PIC_EUNSUPPORTED, "no streaming kernel variant for threads=" + std::to_string(h->threads) +
                             " unroll=" + std::to_string(h->per_thread));
@@ -202,7 +299,7 @@ int configure_launch(pic_handle* h) {
     CK(h, cudaMalloc(&h->partial, sizeof(double) * 2 * (size_t)h->grid_x * h->n_envs));
     const void* kf = (const void*)&field_finalize_kernel<1024>;
     CK(h, cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_plan_bytes<double>(h->M, 1024, false)));
-    return PIC_OK;
+    return configure_gather(h);
 }
 
 int comm_slot_len(const pic_handle* h) { return 2 * h->M * h->n_envs + 2 * h->n_envs; }
@@ -415,8 +512,25 @@ int run_stage(pic_handle* h, int stage, const double* ext, const double* coeffs,
         fill_comm(h, a.comm, 0, 0, 0, nullptr, 0);
     }
     void* args[] = {&a};
-    CK(h, launch_pdl(stream_kernel(h, mode), dim3(h->grid_x, h->n_envs), dim3(h->threads), args, h->smem, h->stream));
-    h->launches++;
+    if (stage >= 1 && h->tex_stage[stage - 1]) {
+        // the field of this sub-stage, solved once and written as the gather table the pass reads through the texture pipe
+        FieldTableArgs t{};
+        t.mc = h->mc; t.rho_in = a.rho_in; t.act = a.act; t.table = h->table[stage - 1];
+        void* targs[] = {&t};
+        CK(h, launch_pdl(field_table_kernel_for(h->f32), dim3(h->n_envs), dim3(1024), targs,
+                         h->f32 ? smem_plan_bytes<float>(h->M, 1024, false) : smem_plan_bytes<double>(h->M, 1024, false), h->stream));
+        a.table_tex = h->table_tex[stage - 1];
+        CK(h, launch_pdl(stream_kernel_tex(h->f32, h->threads, h->per_thread, mode, h->ip), dim3(h->grid_x, h->n_envs),
+                         dim3(h->threads), args, h->smem_tex[stage - 1], h->stream));
+        h->launches += 2;
+    } else if (stage == -1 && h->tableless) {
+        CK(h, launch_pdl(stream_kernel_tex(h->f32, h->threads, h->per_thread, MODE_INIT, h->ip), dim3(h->grid_x, h->n_envs),
+                         dim3(h->threads), args, h->smem_init, h->stream));
+        h->launches++;
+    } else {
+        CK(h, launch_pdl(stream_kernel(h, mode), dim3(h->grid_x, h->n_envs), dim3(h->threads), args, h->smem, h->stream));
+        h->launches++;
+    }
     return allreduce_u64(h, reduce, reduce_count);     // S and W0 are adjacent: one all-reduce covers both
 }
 
@@ -720,6 +834,10 @@ int pic_destroy(pic_handle* h) {
                     h->ext, h->coeffs, h->bcos, h->bsin, h->trace, h->stage64, h->err, h->tw_cos, h->tw_sin, h->modes,
                     h->mode_trace, h->ph_counts, h->ph_feq, h->ph_kl, h->ticket};
     for (void* b : bufs) if (b) cudaFree(b);
+    for (int i = 0; i < 3; ++i) {
+        if (h->table_tex[i]) cudaDestroyTextureObject(h->table_tex[i]);
+        if (h->table[i]) cudaFree(h->table[i]);
+    }
     if (h->fin_stream) { cudaStreamSynchronize(h->fin_stream); cudaStreamDestroy(h->fin_stream); }
     if (h->ev_pass_done) cudaEventDestroy(h->ev_pass_done);
     if (h->ev_fin_done) cudaEventDestroy(h->ev_fin_done);
@@ -754,6 +872,26 @@ int pic_set_tuning(pic_handle* h, int32_t threads, int32_t per_thread, int32_t c
     int rc = configure_launch(h);
     if (rc) { h->threads = t0; h->per_thread = p0; h->ctas_per_sm = c0; h->cluster = cl0; configure_launch(h); }
     return rc;
+}
+
+int pic_set_gather(pic_handle* h, int32_t route) {
+    if (!h) return PIC_EINVAL;
+    if (route != PIC_GATHER_AUTO && route != PIC_GATHER_SHARED && route != PIC_GATHER_TEXTURE &&
+        (route < PIC_GATHER_TEXTURE_STAGES(1) || route > PIC_GATHER_TEXTURE_STAGES(7)))
+        return fail(h, PIC_EINVAL, "route must be PIC_GATHER_AUTO, PIC_GATHER_SHARED, PIC_GATHER_TEXTURE or PIC_GATHER_TEXTURE_STAGES(mask)");
+    const int r0 = h->gather_req;
+    h->gather_req = route;
+    cudaStreamSynchronize(h->stream);
+    int rc = configure_gather(h);
+    if (rc) { h->gather_req = r0; configure_gather(h); }
+    return rc;
+}
+
+int pic_get_gather(pic_handle* h, int32_t* route) {
+    if (!h || !route) return PIC_EINVAL;
+    const int mask = (h->tex_stage[0] ? 1 : 0) | (h->tex_stage[1] ? 2 : 0) | (h->tex_stage[2] ? 4 : 0);
+    *route = mask == 0 ? PIC_GATHER_SHARED : mask == 7 ? PIC_GATHER_TEXTURE : PIC_GATHER_TEXTURE_STAGES(mask);
+    return PIC_OK;
 }
 
 int pic_get_launch_info(pic_handle* h, int32_t* mode, int32_t* threads, int32_t* per_thread, int32_t* grid_x,
@@ -1166,7 +1304,8 @@ int pic_comm_init_peer(pic_handle* h, int32_t rank, int32_t world, void* const* 
         h->exch[r] = (unsigned long long*)exch_ptrs[r]; h->cflags[r] = (unsigned long long*)flag_ptrs[r];
     }
     h->rank = rank; h->world = world; h->fused = true; h->seq = 0; h->seq_state = 0;
-    return PIC_OK;
+    if (h->gather_req != PIC_GATHER_SHARED) h->gather_req = PIC_GATHER_AUTO;    // the fused prologue consumes the peers' slots itself
+    return configure_gather(h);
 }
 
 int pic_set_stage_actuation(pic_handle* h, const double* ext_dev, const double* coeffs_dev) {

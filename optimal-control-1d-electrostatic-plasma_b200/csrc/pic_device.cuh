@@ -151,6 +151,24 @@ template <typename R> struct PairT;
 template <> struct PairT<double> { using type = double2; };
 template <> struct PairT<float> { using type = float2; };
 
+// The same table read through the TEXTURE pipe (streaming kernels with gather = texture): a linear texture object over a
+// global copy of the pair table, written by field_table_kernel before the pass.  The fetch runs on the SM's texture
+// pipe and is served by the L1, so it no longer competes with the deposit's shared atomics for the LSU data pipe --
+// the unit that bounds the SM-side passes (a random 16-byte LDS costs 10.6 LSU wavefronts per warp next to 3.7 per
+// atomic; tools/tex_probe.cu: 6 atomics + LDS gather 3.41 ms per 1e9 particles, + texture gather 2.30 ms, no gather 2.29).
+template <typename R> struct TexTable;
+template <> struct TexTable<double> {
+    cudaTextureObject_t tex; int base;                 // base: first texel of this env's table
+    __device__ __forceinline__ double2 operator[](int i) const {
+        const int4 q = tex1Dfetch<int4>(tex, base + i);
+        return make_double2(__hiloint2double(q.y, q.x), __hiloint2double(q.w, q.z));
+    }
+};
+template <> struct TexTable<float> {
+    cudaTextureObject_t tex; int base;
+    __device__ __forceinline__ float2 operator[](int i) const { return tex1Dfetch<float2>(tex, base + i); }
+};
+
 // ------------------------------------------------------------ kernel parameters
 struct MeshConst {
     int M;                 // N_mesh
@@ -820,23 +838,38 @@ __device__ __forceinline__ void tsc_weights(R d, R& wl, R& wm, R& wr) {
     wr = RT<R>::mul((R)0.5, RT<R>::mul(q, q));
 }
 
-// gathered field at a particle of cell il (already inside the mesh) with in-cell numerators, util.py:106 / :110
+// gathered field at a particle of cell il (already inside the mesh) with in-cell numerators, util.py:106 / :110.
+// Split into the table read (fetch_field) and the arithmetic (apply_gather) so that the texture-gather kernels can issue
+// the reads of a whole tile before they consume the first of them (the texture pipe's latency is several times a
+// shared load's); gather_field is the two back to back.
+template <typename R, int IP> struct Fetched { typename PairT<R>::type e1, e0; };   // e1 = (E_m, E_{m+1}); e0 = (E_{m-1}, E_m): TSC only
+
+template <typename R, int IP, typename ET>
+__device__ __forceinline__ Fetched<R, IP> fetch_field(int il, const ET& E_s, int M) {
+    Fetched<R, IP> q;
+    if (IP == IP_TSC) q.e0 = E_s[il == 0 ? M - 1 : il - 1];
+    q.e1 = E_s[il];
+    return q;
+}
+
 template <typename R, int IP, bool EXACT_W>
-__device__ __forceinline__ R gather_field(R x, int il, R f, const typename PairT<R>::type* __restrict__ E_s,
-                                          const PartConst<R>& c, int M) {
+__device__ __forceinline__ R apply_gather(R x, R f, const Fetched<R, IP>& q, const PartConst<R>& c) {
     R nr = RT<R>::sub(x, RT<R>::mul(f, c.dx));
     R wr = EXACT_W ? RT<R>::div(nr, c.dx) : RT<R>::mul(nr, c.inv_dx);
     if (IP == IP_TSC) {
         R wl, wm, wrr;
         tsc_weights<R>(wr, wl, wm, wrr);
-        const typename PairT<R>::type e0 = E_s[il == 0 ? M - 1 : il - 1], e1 = E_s[il];   // (E_{m-1},E_m), (E_m,E_{m+1})
-        return RT<R>::add(RT<R>::add(RT<R>::mul(wl, e0.x), RT<R>::mul(wm, e1.x)), RT<R>::mul(wrr, e1.y));
+        return RT<R>::add(RT<R>::add(RT<R>::mul(wl, q.e0.x), RT<R>::mul(wm, q.e1.x)), RT<R>::mul(wrr, q.e1.y));
     }
     R fr = RT<R>::add(f, (R)1);
     R nl = RT<R>::sub(RT<R>::mul(fr, c.dx), x);
     R wl = EXACT_W ? RT<R>::div(nl, c.dx) : RT<R>::mul(nl, c.inv_dx);
-    const typename PairT<R>::type e = E_s[il];
-    return RT<R>::add(RT<R>::mul(wl, e.x), RT<R>::mul(wr, e.y));
+    return RT<R>::add(RT<R>::mul(wl, q.e1.x), RT<R>::mul(wr, q.e1.y));
+}
+
+template <typename R, int IP, bool EXACT_W, typename ET>
+__device__ __forceinline__ R gather_field(R x, int il, R f, const ET& E_s, const PartConst<R>& c, int M) {
+    return apply_gather<R, IP, EXACT_W>(x, f, fetch_field<R, IP>(il, E_s, M), c);
 }
 
 // fixed-point deposit weights of a particle at wrapped position xw in cell with floor f:
@@ -857,10 +890,9 @@ __device__ __forceinline__ void deposit_weights(R xw, R f, const PartConst<R>& c
     }
 }
 
-template <typename R, int IP, bool KICK, bool MOVE, bool EXACT_W>
+template <typename R, int IP, bool KICK, bool MOVE, bool EXACT_W, typename ET>
 __device__ __forceinline__ bool particle_fast(R x, R v, R& xn, R& vn, int& il_dep, long long& Wa, long long& Wb,
-                                              const typename PairT<R>::type* __restrict__ E_s, R cc, R dd,
-                                              const PartConst<R>& c, const MeshConst& mc) {
+                                              const ET& E_s, R cc, R dd, const PartConst<R>& c, const MeshConst& mc) {
     bool slow = false;
     vn = v;
     if (KICK) {
@@ -879,11 +911,10 @@ __device__ __forceinline__ bool particle_fast(R x, R v, R& xn, R& vn, int& il_de
 
 // Reference semantics, every case handled (cold block; reached by ~1e-5 .. 1e-2 of the particles).
 // wrap_state: the position written back is the wrapped one (pic.py:139 / util.py:51), else the unwrapped drift.
-template <typename R, int IP, bool KICK, bool MOVE, bool EXACT_W>
+template <typename R, int IP, bool KICK, bool MOVE, bool EXACT_W, typename ET>
 __device__ __forceinline__ void particle_careful(R& x, R& v, int& il_dep, long long& Wa, long long& Wb,
-                                                 const typename PairT<R>::type* __restrict__ E_s, R cc, R dd,
-                                                 const PartConst<R>& c, const MeshConst& mc, bool wrap_state,
-                                                 unsigned& err) {
+                                                 const ET& E_s, R cc, R dd, const PartConst<R>& c, const MeshConst& mc,
+                                                 bool wrap_state, unsigned& err) {
     if (KICK) {
         R xk = wrap_pos<R>(x, c, err), fk;
         int ik = cell_index<R>(xk, c, mc.M, fk, err);
@@ -949,8 +980,10 @@ __device__ __forceinline__ void deposit_hinted(H& hist, int il, long long Wa, lo
 // One sub-stage for one particle: fast path, careful fallback, deposit.  x, v are updated in place.
 // FULL_WARP: the caller guarantees that all 32 lanes of the warp execute this call (enables the aggregated deposit,
 // steered by the per-tile hint `agg`; PROBE: this call refreshes the hint).
-template <typename R, int IP, bool KICK, bool MOVE, bool EXACT_W, bool FULL_WARP, typename H, bool PROBE = false>
-__device__ __forceinline__ void particle_substage(R& x, R& v, H& hist, const typename PairT<R>::type* __restrict__ E_s,
+// ET: the gather table -- a pointer to the shared-memory pair table, or a TexTable (anything with operator[](cell)).
+template <typename R, int IP, bool KICK, bool MOVE, bool EXACT_W, bool FULL_WARP, typename H, bool PROBE = false,
+          typename ET = const typename PairT<R>::type*>
+__device__ __forceinline__ void particle_substage(R& x, R& v, H& hist, const ET& E_s,
                                                   R cc, R dd, const PartConst<R>& c, const MeshConst& mc,
                                                   bool wrap_state, unsigned& err, bool* agg = nullptr) {
     R xn, vn; int il; long long Wa, Wb;
@@ -962,6 +995,31 @@ __device__ __forceinline__ void particle_substage(R& x, R& v, H& hist, const typ
     }
     if (FULL_WARP) {
         __syncwarp();                                     // reconverge after the cold branch before the warp-wide part
+        deposit_hinted<IP, PROBE>(hist, il, Wa, Wb, mc.fix_one, *agg);
+    } else {
+        deposit_one<IP>(hist, il, Wa, Wb, mc.fix_one);
+    }
+}
+
+// The same sub-stage for a particle whose gather was issued ahead of time (texture-gather kernels): `f`, `slow_gather`
+// and `q` are what fast_cell and fetch_field returned for the particle's position x.  Same arithmetic, same bits.
+template <typename R, int IP, bool MOVE, bool EXACT_W, bool FULL_WARP, typename H, bool PROBE, typename ET>
+__device__ __forceinline__ void particle_substage_pre(R& x, R& v, R f, bool slow_gather, const Fetched<R, IP>& q, H& hist,
+                                                      const ET& E_s, R cc, R dd, const PartConst<R>& c, const MeshConst& mc,
+                                                      bool wrap_state, unsigned& err, bool* agg) {
+    const R Ep = apply_gather<R, IP, EXACT_W>(x, f, q, c);
+    const R vn = RT<R>::add(v, RT<R>::mul(RT<R>::mul(dd, -Ep), c.dt));
+    const R xn = MOVE ? RT<R>::add(x, RT<R>::mul(RT<R>::mul(cc, vn), c.dt)) : x;
+    int il; R f2; long long Wa, Wb;
+    const bool slow = slow_gather | fast_cell<R>(xn, c, mc.M, il, f2);
+    deposit_weights<R, IP, EXACT_W>(xn, f2, c, mc, Wa, Wb);
+    if (__builtin_expect(slow, 0)) {
+        particle_careful<R, IP, true, MOVE, EXACT_W>(x, v, il, Wa, Wb, E_s, cc, dd, c, mc, wrap_state, err);
+    } else {
+        x = xn; v = vn;
+    }
+    if (FULL_WARP) {
+        __syncwarp();
         deposit_hinted<IP, PROBE>(hist, il, Wa, Wb, mc.fix_one, *agg);
     } else {
         deposit_one<IP>(hist, il, Wa, Wb, mc.fix_one);
@@ -1023,6 +1081,18 @@ template <typename V> __device__ __forceinline__ V ld_stream(const V* p) {
 #else
     return __ldg(p);
 #endif
+}
+// the same, but not allocated in the L1 at all: the texture-gather kernels keep the L1 for the field table
+__device__ __forceinline__ double2 ld_stream_nol1(const double2* p) {
+    double2 r;
+    asm volatile("ld.global.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ float4 ld_stream_nol1(const float4* p) {
+    float4 r;
+    asm volatile("ld.global.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+    return r;
 }
 template <typename V> __device__ __forceinline__ void st_stream(V* p, const V& v) {
 #if PIC_ST_FLAVOR == 0

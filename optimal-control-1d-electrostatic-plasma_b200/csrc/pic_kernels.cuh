@@ -137,6 +137,7 @@ struct StreamArgs {
     CommArgs comm;                     // fused exchange over peer memory (world <= 1: off)
     double* partial;                   // [n_envs][gridDim.x][2] per-CTA sum v^2, sum v (MODE_FINAL / MODE_INIT)
     unsigned* err;
+    cudaTextureObject_t table_tex;     // TEXG kernels: linear texture over the [n_envs][M] pair table of this sub-stage
 };
 
 // Shared-memory plan of one CTA.  SEPARATE_D: the prefix-sum scratch gets its own region (needed when the density
@@ -148,8 +149,8 @@ __host__ __device__ constexpr size_t hist_region_bytes(int M, int ip) {      // 
 
 template <typename R>
 __host__ __device__ constexpr size_t smem_plan_bytes(int M, int threads, bool separate_d, int ip = IP_CIC,
-                                                     bool second_hist = false) {
-    return (size_t)M * 2 * sizeof(R)                 // gather pair table
+                                                     bool second_hist = false, bool table = true) {
+    return (table ? (size_t)M * 2 * sizeof(R) : 0)   // gather pair table (none: the kernel gathers through a texture)
          + hist_region_bytes(M, ip) * (second_hist ? 2 : 1)   // histogram(s)
          + (separate_d ? (size_t)M * 8 : 0)          // D_s
          + (size_t)(field_scratch_doubles(threads) + threads / 32 + 2) * 8;   // field / reduction scratch
@@ -159,15 +160,15 @@ __host__ __device__ constexpr size_t smem_plan_bytes(int M, int threads, bool se
 struct SmemOffsets { unsigned hist, hist2, D, red, x, v, ext; };
 template <typename R>
 __host__ __device__ inline SmemOffsets smem_offsets(int M, int threads, bool separate_d, int ip = IP_CIC,
-                                                    bool second_hist = false, long long n_resident = 0) {
+                                                    bool second_hist = false, long long n_resident = 0, bool table = true) {
     SmemOffsets o;
-    size_t b = (size_t)M * 2 * sizeof(R);
+    size_t b = table ? (size_t)M * 2 * sizeof(R) : 0;
     o.hist = (unsigned)b;       b += hist_region_bytes(M, ip);
     o.hist2 = (unsigned)b;      if (second_hist) b += hist_region_bytes(M, ip);
     o.D = separate_d ? (unsigned)b : o.hist;
     if (separate_d) b += (size_t)M * 8;
     o.red = (unsigned)b;
-    o.x = (unsigned)smem_plan_bytes<R>(M, threads, separate_d, ip, second_hist);       // resident particle state
+    o.x = (unsigned)smem_plan_bytes<R>(M, threads, separate_d, ip, second_hist, table);   // resident particle state
     o.v = o.x + (unsigned)((n_resident + 1) / 2 * 2 * sizeof(R));
     o.ext = o.v + (unsigned)((n_resident + 1) / 2 * 2 * sizeof(R));                    // resident: E_ext of the step, M doubles
     return o;
@@ -181,8 +182,8 @@ struct SmemLayout {
         hist = base + o.hist; hist2 = base + o.hist2; D_s = (double*)(base + o.D); red = (double*)(base + o.red);
     }
     __device__ __forceinline__ SmemLayout(unsigned char* base, int M, bool separate_d, int ip = IP_CIC,
-                                          bool second_hist = false)
-        : SmemLayout(base, smem_offsets<R>(M, 0, separate_d, ip, second_hist)) {}
+                                          bool second_hist = false, bool table = true)
+        : SmemLayout(base, smem_offsets<R>(M, 0, separate_d, ip, second_hist, 0, table)) {}
 };
 
 struct GlobalRho {
@@ -206,7 +207,10 @@ __device__ __forceinline__ ExtSrc stage_ext(const ActuatorArgs& act, int env, in
 template <int DEP, int IP> struct HistSel { using type = Hist<DEP>; };
 template <int DEP> struct HistSel<DEP, IP_TSC> { using type = HistTSC; };
 
-template <typename R, int THREADS, int UNROLL, int MODE, int DEP, bool EXACT_W, int IP = IP_CIC>
+// TEXG: the gather goes through the texture pipe (TexTable) instead of a shared-memory table.  The table was written to
+// global memory by field_table_kernel, launched between the passes, so these kernels have no field prologue and no
+// table in shared memory: the L1 that the smaller shared-memory carve-out frees holds the 64 KB table.
+template <typename R, int THREADS, int UNROLL, int MODE, int DEP, bool EXACT_W, int IP = IP_CIC, bool TEXG = false>
 __global__ void __launch_bounds__(THREADS) push_stream_kernel(const StreamArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     using V = typename RT<R>::vec;
@@ -215,7 +219,7 @@ __global__ void __launch_bounds__(THREADS) push_stream_kernel(const StreamArgs a
     constexpr bool KICK = (MODE != MODE_INIT);
     constexpr bool SUMS = (MODE == MODE_FINAL || MODE == MODE_INIT);      // these also deposit stage 0 of the next step
     const int tid = threadIdx.x, env = blockIdx.y, M = a.mc.M;
-    SmemLayout<R> sm(smem_raw, M, false, IP, SUMS);
+    SmemLayout<R> sm(smem_raw, M, false, IP, SUMS, !TEXG);
     using H = typename HistSel<DEP, IP>::type;
     H hist; hist.init(sm.hist, M);
     H hist_next; hist_next.init(sm.hist2, M);
@@ -231,7 +235,7 @@ __global__ void __launch_bounds__(THREADS) push_stream_kernel(const StreamArgs a
 
     const bool fused = a.comm.world > 1;
     bool dead = false;                                  // fused exchange timed out: leave the particle state untouched
-    if (KICK) {                                         // D_s aliases the histogram: solve first, then clear
+    if (KICK && !TEXG) {                                // D_s aliases the histogram: solve first, then clear
         const ExtSrc ext = stage_ext(a.act, env, M);
         if (fused) {
             dead = comm_wait(a.comm, a.comm.seq_in, a.err);
@@ -274,11 +278,16 @@ __global__ void __launch_bounds__(THREADS) push_stream_kernel(const StreamArgs a
 
     // x, v: updated in place.  probe: this particle refreshes the tile's aggregation hint (deposit_hinted)
     bool agg = false;
+    const TexTable<R> table{a.table_tex, env * M};
     auto one = [&](R& x, R& v, auto full_warp, auto probe) {
         constexpr bool FW = decltype(full_warp)::value, PROBE = decltype(probe)::value;
         if (REDRIFT) x = drift<R>(x, v, cpre, pc);      // stage 0 / stage 2 drift (its deposit was done a pass ago)
-        particle_substage<R, IP, KICK, MODE != MODE_INIT, EXACT_W, FW, H, PROBE>(x, v, hist, sm.E_s, cc, dd, pc, a.mc, SUMS,
-                                                                                 err, &agg);
+        if constexpr (TEXG)
+            particle_substage<R, IP, KICK, MODE != MODE_INIT, EXACT_W, FW, H, PROBE>(x, v, hist, table, cc, dd, pc, a.mc, SUMS,
+                                                                                     err, &agg);
+        else
+            particle_substage<R, IP, KICK, MODE != MODE_INIT, EXACT_W, FW, H, PROBE>(x, v, hist, sm.E_s, cc, dd, pc, a.mc, SUMS,
+                                                                                     err, &agg);
         if (SUMS) {
             s2 += (double)v * (double)v; s1 += (double)v;
             next_stage0<R, IP, EXACT_W, FW>(x, v, hist_next, cnext, pc, a.mc, err, &agg);
@@ -321,6 +330,10 @@ __global__ void __launch_bounds__(THREADS) push_stream_kernel(const StreamArgs a
     // for the 32-byte stage-1 pass, which already runs at 94 % of the HBM copy rate and only loses from read bursts
     // running ahead of its writes -- so the passes that are bound by HBM alone do without.
     constexpr int PF = (MODE == MODE_KICK || MODE == MODE_FINAL) ? PIC_PREFETCH_TILES : PIC_PREFETCH_TILES_HBM;
+#ifndef PIC_TEX_LD_NOL1
+#define PIC_TEX_LD_NOL1 1
+#endif
+    constexpr bool LD_NOL1 = PIC_TEX_LD_NOL1 != 0;      // texture-gather kernels: the particle stream bypasses the L1
     auto prefetch_tile = [&](long long tile) {
         if (PF > 0 && tid == 0 && tile < n_tiles) {
             prefetch_l2_bulk(xv + tile * TILE, (unsigned)(TILE * sizeof(V)));
@@ -333,6 +346,47 @@ __global__ void __launch_bounds__(THREADS) push_stream_kernel(const StreamArgs a
         prefetch_tile(tile + (long long)PF * gridDim.x);
         const long long base = tile * TILE + tid;
         V xs[UNROLL], vs[UNROLL];
+        if constexpr (TEXG && KICK) {
+            // Texture gather: the fetches of all the tile's particles are issued before the first is consumed (a texture
+            // fetch takes several times as long as a shared load, and the atomics of the deposit are ordering points the
+            // compiler will not move a later particle's fetch across).
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) { xs[u] = LD_NOL1 ? ld_stream_nol1(xv + base + u * THREADS) : ld_stream(xv + base + u * THREADS);
+                                               vs[u] = LD_NOL1 ? ld_stream_nol1(vv + base + u * THREADS) : ld_stream(vv + base + u * THREADS); }
+            R fs[UNROLL * VEC]; bool slowg[UNROLL * VEC]; Fetched<R, IP> qs[UNROLL * VEC];
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) {
+                R* px = reinterpret_cast<R*>(&xs[u]);
+                R* pv = reinterpret_cast<R*>(&vs[u]);
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) {
+                    const int p = u * VEC + e;
+                    if (REDRIFT) px[e] = drift<R>(px[e], pv[e], cpre, pc);
+                    int il;
+                    slowg[p] = fast_cell<R>(px[e], pc, M, il, fs[p]);
+                    il = (int)min((unsigned)il, (unsigned)(M - 1));      // keep the fetch legal on the slow path
+                    qs[p] = fetch_field<R, IP>(il, table, M);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) {
+                R* px = reinterpret_cast<R*>(&xs[u]);
+                R* pv = reinterpret_cast<R*>(&vs[u]);
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) {
+                    const int p = u * VEC + e;
+                    if (p == 0) particle_substage_pre<R, IP, true, EXACT_W, true, H, true>(px[e], pv[e], fs[p], slowg[p], qs[p], hist, table, cc, dd, pc, a.mc, SUMS, err, &agg);
+                    else particle_substage_pre<R, IP, true, EXACT_W, true, H, false>(px[e], pv[e], fs[p], slowg[p], qs[p], hist, table, cc, dd, pc, a.mc, SUMS, err, &agg);
+                    if (SUMS) {
+                        s2 += (double)pv[e] * (double)pv[e]; s1 += (double)pv[e];
+                        next_stage0<R, IP, EXACT_W, true>(px[e], pv[e], hist_next, cnext, pc, a.mc, err, &agg);
+                    }
+                }
+                if (STORE_X) st_stream(xv + base + u * THREADS, xs[u]);
+                st_stream(vv + base + u * THREADS, vs[u]);
+            }
+            continue;
+        }
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u) { xs[u] = ld_stream(xv + base + u * THREADS); vs[u] = ld_stream(vv + base + u * THREADS); }
 #pragma unroll
@@ -421,6 +475,34 @@ __global__ void __launch_bounds__(THREADS) push_stream_kernel(const StreamArgs a
             if (tid == 0) *a.comm.ticket = 0u;
         }
     }
+}
+
+// ----------------------------------------------------------------- field table (texture gather)
+// One CTA per env: the field solve that the streaming kernels otherwise repeat in every CTA's prologue, done once, and
+// the gather table (E_j + ext_j, E_{j+1} + ext_{j+1}) written to global memory for the TEXG kernels of the next pass.
+// The same block_field instance on the same integers: the table holds the same bits as the shared-memory one.
+struct FieldTableArgs {
+    MeshConst mc;
+    const unsigned long long* rho_in;  // [n_envs][M]
+    ActuatorArgs act;
+    void* table;                       // [n_envs][M] pairs of R
+};
+
+template <typename R, int THREADS>
+__global__ void __launch_bounds__(THREADS) field_table_kernel(const FieldTableArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    using P = typename PairT<R>::type;
+    const int env = blockIdx.x, M = a.mc.M, tid = threadIdx.x;
+#ifndef PIC_NO_PDL
+    griddep_launch_dependents();
+    griddep_wait();
+#endif
+    SmemLayout<R> sm(smem_raw, M, false);
+    const ExtSrc ext = stage_ext(a.act, env, M);
+    GlobalRho rho{a.rho_in + (size_t)env * M};
+    block_field<R, THREADS, false, true>(rho, sm.E_s, sm.D_s, sm.red, a.mc, ext, nullptr, nullptr, 0.0, 0.0, [] {});
+    P* out = (P*)a.table + (size_t)env * M;
+    for (int j = tid; j < M; j += THREADS) out[j] = sm.E_s[j];
 }
 
 // ----------------------------------------------------------------- finalize

@@ -291,6 +291,24 @@ class Engine:
     def set_tuning(self, threads=0, per_thread=0, ctas_per_sm=-1):
         self._ck(self._lib.pic_set_tuning(self._h, int(threads), int(per_thread), int(ctas_per_sm)))
 
+    def set_gather(self, route="auto"):
+        """Streaming mode: where the kick's field gather reads the mesh field -- "shared" (table rebuilt in every CTA's
+        prologue), "texture" (one table per sub-stage in global memory, read through the texture pipe), "texture:23"
+        (texture for the listed Yoshida stages only) or "auto"."""
+        if route.startswith("texture:"):
+            code = 0x10 | sum(1 << (int(c) - 1) for c in route[8:])
+        else:
+            code = {"auto": 0, "shared": 1, "texture": 2}[route]
+        self._ck(self._lib.pic_set_gather(self._h, code))
+
+    @property
+    def gather(self):
+        r = C.c_int32()
+        self._ck(self._lib.pic_get_gather(self._h, C.byref(r)))
+        if r.value & 0x10:
+            return "texture:" + "".join(str(i + 1) for i in range(3) if r.value >> i & 1)
+        return {1: "shared", 2: "texture"}[r.value]
+
     def launch_count(self):
         return int(self._lib.pic_kernel_launch_count(self._h))
 

@@ -25,6 +25,8 @@ ap.add_argument("--steps", type=int, default=40)
 ap.add_argument("--precision", default="f64")
 ap.add_argument("--shapes", default="1024x2")
 ap.add_argument("--tag", default="")
+ap.add_argument("--gather", default="auto")
+ap.add_argument("--interpol", default="CIC")
 a = ap.parse_args()
 N, M, L = int(a.n), a.mesh, 50.0
 esz = 4 if a.precision == "f32" else 8
@@ -36,12 +38,13 @@ for dep in a.deps.split(","):
         if dep.endswith("@31"):
             kw["fixed_bits"] = 31
         eng = pic_b200.Engine(N, M, L, 2 / np.sqrt(N / L), mode="streaming", deposit=dep.split("@")[0],
-                              precision=a.precision, **kw)
+                              precision=a.precision, interpol=a.interpol, **kw)
         try:
             eng.set_tuning(th, un, 0)
         except Exception as e:
             print("skip", dep, shape, e)
             continue
+        eng.set_gather(a.gather)
         eng.sample_state("bump-on-tail", seed=42)
         for _ in range(3):
             eng.step_mesh_device(None, 1)
@@ -76,12 +79,12 @@ for dep in a.deps.split(","):
         bytes_ = np.array([4, 3, 4]) * esz * N
         gbs = bytes_ / (t[:3] * 1e-3) / 1e9
         info = eng.launch_info()
-        rec = dict(dep=dep, shape=shape, precision=a.precision, n=N, mesh=M, stage_ms=t.tolist(), gbs=gbs.tolist(),
+        rec = dict(dep=dep, shape=shape, gather=eng.gather, precision=a.precision, n=N, mesh=M, stage_ms=t.tolist(), gbs=gbs.tolist(),
                    step_ms=step_ms, gps=N / (step_ms * 1e-3) / 1e9, flags=eng.error_flags(), info=info,
                    diag=eng.get_diag()[0].tolist())
         out.append(rec)
-        print("%-10s %-7s %s k=%d | ms %s | GB/s %s | step %.3f ms = %.2f G/s = %.3f of %d B roofline | flags %d" % (
-            dep, shape, a.precision, info["fixed_bits"], " ".join("%.3f" % m for m in t), " ".join("%.0f" % g for g in gbs),
+        print("%-10s %-7s %s %s k=%d | ms %s | GB/s %s | step %.3f ms = %.2f G/s = %.3f of %d B roofline | flags %d" % (
+            dep, shape, a.precision, eng.gather, info["fixed_bits"], " ".join("%.3f" % m for m in t), " ".join("%.0f" % g for g in gbs),
             step_ms, rec["gps"], 11 * esz * N / (step_ms * 1e-3) / 6536.7e9, 11 * esz, rec["flags"]), flush=True)
         eng.close()
         torch.cuda.empty_cache()
