@@ -326,6 +326,8 @@ def parity_side_check(rank=0, world=1, device=0, collective="nccl"):
     import pic_b200
     sim = pic_b200.ShardedPIC(PARITY_N, N_MESH, 1.0, L_BOX, 0.1, rank=rank, world_size=world, device=device,
                               collective=collective)
+    if collective == "nccl":       # the gather route the headline workload runs with (AUTO would keep a run this small on
+        sim.engine.set_gather("texture:3")   # the shared-memory table); the routes are bit-identical, so the hash is the same
     sim.sample_state("bump-on-tail", a=0.2, v0=3.0, sigma=1.0, A=0.1, n_mode=2, seed=PARITY_SEED)
     sim.step(None, PARITY_STEPS)
     d = sim.diag()
@@ -333,7 +335,7 @@ def parity_side_check(rank=0, world=1, device=0, collective="nccl"):
     out = {"rho_crc": hashlib.blake2b(np.ascontiguousarray(rho).tobytes(), digest_size=8).hexdigest(),
            "rho_crc_kind": "blake2b-64 of the uint64[4096] fixed-point state density after %d steps" % PARITY_STEPS,
            "fixed_bits": int(k), "pe_mesh": repr(float(d[1])), "sum_v": "%.10e" % float(d[2]),
-           "n_particles": PARITY_N, "seed": PARITY_SEED, "ranks": world}
+           "n_particles": PARITY_N, "seed": PARITY_SEED, "ranks": world, "gather": sim.engine.gather}
     sim.engine.close()
     return out
 
@@ -378,6 +380,8 @@ def run_gpu_arm(args):
     eng = sim.engine
     if args.threads:
         eng.set_tuning(args.threads, args.unroll, args.ctas)
+    if args.gather != "auto":
+        eng.set_gather(args.gather)
     sim.sample_state("bump-on-tail", a=0.2, v0=3.0, sigma=1.0, A=0.1, n_mode=2, seed=42)
     info = eng.launch_info()
     N_local = sim.N_local
@@ -488,6 +492,11 @@ def run_gpu_arm(args):
              "push_stream_kernel<MODE_KICK> (stage 2: kick, drift, deposit; stores v only; 24 B)",
              "push_stream_kernel<MODE_FINAL> (stage 3: stage-2 drift redone on load, kick, drift, wrap, state deposit + "
              "stage-0 deposit of the next step; 32 B)"]
+    route = info.get("gather", "shared")                # which passes gather through the texture pipe (engine.gather)
+    tex_stages = {"shared": "", "texture": "123"}.get(route, route.partition(":")[2])
+    for k in range(3):
+        names[k] += (" [gather: texture pipe; the time includes the one-CTA field_table_kernel launched before the pass]"
+                     if str(k + 1) in tex_stages else " [gather: shared-memory table rebuilt in the prologue]")
     traffic = {}
     try:                                                # DRAM bytes per particle per launch from the committed ncu capture
         with open(os.path.join(ROOT, "profiles", "traffic_r02.json")) as f:
@@ -733,6 +742,7 @@ def main():
     ap.add_argument("--threads", type=int, default=0)
     ap.add_argument("--unroll", type=int, default=0)
     ap.add_argument("--ctas", type=int, default=0)
+    ap.add_argument("--gather", default="auto", help="streaming gather route: auto | shared | texture | texture:<stages>")
     ap.add_argument("--collective", default="nccl", choices=["fused", "nccl"],
                     help="density exchange of the particle-sharded mode: fused peer-memory exchange or ncclAllReduce")
     ap.add_argument("--no-cpu", action="store_true")

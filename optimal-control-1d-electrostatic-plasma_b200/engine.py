@@ -286,6 +286,8 @@ class Engine:
         d = dict(zip(keys, [a.value for a in v]))
         d["mode"] = "resident" if d["mode"] == L.PIC_MODE_RESIDENT else "streaming"
         d["deposit"] = "split32" if d["deposit"] == L.PIC_DEPOSIT_SPLIT32 else "cas64"
+        if d["mode"] == "streaming":
+            d["gather"] = self.gather
         return d
 
     def set_tuning(self, threads=0, per_thread=0, ctas_per_sm=-1):

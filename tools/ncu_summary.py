@@ -20,6 +20,10 @@ KEYS = [
     ("l1tex__data_pipe_lsu_wavefronts_mem_shared_op_atom.sum", "shared-atomic wavefronts"),
     ("smsp__inst_executed_op_shared_atom.sum", "shared-atomic warp instructions"),
     ("l1tex__data_pipe_lsu_wavefronts_mem_shared_op_ld.sum", "shared-load wavefronts"),
+    ("l1tex__data_pipe_tex_wavefronts.avg.pct_of_peak_sustained_elapsed", "TEX data-pipe wavefronts % of peak"),
+    ("l1tex__data_pipe_tex_wavefronts_mem_texture.sum", "texture wavefronts"),
+    ("l1tex__t_sector_pipe_tex_mem_texture_hit_rate.pct", "texture L1 sector hit rate %"),
+    ("smsp__inst_executed_pipe_tex.sum", "texture-pipe warp instructions"),
     ("l1tex__data_bank_conflicts_pipe_lsu_mem_shared_op_atom.sum", "shared-atomic bank conflicts"),
     ("smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio", "stall long_scoreboard"),
     ("smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio", "stall short_scoreboard"),

@@ -15,11 +15,13 @@ if which == "stream":
     th = int(sys.argv[3]) if len(sys.argv) > 3 else 1024
     pt = int(sys.argv[4]) if len(sys.argv) > 4 else 2
     dep = sys.argv[5] if len(sys.argv) > 5 else "split32"
+    gather = sys.argv[6] if len(sys.argv) > 6 else "auto"
     torch.manual_seed(0)
     x = torch.rand(N, dtype=torch.float64, device="cuda") * L
     v = torch.randn(N, dtype=torch.float64, device="cuda") + 3.0 * (torch.rand(N, device="cuda") < 0.1667)
     eng = pic_b200.Engine(N, 4096, L, 2 / np.sqrt(N / L), mode="streaming", deposit=dep)
     eng.set_tuning(th, pt, 0)
+    eng.set_gather(gather)
     eng.set_state_device(x.data_ptr(), v.data_ptr())
     eng.step_mesh(None, 3)
     eng.sync()

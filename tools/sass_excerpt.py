@@ -24,7 +24,9 @@ hist = collections.Counter(op(s) for _, s in ins)
 # the hot loop = the innermost loop around the full-tile loads: the backward branch with the SHORTEST span that
 # encloses four consecutive 128-bit loads (2 x-vectors + 2 v-vectors; 2 in a 24-byte pass ... still >= 2 pairs)
 addr_index = {a: i for i, (a, _) in enumerate(ins)}
-ldg = [i for i, (_, s) in enumerate(ins) if "LDG.E" in s and ".128" in s]
+ldg = [i for i, (_, s) in enumerate(ins) if "LDG.E" in s and ".128" in s and ".NA" in s]
+if len(ldg) < 4:                                        # not a texture-gather kernel: the evict-first loads
+    ldg = [i for i, (_, s) in enumerate(ins) if "LDG.E" in s and ".128" in s]
 best = None
 for i, (a, s) in enumerate(ins):
     m = re.search(r"BRA(?:\.U)?\s+(?:!?U?P\d+,\s*)?0x([0-9a-f]+)", s)
@@ -45,6 +47,8 @@ with open(out, "w") as f:
             % (title, dem, len(ins), len(loop)))
     f.write("## What to look for\n\n")
     checks = [("LDG.E.EF.128 / STG.E.EF.128", "16-byte evict-first particle loads / stores", ["LDG.E.EF.128", "STG.E.EF.128"]),
+              ("LDG.E.NA.128", "texture-gather kernels: 16-byte particle loads that do not allocate in the L1 (it holds the field table)", ["LDG.E.NA.128"]),
+              ("TLD.LZ", "texture-gather kernels: the (E_j, E_j+1) gather as a texture fetch (texture pipe, not the LSU data pipe)", ["TLD"]),
               ("UBLKPF.L2", "bulk L2 prefetch of the tile two iterations ahead (one thread)", ["UBLKPF.L2"]),
               ("DFMA.RM", "floor(x a) by a round-down FMA against the magic constant (cell index bracket, 2 per position)", ["DFMA.RM"]),
               ("ATOMS.ADD / ATOMS.POPC.INC", "native 32-bit shared atomics of the split deposit; no ATOMS.CAST.SPIN (CAS loop)", ["ATOMS.ADD", "ATOMS.POPC.INC.32", "ATOMS.CAST.SPIN"]),
