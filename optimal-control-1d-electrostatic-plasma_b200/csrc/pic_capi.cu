@@ -8,7 +8,10 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <map>
+#include <mutex>
 #include <string>
+#include <tuple>
 #include <vector>
 
 #include "../../include/pic_b200.h"
@@ -147,6 +150,22 @@ int fail(pic_handle* h, int code, const std::string& msg) {
 #define CK(h, call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) \
     return fail(h, PIC_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); } while (0)
 
+// Function attributes belong to a kernel on a device, not to a handle, and handles with different meshes share the
+// kernels: the opt-in dynamic shared-memory limit (and the carve-out preference) therefore only ever GROW -- a small env
+// created after a large one must not pull the limit back under what the large one launches with.
+cudaError_t raise_func_attr(const void* k, cudaFuncAttribute attr, int value) {
+    static std::mutex mu;
+    static std::map<std::tuple<int, const void*, int>, int> current;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> g(mu);
+    int& c = current[std::make_tuple(dev, k, (int)attr)];
+    if (value <= c) return cudaSuccess;
+    cudaError_t e = cudaFuncSetAttribute(k, attr, value);
+    if (e == cudaSuccess) c = value;
+    return e;
+}
+
 void yoshida(double cs[4], double ds[4]) {          // src/env/integration.py:62-69, same evaluation order
     double phi = pow(2.0, 1.0 / 3.0);
     double w0 = (-1) * phi / (2 - phi);
@@ -196,7 +215,7 @@ int configure_gather(pic_handle* h) {
     if (h->resident) return PIC_OK;
     if (h->tableless) {
         const void* ki = stream_kernel_tex(h->f32, h->threads, h->per_thread, MODE_INIT, h->ip);
-        CK(h, cudaFuncSetAttribute(ki, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_init));
+        CK(h, raise_func_attr(ki, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_init));
     }
     if (h->gather_req == PIC_GATHER_SHARED && !h->tableless) return PIC_OK;
     int mask = h->gather_req == PIC_GATHER_AUTO ? kTexAutoStages
@@ -237,14 +256,14 @@ int configure_gather(pic_handle* h) {
         h->smem_tex[i] = h->f32 ? smem_plan_bytes<float>(h->M, h->threads, false, h->ip, second, false)
                                 : smem_plan_bytes<double>(h->M, h->threads, false, h->ip, second, false);
         const void* k = stream_kernel_tex(h->f32, h->threads, h->per_thread, kStageMode[i], h->ip);
-        CK(h, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_tex[i]));
+        CK(h, raise_func_attr(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_tex[i]));
         // the smallest shared-memory carve-out that holds the CTA: everything else of the SM's 256 KB is L1 for the table
         int pct = (int)(((h->smem_tex[i] + 1024) * 100 + prop.sharedMemPerMultiprocessor - 1) / prop.sharedMemPerMultiprocessor);
         if (pct > 100) pct = 100;
-        CK(h, cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+        CK(h, raise_func_attr(k, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
     }
     const void* kt = field_table_kernel_for(h->f32);
-    CK(h, cudaFuncSetAttribute(kt, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    CK(h, raise_func_attr(kt, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                (int)(h->f32 ? smem_plan_bytes<float>(h->M, 1024, false) : smem_plan_bytes<double>(h->M, 1024, false))));
     for (int i = 0; i < 3; ++i) h->tex_stage[i] = (mask >> i) & 1;
     h->texg = mask != 0;
@@ -272,7 +291,7 @@ int configure_launch(pic_handle* h) {
         const void* k = resident_kernel(h);
         if (!k) return fail(h, PIC_EUNSUPPORTED, "no resident kernel variant for threads=" + std::to_string(h->threads) +
                             " cluster=" + std::to_string(h->cluster) + " (clusters: split32 deposit, exact_weights=0)");
-        CK(h, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
+        CK(h, raise_func_attr(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
         h->grid_x = h->n_envs * h->cluster;
         return PIC_OK;
     }
@@ -282,7 +301,7 @@ int configure_launch(pic_handle* h) {
         const void* k = stream_kernel(h, mode);
         if (!k) return fail(h, PIC_EUNSUPPORTED, "no streaming kernel variant for threads=" + std::to_string(h->threads) +
                             " unroll=" + std::to_string(h->per_thread));
-        CK(h, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
+        CK(h, raise_func_attr(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
         int occ = 0;
         CK(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, h->threads, h->smem));
         if (occ < occ_min) occ_min = occ;
@@ -298,7 +317,7 @@ int configure_launch(pic_handle* h) {
     if (h->partial) { cudaFree(h->partial); h->partial = nullptr; }
     CK(h, cudaMalloc(&h->partial, sizeof(double) * 2 * (size_t)h->grid_x * h->n_envs));
     const void* kf = (const void*)&field_finalize_kernel<1024>;
-    CK(h, cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_plan_bytes<double>(h->M, 1024, false)));
+    CK(h, raise_func_attr(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_plan_bytes<double>(h->M, 1024, false)));
     return configure_gather(h);
 }
 

@@ -385,21 +385,21 @@ __global__ void __launch_bounds__(THREADS) push_stream_kernel(const StreamArgs a
                 if (STORE_X) st_stream(xv + base + u * THREADS, xs[u]);
                 st_stream(vv + base + u * THREADS, vs[u]);
             }
-            continue;
-        }
+        } else {
 #pragma unroll
-        for (int u = 0; u < UNROLL; ++u) { xs[u] = ld_stream(xv + base + u * THREADS); vs[u] = ld_stream(vv + base + u * THREADS); }
+            for (int u = 0; u < UNROLL; ++u) { xs[u] = ld_stream(xv + base + u * THREADS); vs[u] = ld_stream(vv + base + u * THREADS); }
 #pragma unroll
-        for (int u = 0; u < UNROLL; ++u) {
-            R* px = reinterpret_cast<R*>(&xs[u]);
-            R* pv = reinterpret_cast<R*>(&vs[u]);
+            for (int u = 0; u < UNROLL; ++u) {
+                R* px = reinterpret_cast<R*>(&xs[u]);
+                R* pv = reinterpret_cast<R*>(&vs[u]);
 #pragma unroll
-            for (int e = 0; e < VEC; ++e) {
-                if (u == 0 && e == 0) one(px[e], pv[e], std::true_type{}, std::true_type{});
-                else one(px[e], pv[e], std::true_type{}, std::false_type{});
+                for (int e = 0; e < VEC; ++e) {
+                    if (u == 0 && e == 0) one(px[e], pv[e], std::true_type{}, std::true_type{});
+                    else one(px[e], pv[e], std::true_type{}, std::false_type{});
+                }
+                if (STORE_X) st_stream(xv + base + u * THREADS, xs[u]);
+                if (KICK) st_stream(vv + base + u * THREADS, vs[u]);
             }
-            if (STORE_X) st_stream(xv + base + u * THREADS, xs[u]);
-            if (KICK) st_stream(vv + base + u * THREADS, vs[u]);
         }
     }
     // ragged remainder (< one tile of vectors) and the scalar tail (N not a multiple of the vector width)

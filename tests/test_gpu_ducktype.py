@@ -103,3 +103,34 @@ def test_write_through_views_then_refresh(mode):
     xa, va = a.get_state(); xb, vb = b.get_state()
     assert np.array_equal(xa, xb) and np.array_equal(va, vb)
     assert np.array_equal(a.get_diag(), b.get_diag())
+
+
+def test_handles_with_different_meshes_share_the_kernels():
+    """Kernel attributes (the opt-in shared-memory limit) belong to the kernel, not to the handle: creating a small env
+    after a large one must not break the large one's launches (several envs of different sizes in one process, as an
+    RL script with a small training env and a large evaluation env has them)."""
+    from pic_b200 import Engine
+    L = 50.0
+    rng = np.random.RandomState(4)
+
+    def make(N, M, gather):
+        e = Engine(N, M, L, 0.01, mode="streaming")
+        e.set_gather(gather)
+        x = rng.uniform(0, L, (1, N)); v = rng.normal(size=(1, N))
+        e.set_state(x, v)
+        return e, x, v
+
+    for gather in ("shared", "texture"):
+        big, xb, vb = make(300_000, 4096, gather)
+        big.step_mesh(None, 1)
+        small, xs, vs = make(40_000, 128, gather)        # same kernels, a fraction of the shared memory
+        small.step_mesh(None, 2)
+        big.step_mesh(None, 1)                           # must still launch with its own (larger) plan
+        alone, _, _ = make(300_000, 4096, gather)
+        alone.set_state(xb, vb)
+        alone.step_mesh(None, 2)
+        for p, q in zip(big.get_state(), alone.get_state()):
+            assert np.array_equal(p, q)
+        assert big.error_flags() == 0 and small.error_flags() == 0
+        for e in (big, small, alone):
+            e.close()
