@@ -149,3 +149,16 @@ def test_batched_env_sharding_covers_all_envs():
     for w in (1, 2, 4, 8):
         owned = [shard_range(B, r, w) for r in range(w)]
         assert sum(b - a for a, b in owned) == B
+
+
+def test_graft_entry_build_is_consistent_with_the_library():
+    """The driver's build check: __graft_entry__.build() compiles (a no-op when up to date), imports the package and
+    asserts the ABI version the library reports -- it must not drift from include/pic_b200.h."""
+    import importlib
+    import re
+    g = importlib.import_module("__graft_entry__")
+    g.build()
+    hdr = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "pic_b200.h")).read()
+    ver = int(re.search(r"#define PIC_B200_ABI_VERSION (\d+)", hdr).group(1))
+    from pic_b200 import _lib
+    assert _lib.load().pic_abi_version() == ver
