@@ -20,7 +20,7 @@ with open(out, "w") as f:
     f.write("# %s\n\n" % title)
     f.write("`ncu --metrics gpu__time_duration.sum --clock-control none -c 400` -- per-launch times are cold-cache and "
             "serialised; compare SHARES.\nTemplate arguments of push_stream_kernel: <real, threads, unroll, MODE (1 kick, "
-            "2 final + next stage-0 deposit, 3 init, 4 kick with the stage-0 drift redone on load), deposit, exact_w, interp>.\n\n")
+            "2 final + next stage-0 deposit, 3 init, 4 kick with the stage-0 drift redone on load), deposit, exact_w, interp, gather through the texture pipe>.\n\n")
     f.write("| kernel | launches | total us | share |\n|---|---|---|---|\n")
     for k, (n, t) in sorted(acc.items(), key=lambda kv: -kv[1][1]):
         f.write("| `%s` | %d | %.1f | %.1f %% |\n" % (k[:120], n, t, 100 * t / tot))
