@@ -35,8 +35,8 @@ for dep in a.deps.split(","):
     for shape in a.shapes.split(","):
         th, un = (int(t) for t in shape.split("x"))
         kw = {}
-        if dep.endswith("@31"):
-            kw["fixed_bits"] = 31
+        if "@" in dep:                                   # e.g. split32@32: fixed_bits = 32
+            kw["fixed_bits"] = int(dep.split("@")[1])
         eng = pic_b200.Engine(N, M, L, 2 / np.sqrt(N / L), mode="streaming", deposit=dep.split("@")[0],
                               precision=a.precision, interpol=a.interpol, **kw)
         try:
