@@ -1052,6 +1052,80 @@ __device__ __forceinline__ void next_stage0(R x_state, R v, H& hist_next, R c0, 
     }
 }
 
+// next_stage0 without the deposit: cell and fixed-point weights of x1 = x_state + (c0 v) dt (used by the packed float32
+// path when a pair falls back to the scalar code; same statements as next_stage0 above)
+template <typename R, int IP, bool EXACT_W>
+__device__ __forceinline__ void next_stage0_compute(R x_state, R v, R c0, const PartConst<R>& c, const MeshConst& mc,
+                                                    unsigned& err, int& il, long long& Wa, long long& Wb) {
+    const R x1 = RT<R>::add(x_state, RT<R>::mul(RT<R>::mul(c0, v), c.dt));
+    R f;
+    const bool slow = fast_cell<R>(x1, c, mc.M, il, f);
+    deposit_weights<R, IP, EXACT_W>(x1, f, c, mc, Wa, Wb);
+    if (__builtin_expect(slow, 0)) {
+        const R xw = wrap_pos<R>(x1, c, err);
+        il = cell_index<R>(xw, c, mc.M, f, err);
+        deposit_weights<R, IP, EXACT_W>(xw, f, c, mc, Wa, Wb);
+    }
+}
+
+// ------------------------------------------------------------- packed float32 pairs
+// float32 mode, CIC: TWO particles per floating-point instruction (sm_100's FFMA2 / FADD2 / FMUL2 on aligned register
+// pairs; the 16-byte particle vector already holds four).  Every lane of a packed instruction is rounded exactly as the
+// scalar instruction it replaces (rn everywhere, rd in the cell bracket; a - b is the single-rounding fma(b, -1, a)), so
+// the pair path produces the same bits as the scalar path: the float32 passes execute the same ~80-130 instructions per
+// particle as the float64 ones on half the bytes and are bound by instruction issue, not by HBM or the LSU pipe.
+// Cell extraction, the table loads and the atomics stay per lane; a particle that needs the careful path is redone by the
+// scalar code (its partner keeps the packed result).
+namespace f32x2 {
+__device__ __forceinline__ float2 bc(float a) { return make_float2(a, a); }
+// a + b as fma(a, 1, b): the same single rounding, but ptxas (12.9) contracts a mul.rn.f32x2 feeding an add.rn.f32x2 into one
+// FFMA2 despite the explicit rounding modifiers -- which would change the bits -- and it does not contract into an fma
+__device__ __forceinline__ float2 add(float2 a, float2 b) { return __ffma2_rn(make_float2(-a.x, -a.y), bc(-1.0f), b); }
+__device__ __forceinline__ float2 mul(float2 a, float2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ float2 sub(float2 a, float2 b) { return __ffma2_rn(b, bc(-1.0f), a); }   // round(a - b), one rounding
+
+// fast_cell for two positions; bad0 / bad1: that lane must take the careful path
+__device__ __forceinline__ void fast_cell(float2 xw, const PartConst<float>& c, int M, int& il0, int& il1, float2& f,
+                                          bool& bad0, bool& bad1) {
+    const float2 t_lo = __ffma2_rd(xw, bc(c.inv_lo), bc(12582912.0f));
+    const float2 t_hi = __ffma2_rd(xw, bc(c.inv_hi), bc(12582912.0f));
+    f = add(t_lo, bc(-12582912.0f));
+    const int a0 = __float_as_int(t_lo.x), a1 = __float_as_int(t_lo.y);
+    il0 = a0 - 0x4B400000; il1 = a1 - 0x4B400000;
+    bad0 = ((a0 >> 22) != (0x4B400000 >> 22)) | (a0 != __float_as_int(t_hi.x)) | ((unsigned)il0 >= (unsigned)M);
+    bad1 = ((a1 >> 22) != (0x4B400000 >> 22)) | (a1 != __float_as_int(t_hi.y)) | ((unsigned)il1 >= (unsigned)M);
+}
+
+__device__ __forceinline__ float2 drift(float2 x, float2 v, float cc, const PartConst<float>& c) {
+    return add(x, mul(mul(bc(cc), v), bc(c.dt)));
+}
+
+// right weights of two wrapped positions with floors f (deposit_weights, CIC, EXACT_W = false)
+__device__ __forceinline__ float2 weight_r(float2 xw, float2 f, const PartConst<float>& c) {
+    return mul(sub(xw, mul(f, bc(c.dx))), bc(c.inv_dx));
+}
+
+// particle_fast<float, IP_CIC, true, true, false> for two particles: gather, kick, drift, cell + weight of the new
+// position; slow0 / slow1: that particle must be redone by particle_careful
+__device__ __forceinline__ void particle_fast(float2 x, float2 v, float2& xn, float2& vn, int& il0, int& il1, float2& wr_dep,
+                                              const float2* __restrict__ E_s, float cc, float dd,
+                                              const PartConst<float>& c, int M, bool& slow0, bool& slow1) {
+    int g0, g1; float2 f;
+    fast_cell(x, c, M, g0, g1, f, slow0, slow1);
+    g0 = (int)min((unsigned)g0, (unsigned)(M - 1)); g1 = (int)min((unsigned)g1, (unsigned)(M - 1));
+    const float2 e0 = E_s[g0], e1 = E_s[g1];
+    const float2 wr = weight_r(x, f, c);                                        // (x - f dx) (1/dx)
+    const float2 wl = mul(sub(mul(add(f, bc(1.0f)), bc(c.dx)), x), bc(c.inv_dx));   // ((f + 1) dx - x) (1/dx)
+    const float2 Ep = add(mul(wl, make_float2(e0.x, e1.x)), mul(wr, make_float2(e0.y, e1.y)));
+    vn = add(v, mul(mul(bc(dd), make_float2(-Ep.x, -Ep.y)), bc(c.dt)));
+    xn = add(x, mul(mul(bc(cc), vn), bc(c.dt)));
+    float2 f2; bool b0, b1;
+    fast_cell(xn, c, M, il0, il1, f2, b0, b1);
+    slow0 |= b0; slow1 |= b1;
+    wr_dep = weight_r(xn, f2, c);
+}
+}  // namespace f32x2
+
 // One thread asks the L2 to fetch a contiguous range ahead of the loads that will consume it (UBLKPF.L2): no registers,
 // no shared memory, one instruction per range.  p 16-byte aligned, bytes a multiple of 16.
 __device__ __forceinline__ void prefetch_l2_bulk(const void* p, unsigned bytes) {

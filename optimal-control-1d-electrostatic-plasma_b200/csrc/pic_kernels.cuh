@@ -293,6 +293,68 @@ __global__ void __launch_bounds__(THREADS) push_stream_kernel(const StreamArgs a
             next_stage0<R, IP, EXACT_W, FW>(x, v, hist_next, cnext, pc, a.mc, err, &agg);
         }
     };
+    // float32, CIC: two particles per floating-point instruction (f32x2 in pic_device.cuh); full tiles only.  px, pv point
+    // at two consecutive particles of a vector.  Same bits as two calls of `one`: the packed lanes round like the scalar
+    // instructions, a pair with a particle that needs the careful path is redone by the scalar code, the kinetic sums are
+    // accumulated in particle order, and the deposits are integers.
+#ifdef PIC_NO_F32X2
+    constexpr bool PAIRS = false;
+#else
+    // stages 1 and 2 only: measured at N = 1e9, 3.31 -> 3.08 ms and 3.15 -> 2.68 ms; the stage-3 pass (two more positions per
+    // particle, both particles' careful blocks inlined) got slower with pairs (5.39 -> 7.65 ms) and keeps the scalar code
+#ifdef PIC_F32X2_FINAL
+    constexpr bool PAIRS = std::is_same<R, float>::value && IP == IP_CIC && !EXACT_W && KICK && !TEXG;
+#else
+    constexpr bool PAIRS = std::is_same<R, float>::value && IP == IP_CIC && !EXACT_W && KICK && !TEXG && !SUMS;
+#endif
+#endif
+    auto pair = [&](R* px, R* pv, auto probe) {
+        if constexpr (PAIRS) {
+            constexpr bool PROBE = decltype(probe)::value;
+            float2 x = make_float2(px[0], px[1]);
+            const float2 v = make_float2(pv[0], pv[1]);
+            if (REDRIFT) x = f32x2::drift(x, v, cpre, pc);
+            float2 xn, vn, wr, wr1;
+            int il[2], jl[2] = {0, 0};
+            long long Wa[2], Wn[2] = {0, 0}, Wb;
+            bool slow[2], slown[2] = {false, false};
+            f32x2::particle_fast(x, v, xn, vn, il[0], il[1], wr, sm.E_s, cc, dd, pc, M, slow[0], slow[1]);
+            if (SUMS) {
+                const float2 x1 = f32x2::drift(xn, vn, cnext, pc);
+                float2 f1;
+                f32x2::fast_cell(x1, pc, M, jl[0], jl[1], f1, slown[0], slown[1]);
+                wr1 = f32x2::weight_r(x1, f1, pc);
+            }
+            R xo[2] = {xn.x, xn.y}, vo[2] = {vn.x, vn.y};
+            Wa[0] = fix_weight((double)wr.x, a.mc.fix_scale); Wa[1] = fix_weight((double)wr.y, a.mc.fix_scale);
+            if (SUMS) { Wn[0] = fix_weight((double)wr1.x, a.mc.fix_scale); Wn[1] = fix_weight((double)wr1.y, a.mc.fix_scale); }
+            if (__builtin_expect(slow[0] | slow[1] | slown[0] | slown[1], 0)) {      // rare; no warp-wide step inside
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {
+                    if (slow[k]) {                      // the whole sub-stage of this particle with the reference semantics
+                        R xs = px[k], vs = pv[k];
+                        if (REDRIFT) xs = drift<R>(xs, vs, cpre, pc);
+                        particle_careful<R, IP, true, true, EXACT_W>(xs, vs, il[k], Wa[k], Wb, sm.E_s, cc, dd, pc, a.mc, SUMS, err);
+                        xo[k] = xs; vo[k] = vs;
+                        if (SUMS) next_stage0_compute<R, IP, EXACT_W>(xs, vs, cnext, pc, a.mc, err, jl[k], Wn[k], Wb);
+                    } else if (SUMS && slown[k]) {      // only the stage-0 position of the next step
+                        next_stage0_compute<R, IP, EXACT_W>(xo[k], vo[k], cnext, pc, a.mc, err, jl[k], Wn[k], Wb);
+                    }
+                }
+            }
+            __syncwarp();                               // reconverge before the warp-wide deposits
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                if (k == 0) deposit_hinted<IP, PROBE>(hist, il[k], Wa[k], 0, a.mc.fix_one, agg);
+                else deposit_hinted<IP, false>(hist, il[k], Wa[k], 0, a.mc.fix_one, agg);
+                if (SUMS) {
+                    s2 += (double)vo[k] * (double)vo[k]; s1 += (double)vo[k];
+                    deposit_hinted<IP, false>(hist_next, jl[k], Wn[k], 0, a.mc.fix_one, agg);
+                }
+                px[k] = xo[k]; pv[k] = vo[k];
+            }
+        }
+    };
     auto vec_pair = [&](long long i, auto full_warp) {      // one 16-byte vector of x and of v
         V xq = ld_stream(xv + i), vq = ld_stream(vv + i);
         R* px = reinterpret_cast<R*>(&xq);
@@ -392,10 +454,18 @@ __global__ void __launch_bounds__(THREADS) push_stream_kernel(const StreamArgs a
             for (int u = 0; u < UNROLL; ++u) {
                 R* px = reinterpret_cast<R*>(&xs[u]);
                 R* pv = reinterpret_cast<R*>(&vs[u]);
+                if constexpr (PAIRS) {
 #pragma unroll
-                for (int e = 0; e < VEC; ++e) {
-                    if (u == 0 && e == 0) one(px[e], pv[e], std::true_type{}, std::true_type{});
-                    else one(px[e], pv[e], std::true_type{}, std::false_type{});
+                    for (int e = 0; e < VEC; e += 2) {
+                        if (u == 0 && e == 0) pair(px + e, pv + e, std::true_type{});
+                        else pair(px + e, pv + e, std::false_type{});
+                    }
+                } else {
+#pragma unroll
+                    for (int e = 0; e < VEC; ++e) {
+                        if (u == 0 && e == 0) one(px[e], pv[e], std::true_type{}, std::true_type{});
+                        else one(px[e], pv[e], std::true_type{}, std::false_type{});
+                    }
                 }
                 if (STORE_X) st_stream(xv + base + u * THREADS, xs[u]);
                 if (KICK) st_stream(vv + base + u * THREADS, vs[u]);
