@@ -223,6 +223,12 @@ int configure_gather(pic_handle* h) {
              : h->gather_req == PIC_GATHER_SHARED ? 0 : (h->gather_req & 0x7);
     if (h->tableless) mask |= 0x4;
     bool have = h->dep == DEP_SPLIT32 && !h->exact_w && !h->fused;
+    {                                               // a linear texture addresses at most maxTexture1DLinear texels
+        size_t max_texels = 0;
+        const cudaChannelFormatDesc fd = h->f32 ? cudaCreateChannelDesc<float2>() : cudaCreateChannelDesc<int4>();
+        if (cudaDeviceGetTexture1DLinearMaxWidth(&max_texels, &fd, h->device) != cudaSuccess ||
+            (size_t)h->M * (size_t)h->n_envs > max_texels) have = false;
+    }
     for (int i = 0; i < 3 && have; ++i) have = stream_kernel_tex(h->f32, h->threads, h->per_thread, kStageMode[i], h->ip) != nullptr;
     if (!have) {
         if (h->tableless)
@@ -230,7 +236,7 @@ int configure_gather(pic_handle* h) {
                                              "(the table-less texture route needs the 1024 x 2 shape and no fused peer exchange)");
         if (h->gather_req != PIC_GATHER_AUTO && h->gather_req != PIC_GATHER_SHARED)
             return fail(h, PIC_EUNSUPPORTED, "gather = texture needs streaming mode, the split32 deposit, exact_weights = 0, "
-                                             "the 1024 x 2 launch shape and no fused peer exchange");
+                                             "the 1024 x 2 launch shape, no fused peer exchange and n_envs * n_mesh within the 1D texture limit");
         return PIC_OK;
     }
     if (h->gather_req == PIC_GATHER_AUTO && !h->tableless) {
