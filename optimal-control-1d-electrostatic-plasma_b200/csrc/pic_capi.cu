@@ -771,7 +771,11 @@ int pic_create(const pic_config* cfg, pic_handle** out) {
     if (k > 50) { drop_handle(h); return fail(nullptr, PIC_EINVAL, "fixed_bits must be <= 50"); }
     h->fixed_bits = k;
     mc.fix_scale = ldexp(1.0, k); mc.inv_fix = ldexp(1.0, -k); mc.fix_one = 1LL << k;
-    mc.idx_thr = (double)h->M * (h->f32 ? ldexp(1.0, -20) : ldexp(1.0, -49));
+    // bracket half-width of the cell index (fast_cell): 16 ulp in float64 (never hit in practice); in float32 every spare
+    // factor costs -- 2 N_mesh eps of all positions take the careful path, and with 32 lanes per warp that is most warps --
+    // so eps = 2^-22 = 4 ulp, the smallest power of two that still brackets the rounded quotient (needs 3 x 2^-24:
+    // rounding of 1/dx, of (1/dx)(1 -+ eps), and of the quotient itself)
+    mc.idx_thr = (double)h->M * (h->f32 ? ldexp(1.0, -22) : ldexp(1.0, -49));
     mc.range_floor = h->ip == IP_TSC ? -(1LL << 61) : -(mc.fix_one << 2);
     h->pcs.d = make_part_const<double>(mc); h->pcs.f = make_part_const<float>(mc);
     mc.field_g = (h->M + 32 * FIELD_VWARPS - 1) / (32 * FIELD_VWARPS);

@@ -812,7 +812,7 @@ __device__ __forceinline__ R drift(R x, R v, R cc, const PartConst<R>& c) {
 template <typename R>
 __device__ __forceinline__ bool fast_cell(R xw, const PartConst<R>& c, int M, int& il, R& f) {
     // Bracket instead of threshold: floor(x a_lo) and floor(x a_hi) with a_lo/hi = (1/dx)(1 -+ eps) are two fused
-    // multiply-adds (round-down, against the magic constant).  eps = 2^-49 (2^-20 in float32) is 8x the relative
+    // multiply-adds (round-down, against the magic constant).  eps = 2^-49 (2^-22 in float32) is 16x (4x) the relative
     // distance between the correctly rounded quotient x/dx and x (1/dx), so when both floors agree every real number
     // in between -- x/dx as IEEE division rounds it included -- has that floor: il == floor(x/dx), bit for bit.  They
     // disagree only within eps of a cell edge (redone exactly on the careful path).  Three fp64-pipe instructions

@@ -60,3 +60,42 @@ def test_f32_large_streaming_invariants():
     H0 = d0[0] + d0[1] * N / L
     assert np.max(np.abs(tr[:, 0] + tr[:, 1] * N / L - H0)) / H0 < 1e-5
     assert eng.error_flags() == 0
+
+
+@pytest.mark.parametrize("M,mode", [(4096, "streaming"), (250, "resident"), (1000, "streaming")])
+def test_f32_cell_edges_deposit_bit_exact(M, mode):
+    """The float32 cell-index bracket (fast_cell, eps = 2^-22) at its worst: positions on every cell edge and 1..8 ulp to
+    either side.  The integer density after set_state must equal, bit for bit, the one built from floor(x / dx) in
+    float32 arithmetic (np.floor of the IEEE quotient) -- a particle put into the neighbouring cell would deposit a
+    weight near 2^k or below zero and change the sum."""
+    from pic_b200 import Engine
+    f = np.float32
+    L = 50.0
+    dx = f(f(L) / f(M)) if False else f(L / M)                # the library rounds the float64 dx to float32
+    edges = (np.arange(M, dtype=np.float64) * (L / M)).astype(f)
+    xs = [edges]
+    for k in (1, 2, 3, 5, 8):
+        up, dn = edges.copy(), edges.copy()
+        for _ in range(k):
+            up = np.nextafter(up, f(np.inf)); dn = np.nextafter(dn, f(-np.inf))
+        xs += [up, dn]
+    rng = np.random.RandomState(3)
+    xs.append(rng.uniform(0, L, 20 * M).astype(f))
+    x = np.concatenate(xs)
+    x = x[(x >= 0) & (x < f(L))]
+    N = x.size
+    eng = Engine(N, M, L, 0.01, precision="f32", mode=mode)
+    eng.set_state(x.astype(np.float64)[None], np.zeros((1, N)))
+    rho, k = eng.get_density_fixed()
+    il = np.floor(x / dx).astype(np.int64)                    # float32 division, then floor
+    assert il.min() >= 0 and il.max() < M
+    wr = ((x - il.astype(f) * dx) * (f(1) / dx)).astype(f)    # the library's weights: separate float32 roundings
+    W = np.rint(wr.astype(np.float64) * 2.0 ** k).astype(np.int64)
+    exp = np.zeros(M, dtype=np.int64)
+    np.add.at(exp, il, (1 << k) - W)
+    np.add.at(exp, (il + 1) % M, W)
+    assert np.array_equal(rho[0].astype(np.int64), exp)
+    got, *_ = eng.get_cells(False, False)
+    assert np.array_equal(got[0], il)
+    assert eng.error_flags() == 0
+    eng.close()

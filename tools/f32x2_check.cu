@@ -37,7 +37,7 @@ int main() {
     const int n = 1 << 22, M = 4096;
     MeshConst mc{};
     mc.M = M; mc.L = 50.0; mc.dx = mc.L / M; mc.inv_dx = 1.0 / mc.dx; mc.dt = 4.4e-4; mc.fix_scale = ldexp(1.0, 41); mc.fix_one = 1ll << 41;
-    mc.idx_thr = M * ldexp(1.0, -20);
+    mc.idx_thr = M * ldexp(1.0, -22);
     PartConst<float> pc = make_part_const<float>(mc);
     std::vector<float> x(n), v(n); std::vector<float2> E(M);
     srand(1);
