@@ -210,6 +210,7 @@ const int kStageMode[3] = {MODE_KICK0, MODE_KICK, MODE_FINAL};     // Yoshida st
 constexpr long long kTexMinParticles = 1ll << 22;
 constexpr int kTexAutoStages = 0x4;                 // bit s-1: stage s
 int configure_gather(pic_handle* h) {
+    CK(h, cudaSetDevice(h->device));                // allocates tables / texture objects and sets kernel attributes
     h->texg = false;
     for (int i = 0; i < 3; ++i) h->tex_stage[i] = false;
     if (h->resident) return PIC_OK;
