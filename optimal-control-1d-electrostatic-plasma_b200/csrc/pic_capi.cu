@@ -768,6 +768,9 @@ int pic_create(const pic_config* cfg, pic_handle** out) {
         k = 62 - (int)ceil(log2(8.0 * per_cell));
         if (k > 50) k = 50;
         if (k < 20) k = 20;
+        // float32 particles carry 24-bit weights: 24 fractional bits lose nothing, a weight then fits the low word of
+        // the split deposit and the high word only sees (rare) carries -- see HistSplit32<RARE_HI>
+        if (h->f32 && k > 24) k = 24;
     }
     if (k > 50) { drop_handle(h); return fail(nullptr, PIC_EINVAL, "fixed_bits must be <= 50"); }
     h->fixed_bits = k;

@@ -349,10 +349,20 @@ template <int OFF> __device__ __forceinline__ unsigned atom_shared_u32_at(unsign
     return old;
 }
 
+// the same, issued only by the lanes whose addend is non-zero (a predicated ATOMS, no branch): lanes that are
+// predicated off cost no data-pipe wavefront
+template <int OFF> __device__ __forceinline__ void red_shared_u32_at_nonzero(unsigned addr, unsigned v) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %1, 0;\n\t@p red.shared.add.u32 [%0+%2], %1;\n\t}"
+                 ::"r"(addr), "r"(v), "n"(OFF) PIC_ATOM_CLOBBER);
+}
+
 // Layout: three words per cell side by side (cnt, S.lo, S.hi), so one address computation serves all three atomics
 // (immediate offsets 0 / 4 / 8).  The stride of 3 words is coprime with the 32 banks: random cells spread over the
 // banks exactly as three separate arrays would, and a flush that walks the cells in order is conflict-free.
-template <> struct Hist<DEP_SPLIT32> {
+// RARE_HI (Hist<DEP_SPLIT32_RARE>, the float32 kernels): with at most 32 fractional bits a particle's weight fits the
+// low word, the high word only ever receives carries, and those are rare (one deposit in 2^(32-k+1) on average) -- the
+// third atomic is predicated on its addend and all but disappears from the LSU data pipe.  Same integers either way.
+template <bool RARE_HI> struct HistSplit32 {
     unsigned* w;
     unsigned w_a;                        // the same array as a shared-window byte address
     int M;
@@ -370,7 +380,8 @@ template <> struct Hist<DEP_SPLIT32> {
         red_shared_u32_at<0>(cell, count);
         unsigned hi_add;                               // wh + carry-out of (old + wl): one add with carry-out, one with carry-in
         asm("{\n\t.reg .u32 t;\n\tadd.cc.u32 t, %1, %2;\n\taddc.u32 %0, %3, 0;\n\t}" : "=r"(hi_add) : "r"(old), "r"(wl), "r"(wh));
-        red_shared_u32_at<8>(cell, hi_add);
+        if (RARE_HI) red_shared_u32_at_nonzero<8>(cell, hi_add);
+        else red_shared_u32_at<8>(cell, hi_add);
     }
     __device__ __forceinline__ void deposit(int il, long long Wr, long long one) {
         deposit_group(il, (unsigned long long)Wr, 1u, one);
@@ -382,6 +393,9 @@ template <> struct Hist<DEP_SPLIT32> {
         return (unsigned long long)w[3 * j] * (unsigned long long)one - S(j) + S(j == 0 ? M - 1 : j - 1);
     }
 };
+constexpr int DEP_SPLIT32_RARE = 2;       // internal: selected by HistSel for float32, never requested through the C ABI
+template <> struct Hist<DEP_SPLIT32> : HistSplit32<false> {};
+template <> struct Hist<DEP_SPLIT32_RARE> : HistSplit32<true> {};
 
 // TSC (3-point) deposit, src/env/interpolate.py:22-44: a particle in cell m gives W_l to cell m-1, W_r to cell m+1 and
 // 2^k - W_l - W_r to its own cell (the reference's three weights sum to one; the middle one may be negative, which

@@ -204,8 +204,9 @@ __device__ __forceinline__ ExtSrc stage_ext(const ActuatorArgs& act, int env, in
     return e;
 }
 
-template <int DEP, int IP> struct HistSel { using type = Hist<DEP>; };
-template <int DEP> struct HistSel<DEP, IP_TSC> { using type = HistTSC; };
+template <int DEP, int IP, typename R = double> struct HistSel { using type = Hist<DEP>; };
+template <int DEP, typename R> struct HistSel<DEP, IP_TSC, R> { using type = HistTSC; };
+template <> struct HistSel<DEP_SPLIT32, IP_CIC, float> { using type = Hist<DEP_SPLIT32_RARE>; };   // float32: fixed_bits <= 24
 
 // TEXG: the gather goes through the texture pipe (TexTable) instead of a shared-memory table.  The table was written to
 // global memory by field_table_kernel, launched between the passes, so these kernels have no field prologue and no
@@ -220,7 +221,7 @@ __global__ void __launch_bounds__(THREADS) push_stream_kernel(const StreamArgs a
     constexpr bool SUMS = (MODE == MODE_FINAL || MODE == MODE_INIT);      // these also deposit stage 0 of the next step
     const int tid = threadIdx.x, env = blockIdx.y, M = a.mc.M;
     SmemLayout<R> sm(smem_raw, M, false, IP, SUMS, !TEXG);
-    using H = typename HistSel<DEP, IP>::type;
+    using H = typename HistSel<DEP, IP, R>::type;
     H hist; hist.init(sm.hist, M);
     H hist_next; hist_next.init(sm.hist2, M);
     #ifdef PIC_DEVICE_PARTCONST                          // experiment: recompute the constants in registers (round-1 behaviour)
@@ -698,7 +699,7 @@ __global__ void __launch_bounds__(THREADS, THREADS <= 512 ? 1024 / THREADS : 1) 
     R* x_s = (R*)(smem_raw + a.lay.x);
     R* v_s = (R*)(smem_raw + a.lay.v);
     double* ext_s = (double*)(smem_raw + a.lay.ext);
-    using H = typename HistSel<DEP, IP>::type;
+    using H = typename HistSel<DEP, IP, R>::type;
     H hist; hist.init(sm.hist, M);
     #ifdef PIC_DEVICE_PARTCONST                          // experiment: recompute the constants in registers (round-1 behaviour)
     const PartConst<R> pc = make_part_const<R>(a.mc);
@@ -894,7 +895,7 @@ __global__ void __launch_bounds__(THREADS, THREADS <= 512 ? 1024 / THREADS : 1) 
     R* v_s = (R*)(smem_raw + a.lay.v);
     double* ext_s = (double*)(smem_raw + a.lay.ext);
     double* part_s = ext_s + M;                               // [NW][2] per-warp sum v^2, sum v of the final sub-stage
-    using H = typename HistSel<DEP_SPLIT32, IP>::type;
+    using H = typename HistSel<DEP_SPLIT32, IP, R>::type;
     // Two histogram buffers; sub-stage s of an env step uses buffer s & 1 (four sub-stages per step: every step starts
     // on buffer 0), so the buffer is a compile-time constant everywhere below and everything stays in registers.
     H hist0, hist1;
