@@ -666,7 +666,15 @@ def run_gpu_arm(args):
             ks = 500 if Nm <= 1_000_000 else 100
             t0 = time.perf_counter(); em.step_mesh_device(None, ks); em.sync()
             us = (time.perf_counter() - t0) / ks * 1e6
-            mids.append({"n_particles": Nm, "n_mesh": Mm, "us_per_step": us, "particle_steps_per_s": Nm / (us * 1e-6)})
+            t0 = time.perf_counter()
+            for _ in range(ks):
+                em.step_mesh_device(None, 1)
+            em.sync()
+            us1 = (time.perf_counter() - t0) / ks * 1e6
+            on, workers = em.coop
+            mids.append({"n_particles": Nm, "n_mesh": Mm, "us_per_step": us, "particle_steps_per_s": Nm / (us * 1e-6),
+                         "call": "%d steps in one call%s" % (ks, " (one cooperative launch, %d pass CTAs + 1 finalize CTA)" % workers if on else ""),
+                         "us_per_one_step_call": us1})
             em.close()
         single["mid_size"] = mids
 

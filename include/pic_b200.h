@@ -26,7 +26,7 @@ extern "C" {
 #pragma GCC visibility push(default)   /* the library is built with -fvisibility=hidden; these are its exports */
 #endif
 
-#define PIC_B200_ABI_VERSION 3
+#define PIC_B200_ABI_VERSION 4
 
 enum { PIC_OK = 0, PIC_EINVAL = -1, PIC_ENODEVICE = -2, PIC_ECUDA = -3, PIC_ENOMEM = -4, PIC_ESTATE = -5,
        PIC_ENUMERIC = -6, PIC_ENCCL = -7, PIC_EUNSUPPORTED = -8 };
@@ -216,6 +216,21 @@ int pic_set_tuning(pic_handle* h, int32_t threads, int32_t unroll_or_cluster, in
 #define PIC_GATHER_TEXTURE_STAGES(mask) (0x10 | ((mask) & 0x7))
 int pic_set_gather(pic_handle* h, int32_t route);
 int pic_get_gather(pic_handle* h, int32_t* route);
+/* streaming mode, one GPU: run whole env steps (any n_steps of a call) as ONE cooperative launch -- the three passes
+ * separated by grid barriers, the finalize of a step on a CTA of its own beside the first pass of the next -- instead
+ * of four launches per step.  Pays for mid-size envs (1e4 .. a few 1e7 particles), whose step is bound by what sits
+ * between the passes, not by the particles.  Identical bits in x, v, densities and fields (the kinetic partial sums are
+ * added over workers instead of CTAs, as with any other grid size).  PIC_COOP_AUTO (default): used for calls of two or
+ * more steps on up to 2^24 particles per handle when available (a lone step gains nothing: a cooperative launch costs
+ * more than a plain one, and there is no next pass to hide the finalize behind); PIC_COOP_ON: every call, fails with
+ * PIC_EUNSUPPORTED when unavailable (it needs CIC, the split32 deposit, exact_weights = 0, the 1024 x 2 shape, the
+ * shared-memory gather, no spectral read-out, no sharding).  pic_get_coop reports whether a multi-step call takes this
+ * path and with how many pass CTAs per env. */
+#define PIC_COOP_AUTO (-1)
+#define PIC_COOP_OFF 0
+#define PIC_COOP_ON 1
+int pic_set_coop(pic_handle* h, int32_t mode);
+int pic_get_coop(pic_handle* h, int32_t* in_effect, int32_t* workers);
 int64_t pic_kernel_launch_count(const pic_handle* h);        /* kernels enqueued by this handle so far */
 
 #if defined(__GNUC__)

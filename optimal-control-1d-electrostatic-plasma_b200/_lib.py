@@ -94,6 +94,8 @@ SIGNATURES = {
     "pic_set_tuning": (C.c_int, [_H, C.c_int32, C.c_int32, C.c_int32]),
     "pic_set_gather": (C.c_int, [_H, C.c_int32]),
     "pic_get_gather": (C.c_int, [_H, C.POINTER(C.c_int32)]),
+    "pic_set_coop": (C.c_int, [_H, C.c_int32]),
+    "pic_get_coop": (C.c_int, [_H, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "pic_kernel_launch_count": (C.c_int64, [_H]),
 }
 

@@ -19,7 +19,7 @@ OBJDIR = os.path.join(ROOT, "build", "pic_b200")
 LIB = os.path.join(LIBDIR, "libpic_b200.so")
 
 SOURCES = ["pic_stream_f64_a.cu", "pic_stream_f64_b.cu", "pic_stream_f64_c.cu", "pic_stream_f32.cu",
-           "pic_stream_tex.cu", "pic_resident.cu", "pic_cluster.cu", "pic_tsc.cu", "pic_capi.cu", "pic_variants.cu"]
+           "pic_stream_tex.cu", "pic_coop.cu", "pic_resident.cu", "pic_cluster.cu", "pic_tsc.cu", "pic_capi.cu", "pic_variants.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr"]
 NVCC_FLAGS += os.environ.get("PIC_EXTRA_NVCC_FLAGS", "").split()     # experiments, e.g. -DPIC_ST_FLAVOR=1

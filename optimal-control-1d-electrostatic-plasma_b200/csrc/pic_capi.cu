@@ -132,6 +132,14 @@ struct pic_handle {
     bool tableless = false;
     size_t smem_init = 0;
 
+    // whole steps in one cooperative launch (step_coop_kernel): mid-size envs, single GPU
+    int coop_req = PIC_COOP_AUTO;                   // what the caller asked for
+    bool coop_ok = false;                           // a kernel variant exists and its grid is co-resident on this device
+    int coop_workers = 0;                           // pass CTAs per env (one more CTA per env does the finalize)
+    size_t coop_smem = 0;
+    unsigned long long* coop_bar = nullptr;         // grid-barrier arrival counter (monotonic) ...
+    unsigned long long coop_bar_count = 0;          // ... and its value after everything launched so far
+
     long long launches = 0;
     std::string last_error;
 };
@@ -277,6 +285,54 @@ int configure_gather(pic_handle* h) {
     return PIC_OK;
 }
 
+// Whole steps in one cooperative launch (step_coop_kernel).  Available when a kernel variant exists for the handle's
+// flavour (CIC, split32, 1024 x 2, shared-memory gather) and workers + one finalize CTA per env are co-resident.
+// AUTO takes it for calls of two or more steps on envs up to kCoopMaxParticles (overridable: PIC_COOP_MAX_PARTICLES).
+// Measured (one B200, float64, us per step inside a multi-step call, kernel-per-pass -> cooperative): 2e4 particles /
+// 250 cells 26.7 -> 23.4, 1e6 / 1024 42.7 -> 36.6, 1e6 / 4096 62.6 -> 51.8, 3e6 / 4096 86.3 -> 75.7, 1e7 / 4096
+// 194.7 -> 189.7, 3e7 equal, 1e8 0.5 % slower (the kernel-per-pass path has the texture-pipe stage 3).  One-step calls
+// are no faster (2e4: 32.8 = 32.8) or slower (1e6: 43.5 -> 47.2 us: a cooperative launch costs more than a plain one and
+// a lone step has no next pass to hide its finalize behind), so AUTO leaves them on the kernel-per-pass path.
+constexpr long long kCoopMaxParticles = 1ll << 24;
+int configure_coop(pic_handle* h) {
+    h->coop_ok = false;
+    if (h->resident || h->tableless) return PIC_OK;
+    const void* k = coop_kernel(h->f32, h->threads, h->per_thread, h->dep, h->exact_w, h->ip);
+    int can = 0;
+    if (!k || cudaDeviceGetAttribute(&can, cudaDevAttrCooperativeLaunch, h->device) != cudaSuccess || !can) return PIC_OK;
+    size_t smem = smem_plan_bytes<double>(h->M, 1024, false);          // the finalize CTA's plan
+    if (h->smem > smem) smem = h->smem;
+    if ((int)smem > h->max_smem) return PIC_OK;
+    CK(h, raise_func_attr(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 0;
+    CK(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, h->threads, smem));
+    const long long per_env = (long long)h->sm_count * occ / h->n_envs;  // co-resident CTAs an env can have
+    if (per_env < 2) return PIC_OK;
+    h->coop_workers = (int)(per_env - 1 < h->grid_x ? per_env - 1 : h->grid_x);
+    h->coop_smem = smem;
+    if (!h->coop_bar) {
+        CK(h, cudaMalloc(&h->coop_bar, sizeof(unsigned long long)));
+        CK(h, cudaMemsetAsync(h->coop_bar, 0, sizeof(unsigned long long), h->stream));
+        h->coop_bar_count = 0;
+    }
+    h->coop_ok = true;
+    return PIC_OK;
+}
+long long coop_max_particles() {
+    static const long long v = [] {
+        const char* e = getenv("PIC_COOP_MAX_PARTICLES");
+        return e && *e ? atoll(e) : kCoopMaxParticles;
+    }();
+    return v;
+}
+// does a step_device call of n_steps steps go through the cooperative kernel?
+bool coop_in_effect(const pic_handle* h, int n_steps) {
+    if (!h->coop_ok || h->coop_req == PIC_COOP_OFF || h->world > 1 || h->fused || h->n_modes > 0) return false;
+    if (h->gather_req != PIC_GATHER_AUTO && h->gather_req != PIC_GATHER_SHARED) return false;   // an explicit texture route
+    if (h->coop_req == PIC_COOP_ON) return true;
+    return n_steps >= 2 && h->N * (long long)h->n_envs <= coop_max_particles();
+}
+
 int configure_launch(pic_handle* h) {
     h->smem = smem_for(h);
     h->tableless = false;
@@ -325,7 +381,8 @@ int configure_launch(pic_handle* h) {
     CK(h, cudaMalloc(&h->partial, sizeof(double) * 2 * (size_t)h->grid_x * h->n_envs));
     const void* kf = (const void*)&field_finalize_kernel<1024>;
     CK(h, raise_func_attr(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_plan_bytes<double>(h->M, 1024, false)));
-    return configure_gather(h);
+    int rc = configure_gather(h);
+    return rc ? rc : configure_coop(h);
 }
 
 int comm_slot_len(const pic_handle* h) { return 2 * h->M * h->n_envs + 2 * h->n_envs; }
@@ -478,6 +535,42 @@ __global__ void kl_kernel(const unsigned* __restrict__ counts, const double* __r
     if (threadIdx.x == 0) kl[env] = acc * dxdv;
 }
 
+// arguments of one streaming pass: stage 1..3 = Yoshida stages, -1 = init deposit (comm is left to the caller).
+// overlap: the flavour of the buffer clearing that lets the finalize of a step run beside the first pass of the next
+// (run_stage below, and always inside the cooperative step kernel).
+StreamArgs stream_args(const pic_handle* h, int stage, const double* ext, const double* coeffs, bool overlap, int* mode,
+                       unsigned long long** reduce, size_t* reduce_count) {
+    StreamArgs a{};
+    a.mc = h->mc; a.pcs = h->pcs; a.x = h->x; a.v = h->v; a.N = h->N; a.ld = h->ld;
+    a.act.ext = ext; a.act.coeffs = coeffs; a.act.bcos = h->bcos; a.act.bsin = h->bsin; a.act.m = h->m;
+    a.partial = h->partial; a.err = h->err; a.c_next = h->cs[0];
+    const size_t sz = (size_t)h->M * h->n_envs;
+    *reduce_count = sz;
+    switch (stage) {
+        case -1: *mode = MODE_INIT; a.rho_out = h->rho[3]; a.rho_next = h->rho[0]; a.c = 0; a.d = 0;
+                 *reduce = h->rho[3]; *reduce_count = 2 * sz; break;
+        case 1: *mode = MODE_KICK0; a.c_pre = h->cs[0]; a.rho_in = h->rho[0]; a.rho_out = h->rho[1];
+                a.rho_zero = overlap ? nullptr : h->rho[3]; *reduce = h->rho[1]; break;
+        case 2: *mode = MODE_KICK; a.rho_in = h->rho[1]; a.rho_out = h->rho[2]; a.rho_zero = h->rho[0];
+                a.rho_zero2 = overlap ? h->rho[3] : nullptr; *reduce = h->rho[2]; break;
+        default: *mode = MODE_FINAL; a.c_pre = h->cs[2]; a.rho_in = h->rho[2]; a.rho_out = h->rho[3]; a.rho_next = h->rho[0];
+                a.rho_zero = h->rho[1]; *reduce = h->rho[3]; *reduce_count = 2 * sz; break;
+    }
+    if (stage >= 1) { a.c = h->cs[stage]; a.d = h->ds[stage]; }
+    return a;
+}
+
+FinalizeArgs finalize_args(const pic_handle* h, const double* coeffs, double* trace_row) {
+    FinalizeArgs f{};
+    f.mc = h->mc; f.rho = h->rho[3]; f.rho_zero = h->rho[2]; f.n_out = h->n; f.E_out = h->E; f.diag = h->diag;
+    f.partial = h->partial; f.vsum = h->vsum; f.n_partial = h->grid_x;
+    f.rw = h->rw; f.coeffs = coeffs; f.two_m = 2 * h->m; f.step_done = trace_row != nullptr;
+    f.tw_cos = h->tw_cos; f.tw_sin = h->tw_sin; f.n_modes = h->n_modes; f.modes = h->n_modes > 0 ? h->modes : nullptr;
+    fill_comm(h, f.comm, h->seq_state, 0, 0, nullptr, 0);
+    f.rho_reduced = h->rho[3]; f.err = h->err; f.trace_row = trace_row;
+    return f;
+}
+
 // one streaming sub-stage: stage 0..3 = Yoshida stages, 4 = finalize, -1 = init deposit.
 // overlap (single GPU, inside a multi-step call): the finalize of a step runs on `fin_on` beside the first pass of the
 // next step; that pass then must not clear the state density the finalize is reading -- the stage-2 pass, which is
@@ -486,14 +579,9 @@ int run_stage(pic_handle* h, int stage, const double* ext, const double* coeffs,
               cudaStream_t fin_on = nullptr) {
     if (stage == 4) {
         cudaStream_t fs = fin_on ? fin_on : h->stream;
-        FinalizeArgs f{};
-        f.mc = h->mc; f.rho = h->rho[3]; f.rho_zero = h->rho[2]; f.n_out = h->n; f.E_out = h->E; f.diag = h->diag;
-        f.partial = h->partial; f.vsum = h->vsum; f.n_partial = h->grid_x;
-        f.rw = h->rw; f.coeffs = coeffs; f.two_m = 2 * h->m; f.step_done = trace_row != nullptr;
-        f.tw_cos = h->tw_cos; f.tw_sin = h->tw_sin; f.n_modes = h->n_modes; f.modes = h->n_modes > 0 ? h->modes : nullptr;
-        fill_comm(h, f.comm, h->seq_state, 0, 0, nullptr, 0);
         const bool nccl_sharded = h->world > 1 && !h->fused;
-        f.rho_reduced = h->rho[3]; f.err = h->err; f.trace_row = nccl_sharded ? nullptr : trace_row;
+        FinalizeArgs f = finalize_args(h, coeffs, nccl_sharded ? nullptr : trace_row);
+        f.step_done = trace_row != nullptr;
         void* args[] = {&f};
         CK(h, launch_pdl((const void*)&field_finalize_kernel<1024>, dim3(h->n_envs), dim3(1024), args,
                          smem_plan_bytes<double>(h->M, 1024, false), fs));
@@ -507,25 +595,11 @@ int run_stage(pic_handle* h, int stage, const double* ext, const double* coeffs,
         return PIC_OK;
     }
     if (stage == 0) return PIC_OK;      // stage 0 (pure drift): deposited ahead of time by stage 3 / init, redone by stage 1
-    StreamArgs a{};
-    a.mc = h->mc; a.pcs = h->pcs; a.x = h->x; a.v = h->v; a.N = h->N; a.ld = h->ld;
-    a.act.ext = ext; a.act.coeffs = coeffs; a.act.bcos = h->bcos; a.act.bsin = h->bsin; a.act.m = h->m;
-    a.partial = h->partial; a.err = h->err; a.c_next = h->cs[0];
-    const size_t sz = (size_t)h->M * h->n_envs;
+    if (stage != -1 && (stage < 1 || stage > 3)) return fail(h, PIC_EINVAL, "stage must be -1..4");
     int mode;
-    unsigned long long* reduce = nullptr; size_t reduce_count = sz;
-    switch (stage) {
-        case -1: mode = MODE_INIT; a.rho_out = h->rho[3]; a.rho_next = h->rho[0]; a.c = 0; a.d = 0;
-                 reduce = h->rho[3]; reduce_count = 2 * sz; break;
-        case 1: mode = MODE_KICK0; a.c_pre = h->cs[0]; a.rho_in = h->rho[0]; a.rho_out = h->rho[1];
-                a.rho_zero = overlap ? nullptr : h->rho[3]; reduce = h->rho[1]; break;
-        case 2: mode = MODE_KICK; a.rho_in = h->rho[1]; a.rho_out = h->rho[2]; a.rho_zero = h->rho[0];
-                a.rho_zero2 = overlap ? h->rho[3] : nullptr; reduce = h->rho[2]; break;
-        case 3: mode = MODE_FINAL; a.c_pre = h->cs[2]; a.rho_in = h->rho[2]; a.rho_out = h->rho[3]; a.rho_next = h->rho[0];
-                a.rho_zero = h->rho[1]; reduce = h->rho[3]; reduce_count = 2 * sz; break;
-        default: return fail(h, PIC_EINVAL, "stage must be -1..4");
-    }
-    if (stage >= 1) { a.c = h->cs[stage]; a.d = h->ds[stage]; }
+    unsigned long long* reduce = nullptr; size_t reduce_count = 0;
+    StreamArgs a = stream_args(h, stage, ext, coeffs, overlap, &mode, &reduce, &reduce_count);
+    const size_t sz = (size_t)h->M * h->n_envs;
     if (stage == -1) CK(h, cudaMemsetAsync(h->rho_block, 0, sizeof(unsigned long long) * 4 * sz, h->stream));
     if (h->fused) {
         // consume: stage 1 reads the next-stage-0 half of the exchange that carried the state (offset sz), stages 2, 3
@@ -616,6 +690,32 @@ int launch_resident(pic_handle* h, int n_steps, const double* ext, const double*
     return PIC_OK;
 }
 
+// n_steps env steps in one cooperative launch (see step_coop_kernel)
+int launch_coop(pic_handle* h, int n_steps, const double* ext, const double* coeffs) {
+    CoopArgs c{};
+    int mode; unsigned long long* reduce; size_t reduce_count;
+    for (int st = 1; st <= 3; ++st) {
+        c.s[st - 1] = stream_args(h, st, ext, coeffs, true, &mode, &reduce, &reduce_count);
+        fill_comm(h, c.s[st - 1].comm, 0, 0, 0, nullptr, 0);
+    }
+    c.f = finalize_args(h, coeffs, h->trace);
+    c.f.n_partial = h->coop_workers;
+    c.n_steps = n_steps; c.coeff_step_stride = (long long)h->n_envs * 2 * h->m; c.trace = h->trace;
+    c.barrier = h->coop_bar; c.barrier_base = h->coop_bar_count; c.n_workers = (unsigned)h->coop_workers;
+    const dim3 grid(h->coop_workers + 1, h->n_envs);
+    void* args[] = {&c};
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = dim3(h->threads); cfg.dynamicSmemBytes = h->coop_smem; cfg.stream = h->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeCooperative;
+    at[0].val.cooperative = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    CK(h, cudaLaunchKernelExC(&cfg, coop_kernel(h->f32, h->threads, h->per_thread, h->dep, h->exact_w, h->ip), args));
+    h->coop_bar_count += 3ull * (unsigned long long)n_steps * grid.x * grid.y;
+    h->launches++;
+    return PIC_OK;
+}
+
 // advance n_steps; ext / coeffs are DEVICE pointers (coeffs: [n_steps][n_envs][2m])
 int step_device(pic_handle* h, const double* ext, const double* coeffs, int n_steps) {
     if (!h->have_state) return fail(h, PIC_ESTATE, "pic_set_state has not been called");
@@ -624,6 +724,7 @@ int step_device(pic_handle* h, const double* ext, const double* coeffs, int n_st
     int rc = ensure_trace(h, n_steps);
     if (rc) return rc;
     if (h->resident) return launch_resident(h, n_steps, ext, coeffs);
+    if (coop_in_effect(h, n_steps)) return launch_coop(h, n_steps, ext, coeffs);
     // Single GPU, several steps in one call: the finalize of step s (one CTA: state density -> field, energies,
     // reward) runs on a side stream beside the first pass of step s + 1, which needs nothing it produces.  The side
     // stream is joined before the stage-2 pass (which clears the buffers the finalize read / cleared) and at the end of
@@ -865,7 +966,7 @@ int pic_destroy(pic_handle* h) {
     if (h->own_comm && h->comm && nccl_api().destroy) nccl_api().destroy(h->comm);
     void* bufs[] = {h->x, h->v, h->rho_block, h->n, h->E, h->diag, h->vsum, h->partial,
                     h->ext, h->coeffs, h->bcos, h->bsin, h->trace, h->stage64, h->err, h->tw_cos, h->tw_sin, h->modes,
-                    h->mode_trace, h->ph_counts, h->ph_feq, h->ph_kl, h->ticket};
+                    h->mode_trace, h->ph_counts, h->ph_feq, h->ph_kl, h->ticket, h->coop_bar};
     for (void* b : bufs) if (b) cudaFree(b);
     for (int i = 0; i < 3; ++i) {
         if (h->table_tex[i]) cudaDestroyTextureObject(h->table_tex[i]);
@@ -924,6 +1025,33 @@ int pic_get_gather(pic_handle* h, int32_t* route) {
     if (!h || !route) return PIC_EINVAL;
     const int mask = (h->tex_stage[0] ? 1 : 0) | (h->tex_stage[1] ? 2 : 0) | (h->tex_stage[2] ? 4 : 0);
     *route = mask == 0 ? PIC_GATHER_SHARED : mask == 7 ? PIC_GATHER_TEXTURE : PIC_GATHER_TEXTURE_STAGES(mask);
+    return PIC_OK;
+}
+
+int pic_set_coop(pic_handle* h, int32_t mode) {
+    if (!h) return PIC_EINVAL;
+    if (mode != PIC_COOP_AUTO && mode != PIC_COOP_OFF && mode != PIC_COOP_ON)
+        return fail(h, PIC_EINVAL, "mode must be PIC_COOP_AUTO, PIC_COOP_OFF or PIC_COOP_ON");
+    if (mode == PIC_COOP_ON) {
+        const int r0 = h->coop_req;
+        h->coop_req = mode;
+        if (!coop_in_effect(h, 1)) {
+            h->coop_req = r0;
+            return fail(h, PIC_EUNSUPPORTED, "the cooperative step needs streaming mode on one GPU, CIC, the split32 deposit, "
+                        "exact_weights = 0, the 1024 x 2 launch shape, the shared-memory gather, no spectral read-out, and "
+                        "a grid (workers + 1 CTA per env) that is co-resident on the device");
+        }
+        return PIC_OK;
+    }
+    h->coop_req = mode;
+    return PIC_OK;
+}
+
+int pic_get_coop(pic_handle* h, int32_t* in_effect, int32_t* workers) {
+    if (!h) return PIC_EINVAL;
+    const bool on = coop_in_effect(h, 2);
+    if (in_effect) *in_effect = on ? 1 : 0;
+    if (workers) *workers = on ? h->coop_workers : 0;
     return PIC_OK;
 }
 

@@ -211,9 +211,15 @@ template <> struct HistSel<DEP_SPLIT32, IP_CIC, float> { using type = Hist<DEP_S
 // TEXG: the gather goes through the texture pipe (TexTable) instead of a shared-memory table.  The table was written to
 // global memory by field_table_kernel, launched between the passes, so these kernels have no field prologue and no
 // table in shared memory: the L1 that the smaller shared-memory carve-out frees holds the 64 KB table.
-template <typename R, int THREADS, int UNROLL, int MODE, int DEP, bool EXACT_W, int IP = IP_CIC, bool TEXG = false>
-__global__ void __launch_bounds__(THREADS) push_stream_kernel(const StreamArgs a) {
+// The pass itself is a device function so that the cooperative step kernel (step_coop_kernel below) can run the three
+// passes of an env step back to back inside one launch.  COOP: called from that kernel -- the CTA's rank among the
+// worker CTAs and their number come as arguments (the grid holds one more CTA, which does the finalize), there is no
+// programmatic dependent launch, and the actuation of the step is passed separately (it changes from step to step
+// while `a` stays the kernel parameter, whose constants the hot loop reads straight from the constant bank).
+template <typename R, int THREADS, int UNROLL, int MODE, int DEP, bool EXACT_W, int IP = IP_CIC, bool TEXG = false, bool COOP = false>
+__device__ __forceinline__ void push_stream_body(const StreamArgs& a, const ActuatorArgs& act, unsigned coop_bid, unsigned coop_nb) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    const unsigned bid = COOP ? coop_bid : blockIdx.x, nb = COOP ? coop_nb : gridDim.x;
     using V = typename RT<R>::vec;
     constexpr int VEC = RT<R>::VEC;
     static_assert(MODE == MODE_KICK || MODE == MODE_KICK0 || MODE == MODE_FINAL || MODE == MODE_INIT, "unknown sub-stage");
@@ -230,14 +236,16 @@ __global__ void __launch_bounds__(THREADS) push_stream_kernel(const StreamArgs a
     const PartConst<R>& pc = part_const<R>(a.pcs);
 #endif
 #ifndef PIC_NO_PDL
-    griddep_launch_dependents();                        // the next kernel of the step may start launching behind this one
-    griddep_wait();                                     // ... and this one touches memory only after its predecessors are done
+    if constexpr (!COOP) {
+        griddep_launch_dependents();                    // the next kernel of the step may start launching behind this one
+        griddep_wait();                                 // ... and this one touches memory only after its predecessors are done
+    }
 #endif
 
     const bool fused = a.comm.world > 1;
     bool dead = false;                                  // fused exchange timed out: leave the particle state untouched
     if (KICK && !TEXG) {                                // D_s aliases the histogram: solve first, then clear
-        const ExtSrc ext = stage_ext(a.act, env, M);
+        const ExtSrc ext = stage_ext(act, env, M);
         if (fused) {
             dead = comm_wait(a.comm, a.comm.seq_in, a.err);
             PeerSumRho rho{comm_in_slots(a.comm, a.comm.seq_in), a.comm.slot_len, a.comm.world};
@@ -252,11 +260,11 @@ __global__ void __launch_bounds__(THREADS) push_stream_kernel(const StreamArgs a
     __syncthreads();
     if (a.rho_zero) {
         unsigned long long* z = a.rho_zero + (size_t)env * M;
-        for (int j = blockIdx.x * THREADS + tid; j < M; j += gridDim.x * THREADS) z[j] = 0ull;
+        for (int j = bid * THREADS + tid; j < M; j += nb * THREADS) z[j] = 0ull;
     }
     if (a.rho_zero2) {
         unsigned long long* z = a.rho_zero2 + (size_t)env * M;
-        for (int j = blockIdx.x * THREADS + tid; j < M; j += gridDim.x * THREADS) z[j] = 0ull;
+        for (int j = bid * THREADS + tid; j < M; j += nb * THREADS) z[j] = 0ull;
     }
 
     R* xe = (R*)a.x + (size_t)env * a.ld;
@@ -404,9 +412,9 @@ __global__ void __launch_bounds__(THREADS) push_stream_kernel(const StreamArgs a
         }
     };
 #pragma unroll
-    for (int d = 0; d < PF; ++d) prefetch_tile((long long)blockIdx.x + (long long)d * gridDim.x);
-    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        prefetch_tile(tile + (long long)PF * gridDim.x);
+    for (int d = 0; d < PF; ++d) prefetch_tile((long long)bid + (long long)d * nb);
+    for (long long tile = bid; tile < n_tiles; tile += nb) {
+        prefetch_tile(tile + (long long)PF * nb);
         const long long base = tile * TILE + tid;
         V xs[UNROLL], vs[UNROLL];
         if constexpr (TEXG && KICK) {
@@ -474,10 +482,10 @@ __global__ void __launch_bounds__(THREADS) push_stream_kernel(const StreamArgs a
         }
     }
     // ragged remainder (< one tile of vectors) and the scalar tail (N not a multiple of the vector width)
-    if (!dead && blockIdx.x == (unsigned)(n_tiles % gridDim.x)) {
+    if (!dead && bid == (unsigned)(n_tiles % nb)) {
         for (long long i = n_tiles * TILE + tid; i < nvec; i += THREADS) vec_pair(i, std::false_type{});
     }
-    if (!dead && blockIdx.x == 0) {
+    if (!dead && bid == 0) {
         long long i = nvec * VEC + tid;
         if (i < a.N) {
             R x = xe[i], v = ve[i];
@@ -493,7 +501,7 @@ __global__ void __launch_bounds__(THREADS) push_stream_kernel(const StreamArgs a
         double t2 = block_sum<THREADS>(s2, sm.red);
         double t1 = block_sum<THREADS>(s1, sm.red);
         if (tid == 0) {
-            double* p = a.partial + ((size_t)env * gridDim.x + blockIdx.x) * 2;
+            double* p = a.partial + ((size_t)env * nb + bid) * 2;
             p[0] = t2; p[1] = t1;
         }
     }
@@ -503,14 +511,14 @@ __global__ void __launch_bounds__(THREADS) push_stream_kernel(const StreamArgs a
         __shared__ unsigned s_is_last;
         __threadfence();
         __syncthreads();
-        if (tid == 0) s_is_last = atomicAdd(a.comm.ticket, 1u) == gridDim.x - 1 ? 1u : 0u;
+        if (tid == 0) s_is_last = atomicAdd(a.comm.ticket, 1u) == nb - 1 ? 1u : 0u;
         __syncthreads();
         if (s_is_last) {
             __threadfence();
             int n_extra = 0;
             if (SUMS) {
                 double q2 = 0.0, q1 = 0.0;
-                for (int i = tid; i < (int)gridDim.x; i += THREADS) { q2 += __ldcg(a.partial + 2 * i); q1 += __ldcg(a.partial + 2 * i + 1); }
+                for (int i = tid; i < (int)nb; i += THREADS) { q2 += __ldcg(a.partial + 2 * i); q1 += __ldcg(a.partial + 2 * i + 1); }
                 q2 = block_sum<THREADS>(q2, sm.red);
                 q1 = block_sum<THREADS>(q1, sm.red);
                 if (tid == 0) { s_extra[0] = q2; s_extra[1] = q1; }
@@ -546,6 +554,11 @@ __global__ void __launch_bounds__(THREADS) push_stream_kernel(const StreamArgs a
             if (tid == 0) *a.comm.ticket = 0u;
         }
     }
+}
+
+template <typename R, int THREADS, int UNROLL, int MODE, int DEP, bool EXACT_W, int IP = IP_CIC, bool TEXG = false>
+__global__ void __launch_bounds__(THREADS) push_stream_kernel(const StreamArgs a) {
+    push_stream_body<R, THREADS, UNROLL, MODE, DEP, EXACT_W, IP, TEXG, false>(a, a.act, 0u, 0u);
 }
 
 // ----------------------------------------------------------------- field table (texture gather)
@@ -599,14 +612,12 @@ struct FinalizeArgs {
     unsigned* err;
 };
 
+// The finalize itself is a device function (one CTA per env calls it): field_finalize_kernel below, and the finalize CTA
+// of the cooperative step kernel, which passes the action and the trace row of the step it closes.
 template <int THREADS>
-__global__ void __launch_bounds__(THREADS) field_finalize_kernel(const FinalizeArgs a) {
+__device__ __forceinline__ void field_finalize_body(const FinalizeArgs& a, int env, const double* coeffs, double* trace_row) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int env = blockIdx.x, M = a.mc.M, tid = threadIdx.x;
-#ifndef PIC_NO_PDL
-    griddep_launch_dependents();
-    griddep_wait();
-#endif
+    const int M = a.mc.M, tid = threadIdx.x;
     SmemLayout<double> sm(smem_raw, M, false);
     const ExtSrc none{nullptr, nullptr, nullptr, nullptr, 0};
     const ModeOut mo{a.tw_cos, a.tw_sin, a.modes ? a.modes + (size_t)env * 2 * a.n_modes : nullptr, a.n_modes};
@@ -639,7 +650,7 @@ __global__ void __launch_bounds__(THREADS) field_finalize_kernel(const FinalizeA
     if (tid == 0) {
         double* d = a.diag + (size_t)env * DIAG_N;
         if (a.step_done) {                             // reward of this transition: field energy of the PRE-step state
-            const double ie = a.coeffs ? input_energy(a.coeffs + (size_t)env * a.two_m, a.two_m, a.rw.L) : 0.0;
+            const double ie = coeffs ? input_energy(coeffs + (size_t)env * a.two_m, a.two_m, a.rw.L) : 0.0;
             d[DIAG_REWARD] = reward_of(a.rw, d[DIAG_PE_MESH], ie);
             d[DIAG_INPUT_E] = ie;
         } else {
@@ -651,8 +662,80 @@ __global__ void __launch_bounds__(THREADS) field_finalize_kernel(const FinalizeA
             a.vsum[env * 2] = t.s1; a.vsum[env * 2 + 1] = t.s2;
             d[DIAG_KE] = 0.5 * t.s1; d[DIAG_SUM_V] = t.s2;
         }
-        if (a.trace_row)
-            for (int k = 0; k < DIAG_N; ++k) a.trace_row[(size_t)env * DIAG_N + k] = d[k];
+        if (trace_row)
+            for (int k = 0; k < DIAG_N; ++k) trace_row[(size_t)env * DIAG_N + k] = d[k];
+    }
+}
+
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) field_finalize_kernel(const FinalizeArgs a) {
+#ifndef PIC_NO_PDL
+    griddep_launch_dependents();
+    griddep_wait();
+#endif
+    field_finalize_body<THREADS>(a, blockIdx.x, a.coeffs, a.trace_row);
+}
+
+// ----------------------------------------------------------------- cooperative step (mid-size envs)
+// One launch per call instead of four per env step.  For envs of 1e4 .. a few 1e7 particles the streaming step is not
+// bound by its particles but by what sits between them: three kernel boundaries and a finalize launch per step (about
+// 28 us for an env whose particles take a few us).  Here the three passes of a step run back to back inside ONE
+// cooperative launch, separated by grid barriers, for any number of steps; the CTAs of column blockIdx.x < n_workers are
+// the passes' CTAs (a CTA walks the same tiles in every pass, so particles never cross CTAs: only the densities and the
+// kinetic partial sums do, through the L2), and one more CTA per env does the finalize of step s while the workers are
+// in the first pass of step s + 1, which needs nothing the finalize produces -- the same overlap step_device arranges
+// with a side stream, and the same buffer-clearing pattern (StreamArgs of the `overlap` flavour).  Same device functions,
+// same order of every floating-point sum => bit-identical to the kernel-per-pass path with n_workers CTAs.
+struct CoopArgs {
+    StreamArgs s[3];                   // Yoshida stages 1, 2, 3; act.coeffs points at the action of the first step
+    FinalizeArgs f;                    // coeffs / trace_row are taken from the fields below instead
+    int n_steps;
+    long long coeff_step_stride;       // elements between the actions of consecutive steps (n_envs * 2m)
+    double* trace;                     // [n_steps][n_envs][DIAG_N]
+    unsigned long long* barrier;       // monotonic arrival counter
+    unsigned long long barrier_base;   // its value when this launch starts (the host keeps count)
+    unsigned n_workers;                // gridDim.x - 1
+};
+
+__device__ __forceinline__ unsigned long long ld_acquire_gpu(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+// every thread of every CTA of the (co-resident: cooperative launch) grid calls this
+__device__ __forceinline__ void grid_barrier(unsigned long long* ctr, unsigned long long target) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        asm volatile("red.release.gpu.global.add.u64 [%0], 1;" ::"l"(ctr) : "memory");
+        while (ld_acquire_gpu(ctr) < target) { }
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+template <typename R, int THREADS, int UNROLL, int DEP, bool EXACT_W>
+__global__ void __launch_bounds__(THREADS) step_coop_kernel(const CoopArgs c) {
+    const unsigned nw = c.n_workers, bid = blockIdx.x;
+    const bool worker = bid < nw;
+    const unsigned long long n_ctas = (unsigned long long)gridDim.x * gridDim.y;
+    unsigned long long target = c.barrier_base;
+    for (int s = 0; ; ++s) {
+        ActuatorArgs act = c.s[0].act;
+        if (act.coeffs) act.coeffs += (size_t)s * c.coeff_step_stride;
+        if (worker) {
+            if (s < c.n_steps)
+                push_stream_body<R, THREADS, UNROLL, MODE_KICK0, DEP, EXACT_W, IP_CIC, false, true>(c.s[0], act, bid, nw);
+        } else if (s > 0) {             // the finalize of the previous step, beside the workers' first pass of this one
+            field_finalize_body<THREADS>(c.f, blockIdx.y, c.f.coeffs ? c.f.coeffs + (size_t)(s - 1) * c.coeff_step_stride : nullptr,
+                                         c.trace + (size_t)(s - 1) * gridDim.y * DIAG_N);
+        }
+        if (s == c.n_steps) break;
+        grid_barrier(c.barrier, target += n_ctas);
+        if (worker) push_stream_body<R, THREADS, UNROLL, MODE_KICK, DEP, EXACT_W, IP_CIC, false, true>(c.s[1], act, bid, nw);
+        grid_barrier(c.barrier, target += n_ctas);
+        if (worker) push_stream_body<R, THREADS, UNROLL, MODE_FINAL, DEP, EXACT_W, IP_CIC, false, true>(c.s[2], act, bid, nw);
+        grid_barrier(c.barrier, target += n_ctas);
     }
 }
 

@@ -287,7 +287,12 @@ class Engine:
         d["mode"] = "resident" if d["mode"] == L.PIC_MODE_RESIDENT else "streaming"
         d["deposit"] = "split32" if d["deposit"] == L.PIC_DEPOSIT_SPLIT32 else "cas64"
         if d["mode"] == "streaming":
-            d["gather"] = self.gather
+            on, workers = self.coop
+            if on:                       # whole steps in one cooperative launch: shared-memory gather in every pass
+                d["coop_workers"] = workers
+                d["gather"] = "shared"
+            else:
+                d["gather"] = self.gather
         return d
 
     def set_tuning(self, threads=0, per_thread=0, ctas_per_sm=-1):
@@ -302,6 +307,19 @@ class Engine:
         else:
             code = {"auto": 0, "shared": 1, "texture": 2}[route]
         self._ck(self._lib.pic_set_gather(self._h, code))
+
+    def set_coop(self, mode="auto"):
+        """Streaming mode, one GPU: whole env steps as ONE cooperative launch (grid barriers between the passes, finalize
+        on a CTA of its own) -- "on" (raises when the handle's flavour has no such kernel), "off" or "auto" (mid-size
+        envs).  Same bits as the kernel-per-pass path."""
+        self._ck(self._lib.pic_set_coop(self._h, {"auto": -1, "off": 0, "on": 1}[mode]))
+
+    @property
+    def coop(self):
+        """(in effect for the next step call, pass CTAs per env)"""
+        on, w = C.c_int32(), C.c_int32()
+        self._ck(self._lib.pic_get_coop(self._h, C.byref(on), C.byref(w)))
+        return bool(on.value), int(w.value)
 
     @property
     def gather(self):

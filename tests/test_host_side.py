@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
     for s in syms:
         assert hasattr(lib, s), "libpic_b200.so does not export %s" % s
         assert s in pic_b200._lib.SIGNATURES, "ctypes binding misses %s" % s
-    assert lib.pic_abi_version() == 3
+    assert lib.pic_abi_version() == 4
     assert b"sm_100a" in lib.pic_build_info()
     assert isinstance(lib, ctypes.CDLL)
 
