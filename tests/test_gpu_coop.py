@@ -66,7 +66,7 @@ def _assert_same(a, b, same_grid):
             assert np.allclose(p, q, rtol=1e-13, atol=1e-9)
 
 
-@pytest.mark.parametrize("N,M,n_envs", [(200_003, 4096, 1), (60_000, 1000, 3), (1_000_001, 1024, 1), (20_000, 250, 1)])
+@pytest.mark.parametrize("N,M,n_envs", [(200_003, 4096, 1), (60_000, 1000, 3), (1_000_001, 1024, 1), (20_000, 250, 1), (33, 7, 1), (1, 2, 2)])
 def test_coop_step_is_bit_identical(N, M, n_envs):
     rng = np.random.RandomState(1)
     ext = 0.2 * np.sin(2 * np.pi * np.arange(M) / M)[None].repeat(n_envs, 0) + 0.05 * rng.normal(size=(n_envs, M))
