@@ -326,8 +326,9 @@ def parity_side_check(rank=0, world=1, device=0, collective="nccl"):
     import pic_b200
     sim = pic_b200.ShardedPIC(PARITY_N, N_MESH, 1.0, L_BOX, 0.1, rank=rank, world_size=world, device=device,
                               collective=collective)
-    if collective == "nccl":       # the gather route the headline workload runs with (AUTO would keep a run this small on
-        sim.engine.set_gather("texture:3")   # the shared-memory table); the routes are bit-identical, so the hash is the same
+    # the gather route the headline workload runs with (AUTO would keep a run this small on the shared-memory table); the
+    # routes are bit-identical, so the hash is the same
+    sim.engine.set_gather("texture:3")
     sim.sample_state("bump-on-tail", a=0.2, v0=3.0, sigma=1.0, A=0.1, n_mode=2, seed=PARITY_SEED)
     sim.step(None, PARITY_STEPS)
     d = sim.diag()
@@ -385,7 +386,7 @@ def run_gpu_arm(args):
     sim.sample_state("bump-on-tail", a=0.2, v0=3.0, sigma=1.0, A=0.1, n_mode=2, seed=42)
     info = eng.launch_info()
     N_local = sim.N_local
-    sim_dt, sim_collective = sim.dt, sim.collective
+    sim_dt, sim_collective, sim_multicast = sim.dt, sim.collective, bool(getattr(sim, "multicast", False))
 
     # ---- value: K steps, state resident in HBM, device-timed, max over ranks
     for _ in range(args.warmup):
@@ -711,7 +712,7 @@ def run_gpu_arm(args):
             "config": {"workload": "large-N single env: %.3g particles, %d cells, bump-on-tail, particle-sharded over %d GPU(s)"
                                    % (N, N_MESH, world),
                        "n_particles": N, "n_mesh": N_MESH, "L": L_BOX, "dt": sim_dt, "parallelism": "particle-shard x%d" % world,
-                       "collective": sim_collective,
+                       "collective": sim_collective, "fused_multicast": sim_multicast,
                        "l2_policy": "inputs (16 B x %.3g particles per rank) exceed the 126 MB L2" % N_local,
                        "launch": info, "extra_untimed_warmup_steps": settle_steps,
                        "timed_region": "exactly %d steps between barriers, measured %d time(s) back to back; ms_per_step and "
@@ -751,8 +752,9 @@ def main():
     ap.add_argument("--unroll", type=int, default=0)
     ap.add_argument("--ctas", type=int, default=0)
     ap.add_argument("--gather", default="auto", help="streaming gather route: auto | shared | texture | texture:<stages>")
-    ap.add_argument("--collective", default="nccl", choices=["fused", "nccl"],
-                    help="density exchange of the particle-sharded mode: fused peer-memory exchange or ncclAllReduce")
+    ap.add_argument("--collective", default="auto", choices=["auto", "fused", "nccl"],
+                    help="density exchange of the particle-sharded mode: fused peer-memory exchange (NVLS multicast "
+                         "publish), ncclAllReduce, or auto = fused where the multicast mapping exists, else nccl")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-batched", action="store_true")
     ap.add_argument("--no-single", action="store_true")

@@ -186,6 +186,11 @@ int pic_comm_init_rank(pic_handle* h, const char* id128, int32_t rank, int32_t w
 int64_t pic_comm_exchange_words(const pic_handle* h, int32_t world_size);
 int pic_comm_init_peer(pic_handle* h, int32_t rank, int32_t world_size, void* const* exchange_ptrs,
                        void* const* flag_ptrs, int64_t exchange_words);
+/* Optional, after pic_comm_init_peer: the NVLS MULTICAST mapping of the same exchange buffers (cuMulticast* /
+ * torch symmetric memory's multicast_ptr): the publishing CTA then issues ONE store per word, which the NVSwitch
+ * replicates into the slot of every rank, instead of one peer store per word and rank.  Same slots, same flags, same
+ * bits.  nullptr switches back to per-rank peer stores. */
+int pic_comm_set_multicast(pic_handle* h, void* exchange_multicast);
 /* Alternative used when the collective is driven from the host side (e.g. torch.distributed): run sub-stage
  * `stage` (1..3, 4 = finalize, -1 = init deposit; 0 is a no-op because the deposit of the drift-only stage 0 is done
  * ahead of time by stage 3 / init of the state it starts from, and stage 1 redoes the drift itself on load) and leave the local density in the buffer returned

@@ -87,6 +87,7 @@ SIGNATURES = {
     "pic_comm_init_rank": (C.c_int, [_H, C.c_char_p, C.c_int32, C.c_int32]),
     "pic_comm_exchange_words": (C.c_int64, [_H, C.c_int32]),
     "pic_comm_init_peer": (C.c_int, [_H, C.c_int32, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_int64]),
+    "pic_comm_set_multicast": (C.c_int, [_H, C.c_void_p]),
     "pic_run_stage": (C.c_int, [_H, C.c_int32]),
     "pic_stage_density": (C.c_int, [_H, C.c_int32, C.POINTER(C.c_void_p)]),
     "pic_set_stage_actuation": (C.c_int, [_H, C.c_void_p, C.c_void_p]),

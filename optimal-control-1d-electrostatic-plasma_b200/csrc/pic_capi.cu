@@ -112,6 +112,7 @@ struct pic_handle {
     bool fused = false;
     unsigned long long* exch[COMM_MAX_WORLD] = {};
     unsigned long long* cflags[COMM_MAX_WORLD] = {};
+    unsigned long long* exch_mc = nullptr;           // NVLS multicast mapping of the exchange buffers (pic_comm_set_multicast)
     unsigned long long seq = 0, seq_state = 0;       // last exchange issued; the exchange holding the state density
     unsigned* ticket = nullptr;
     // finalize of step t overlapped with the first pass of step t+1 inside a multi-step call (single GPU)
@@ -212,9 +213,9 @@ const int kStageMode[3] = {MODE_KICK0, MODE_KICK, MODE_FINAL};     // Yoshida st
 // texture route where it was measured faster (N = 1e9, 4096 cells): the stage-3 pass, whose two deposits + gather
 // saturate the LSU data pipe (6.03 -> 5.52 ms under the power cap); not the stage-1 pass, which is bound by HBM alone and
 // loses (5.31 -> 6.35 ms: the texture fetches queue behind the pass's own outstanding global loads), nor stage 2 (equal
-// under the cap, slower at boost clocks).  Conditions: split32 deposit, default launch shape, no fused peer exchange
-// (whose prologue consumes the peers' slots), and enough particles per launch that the extra one-CTA field launch per
-// pass does not show (kTexMinParticles).
+// under the cap, slower at boost clocks).  Conditions: split32 deposit, default launch shape, and enough particles per
+// launch that the extra one-CTA field launch per pass does not show (kTexMinParticles).  With the fused peer exchange
+// that one-CTA kernel is the consumer of the ranks' slots.
 constexpr long long kTexMinParticles = 1ll << 22;
 constexpr int kTexAutoStages = 0x4;                 // bit s-1: stage s
 int configure_gather(pic_handle* h) {
@@ -231,7 +232,7 @@ int configure_gather(pic_handle* h) {
              : h->gather_req == PIC_GATHER_TEXTURE ? 0x7
              : h->gather_req == PIC_GATHER_SHARED ? 0 : (h->gather_req & 0x7);
     if (h->tableless) mask |= 0x4;
-    bool have = h->dep == DEP_SPLIT32 && !h->exact_w && !h->fused;
+    bool have = h->dep == DEP_SPLIT32 && !h->exact_w;
     {                                               // a linear texture addresses at most maxTexture1DLinear texels
         size_t max_texels = 0;
         const cudaChannelFormatDesc fd = h->f32 ? cudaCreateChannelDesc<float2>() : cudaCreateChannelDesc<int4>();
@@ -242,10 +243,10 @@ int configure_gather(pic_handle* h) {
     if (!have) {
         if (h->tableless)
             return fail(h, PIC_EUNSUPPORTED, "n_mesh too large for the shared-memory mesh tables of this configuration "
-                                             "(the table-less texture route needs the 1024 x 2 shape and no fused peer exchange)");
+                                             "(the table-less texture route needs the 1024 x 2 shape)");
         if (h->gather_req != PIC_GATHER_AUTO && h->gather_req != PIC_GATHER_SHARED)
             return fail(h, PIC_EUNSUPPORTED, "gather = texture needs streaming mode, the split32 deposit, exact_weights = 0, "
-                                             "the 1024 x 2 launch shape, no fused peer exchange and n_envs * n_mesh within the 1D texture limit");
+                                             "the 1024 x 2 launch shape and n_envs * n_mesh within the 1D texture limit");
         return PIC_OK;
     }
     if (h->gather_req == PIC_GATHER_AUTO && !h->tableless) {
@@ -406,6 +407,7 @@ void fill_comm(const pic_handle* h, CommArgs& c, unsigned long long seq_in, int 
                const unsigned long long* out_src, int out_words) {
     c.world = h->fused ? h->world : 1; c.rank = h->rank; c.slot_len = comm_slot_len(h);
     for (int r = 0; r < COMM_MAX_WORLD; ++r) { c.exch[r] = h->exch[r]; c.flags[r] = h->cflags[r]; }
+    c.exch_mc = h->fused ? h->exch_mc : nullptr;
     c.seq_in = seq_in; c.in_offset = in_offset; c.seq_out = seq_out; c.out_src = out_src; c.out_words = out_words;
     c.ticket = h->ticket;
 }
@@ -616,6 +618,7 @@ int run_stage(pic_handle* h, int stage, const double* ext, const double* coeffs,
         // the field of this sub-stage, solved once and written as the gather table the pass reads through the texture pipe
         FieldTableArgs t{};
         t.mc = h->mc; t.rho_in = a.rho_in; t.act = a.act; t.table = h->table[stage - 1];
+        t.comm = a.comm; t.err = h->err;                // fused exchange: the table kernel consumes the ranks' slots
         void* targs[] = {&t};
         CK(h, launch_pdl(field_table_kernel_for(h->f32), dim3(h->n_envs), dim3(1024), targs,
                          h->f32 ? smem_plan_bytes<float>(h->M, 1024, false) : smem_plan_bytes<double>(h->M, 1024, false), h->stream));
@@ -1464,9 +1467,16 @@ int pic_comm_init_peer(pic_handle* h, int32_t rank, int32_t world, void* const* 
         if (!exch_ptrs[r] || !flag_ptrs[r]) return fail(h, PIC_EINVAL, "null peer pointer");
         h->exch[r] = (unsigned long long*)exch_ptrs[r]; h->cflags[r] = (unsigned long long*)flag_ptrs[r];
     }
-    h->rank = rank; h->world = world; h->fused = true; h->seq = 0; h->seq_state = 0;
-    if (h->gather_req != PIC_GATHER_SHARED) h->gather_req = PIC_GATHER_AUTO;    // the fused prologue consumes the peers' slots itself
+    h->rank = rank; h->world = world; h->fused = true; h->seq = 0; h->seq_state = 0; h->exch_mc = nullptr;
     return configure_gather(h);
+}
+
+int pic_comm_set_multicast(pic_handle* h, void* exch_multicast) {
+    if (!h) return PIC_EINVAL;
+    if (!h->fused) return fail(h, PIC_ESTATE, "pic_comm_init_peer has not been called");
+    cudaStreamSynchronize(h->stream);
+    h->exch_mc = (unsigned long long*)exch_multicast;
+    return PIC_OK;
 }
 
 int pic_set_stage_actuation(pic_handle* h, const double* ext_dev, const double* coeffs_dev) {

@@ -56,6 +56,8 @@ struct CommArgs {
     int slot_len;                                      // words per slot (2 * n_envs * M + 2 * n_envs)
     unsigned long long* exch[COMM_MAX_WORLD];          // exchange buffer of every rank (peer pointers); [rank] is local
     unsigned long long* flags[COMM_MAX_WORLD];         // flag array of every rank; this rank writes entry [rank] of each
+    unsigned long long* exch_mc;                       // NVLS multicast mapping of the exchange buffers (one store lands in
+                                                       // every rank's copy), or nullptr: one peer store per rank
     unsigned long long seq_in;                         // exchange to consume in the prologue (0: none)
     unsigned long long seq_out;                        // exchange produced by this kernel (0: none)
     int in_offset;                                     // word offset of the density to consume inside a slot
@@ -71,6 +73,10 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
 }
 __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+// one store to a multicast (NVLS) address: the switch replicates it into the copy of every rank of the group
+__device__ __forceinline__ void multimem_st(unsigned long long* p, unsigned long long v) {
+    asm volatile("multimem.st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
 // every thread of the CTA calls this; returns after all ranks have published exchange `seq`.
@@ -255,6 +261,7 @@ __device__ __forceinline__ void push_stream_body(const StreamArgs& a, const Actu
             block_field<R, THREADS, false, true>(rho, sm.E_s, sm.D_s, sm.red, a.mc, ext, nullptr, nullptr, 0.0, 0.0, [] {});
         }
     }
+    if (KICK && TEXG && fused) dead = (__ldcg(a.err) & ERR_COMM_TIMEOUT) != 0;   // raised by field_table_kernel's wait
     hist.zero(tid, THREADS);
     if (SUMS) hist_next.zero(tid, THREADS);
     __syncthreads();
@@ -527,8 +534,26 @@ __device__ __forceinline__ void push_stream_body(const StreamArgs& a, const Actu
             }
 
             const size_t slot = ((size_t)(a.comm.seq_out % COMM_SETS) * a.comm.world + a.comm.rank) * a.comm.slot_len;
-            // each word is read once (all loads of a batch in flight together) and then posted to every peer
             constexpr int BATCH = 8;
+            if (a.comm.exch_mc) {
+                // NVLS: ONE store per word to the multicast mapping; the switch writes it into slot[set][rank] of every rank
+                unsigned long long* dst = a.comm.exch_mc + slot;
+                for (int j0 = tid; j0 < a.comm.out_words; j0 += THREADS * BATCH) {
+                    unsigned long long w[BATCH];
+#pragma unroll
+                    for (int b = 0; b < BATCH; ++b) {
+                        const int j = j0 + b * THREADS;
+                        w[b] = j < a.comm.out_words ? __ldcg(a.comm.out_src + j) : 0ull;
+                    }
+#pragma unroll
+                    for (int b = 0; b < BATCH; ++b) {
+                        const int j = j0 + b * THREADS;
+                        if (j < a.comm.out_words) multimem_st(dst + j, w[b]);
+                    }
+                }
+                if (tid < n_extra) multimem_st(dst + a.comm.out_words + tid, (unsigned long long)__double_as_longlong(s_extra[tid]));
+            } else {
+            // each word is read once (all loads of a batch in flight together) and then posted to every peer
             for (int j0 = tid; j0 < a.comm.out_words; j0 += THREADS * BATCH) {
                 unsigned long long w[BATCH];
 #pragma unroll
@@ -548,6 +573,7 @@ __device__ __forceinline__ void push_stream_body(const StreamArgs& a, const Actu
             if (tid < n_extra)
                 for (int r = 0; r < a.comm.world; ++r)
                     a.comm.exch[r][slot + a.comm.out_words + tid] = (unsigned long long)__double_as_longlong(s_extra[tid]);
+            }
             __threadfence_system();
             __syncthreads();
             if (tid < a.comm.world) st_release_sys(a.comm.flags[tid] + a.comm.rank, a.comm.seq_out);
@@ -570,6 +596,8 @@ struct FieldTableArgs {
     const unsigned long long* rho_in;  // [n_envs][M]
     ActuatorArgs act;
     void* table;                       // [n_envs][M] pairs of R
+    CommArgs comm;                     // fused exchange: the density is the sum of the ranks' slots of exchange seq_in
+    unsigned* err;
 };
 
 template <typename R, int THREADS>
@@ -583,8 +611,16 @@ __global__ void __launch_bounds__(THREADS) field_table_kernel(const FieldTableAr
 #endif
     SmemLayout<R> sm(smem_raw, M, false);
     const ExtSrc ext = stage_ext(a.act, env, M);
-    GlobalRho rho{a.rho_in + (size_t)env * M};
-    block_field<R, THREADS, false, true>(rho, sm.E_s, sm.D_s, sm.red, a.mc, ext, nullptr, nullptr, 0.0, 0.0, [] {});
+    if (a.comm.world > 1) {
+        // the consumer side of the fused exchange for a texture-route pass: a peer that never arrives leaves the sticky
+        // ERR_COMM_TIMEOUT flag, which makes the pass that follows leave the particle state alone
+        comm_wait(a.comm, a.comm.seq_in, a.err);
+        PeerSumRho rho{comm_in_slots(a.comm, a.comm.seq_in), a.comm.slot_len, a.comm.world};
+        block_field<R, THREADS, false, true>(rho, sm.E_s, sm.D_s, sm.red, a.mc, ext, nullptr, nullptr, 0.0, 0.0, [] {});
+    } else {
+        GlobalRho rho{a.rho_in + (size_t)env * M};
+        block_field<R, THREADS, false, true>(rho, sm.E_s, sm.D_s, sm.red, a.mc, ext, nullptr, nullptr, 0.0, 0.0, [] {});
+    }
     P* out = (P*)a.table + (size_t)env * M;
     for (int j = tid; j < M; j += THREADS) out[j] = sm.E_s[j];
 }

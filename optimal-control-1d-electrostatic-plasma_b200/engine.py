@@ -270,6 +270,10 @@ class Engine:
         fa = (C.c_void_p * world)(*[C.c_void_p(int(p)) for p in flag_ptrs])
         self._ck(self._lib.pic_comm_init_peer(self._h, int(rank), int(world), ea, fa, int(exch_words)))
 
+    def comm_set_multicast(self, exch_multicast_ptr):
+        """NVLS multicast mapping of the exchange buffers (0 / None: per-rank peer stores)."""
+        self._ck(self._lib.pic_comm_set_multicast(self._h, C.c_void_p(int(exch_multicast_ptr or 0))))
+
     @staticmethod
     def nccl_unique_id():
         buf = C.create_string_buffer(128)

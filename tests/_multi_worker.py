@@ -24,8 +24,10 @@ def main():
     v = rng.normal(size=N) + 3.0 * (rng.uniform(size=N) < 0.2)
     ext = 0.2 * np.cos(2 * np.pi * np.arange(M) / M)
     sim = pic_b200.ShardedPIC(N, M, 1.0, L, 0.1, rank=rank, world_size=world, device=local, collective=collective)
-    if collective != "fused":      # every pass gathers through the texture pipe on the sharded side; the one-GPU run below
-        sim.engine.set_gather("texture")     # keeps the shared-memory table: the routes must agree to the bit as well
+    # every pass gathers through the texture pipe on the sharded side (fused exchange: the one-CTA field-table kernel is
+    # then the consumer of the peers' slots); the one-GPU run below keeps the shared-memory table: the routes must agree
+    # to the bit as well
+    sim.engine.set_gather("texture" if collective != "fused" else "texture:13")   # fused: stage 2 through the prologue
     sim.set_state_global(x, v)
     sim.step(ext, 3)
     sim.step(None, 2)

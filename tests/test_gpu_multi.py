@@ -11,7 +11,7 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.parametrize("collective", ["fused", "nccl", "torch"])
+@pytest.mark.parametrize("collective", ["fused", "nccl", "torch", "auto"])
 def test_sharded_equals_single_gpu(collective, tmp_path):
     import torch
     n = torch.cuda.device_count()
