@@ -261,7 +261,14 @@ __device__ __forceinline__ void push_stream_body(const StreamArgs& a, const Actu
             block_field<R, THREADS, false, true>(rho, sm.E_s, sm.D_s, sm.red, a.mc, ext, nullptr, nullptr, 0.0, 0.0, [] {});
         }
     }
-    if (KICK && TEXG && fused) dead = (__ldcg(a.err) & ERR_COMM_TIMEOUT) != 0;   // raised by field_table_kernel's wait
+    // Texture route under the fused exchange: the consumer of the peers' slots was field_table_kernel.  If its wait timed
+    // out it left the sticky flag, and this pass must leave the particle state alone: the whole CTA returns at once
+    // (nothing is published either, so the peers time out on their next wait and do the same; the flag is fatal for the
+    // handle anyway -- the host classes raise on their next read).  Checked here, once: keeping a `dead` flag alive across
+    // the hot loop, or re-reading it after the loop, made ptxas spill in these kernels, which sit at the 64-register limit.
+    if constexpr (KICK && TEXG) {
+        if (fused && (__ldcg(a.err) & ERR_COMM_TIMEOUT) != 0) return;
+    }
     hist.zero(tid, THREADS);
     if (SUMS) hist_next.zero(tid, THREADS);
     __syncthreads();
