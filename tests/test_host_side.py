@@ -30,6 +30,28 @@ def test_library_exports_every_declared_symbol():
     assert isinstance(lib, ctypes.CDLL)
 
 
+def test_headline_kernels_do_not_spill():
+    """The three kernels of the headline step (float64, 1024 x 2, split32: stage 1 and stage 2 on the shared-memory gather
+    table, stage 3 on the texture route) sit at the 64-register limit of a 1024-thread CTA; a harmless-looking change (a
+    flag kept alive across the hot loop) once made ptxas spill in the stage-3 kernel and cost 28 % of that pass.  The
+    built library must show no stack frame for them."""
+    import shutil
+    import subprocess
+    import pic_b200
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    pic_b200._lib.load()
+    out = subprocess.run([cuobjdump, "-res-usage", pic_b200._lib.load()._name], capture_output=True, text=True).stdout
+    usage = dict(re.findall(r"Function (\S+):\n\s*(REG:\d+ STACK:\d+)", out))
+    # push_stream_kernel<double, 1024, 2, MODE, DEP_SPLIT32, EXACT_W = false, IP_CIC, TEXG>; MODE 4 = KICK0, 1 = KICK, 2 = FINAL
+    for mode, texg in ((4, 0), (1, 0), (2, 1)):
+        name = "_ZN3pic18push_stream_kernelIdLi1024ELi2ELi%dELi1ELb0ELi0ELb%dEEEvNS_10StreamArgsE" % (mode, texg)
+        assert name in usage, "kernel %s not found in the library" % name
+        reg, stack = (int(t.split(":")[1]) for t in usage[name].split())
+        assert stack == 0 and reg <= 64, (name, usage[name])
+
+
 def test_no_cpu_fallback_without_device():
     import torch
     import pic_b200
