@@ -113,3 +113,39 @@ def test_auto_route_by_size_and_shape():
     big.set_tuning(1024, 2, 0)
     assert big.gather == "texture:3"
     small.close(); big.close()
+
+
+def test_fused_exchange_timeout_in_the_field_table_kernel_leaves_the_state_alone():
+    """Fused peer exchange + texture-route stage 3 on ONE GPU with a peer that stops publishing: rank 0 of a world of two
+    whose 'peer' buffers are plain local allocations.  The fake peer has 'published' exchanges 1 and 2 (all-zero slots: it
+    owns no particles), so the init deposit, stage 1 and stage 2 see complete exchanges; exchange 3 never arrives.  Its
+    consumer is the one-CTA field_table_kernel of the stage-3 pass: the wait must end (bounded spin, no hang), raise the
+    sticky ERR_COMM_TIMEOUT flag, and the stage-3 pass must leave x and v exactly as stage 2 left them."""
+    import torch
+    import pic_b200
+    N, M, L = 50_000, 512, 50.0
+    rng = np.random.RandomState(5)
+    x = rng.uniform(0, L, (1, N)); v = rng.normal(0, 1, (1, N))
+    eng = pic_b200.Engine(N, M, L, 0.05, mode="streaming")
+    words = eng.comm_exchange_words(2)
+    exch = [torch.zeros(words, dtype=torch.int64, device="cuda") for _ in range(2)]
+    flags = [torch.zeros(16, dtype=torch.int64, device="cuda") for _ in range(2)]
+    flags[0][1] = 2                                  # what rank 0 sees of rank 1: exchanges 1 and 2 are there
+    torch.cuda.synchronize()
+    eng.comm_init_peer(0, 2, [t.data_ptr() for t in exch], [t.data_ptr() for t in flags], words)
+    eng.set_gather("texture:3")
+    assert eng.gather == "texture:3"
+    eng.set_state(x, v)
+    assert eng.error_flags() == 0
+    eng.step_mesh(None, 1)                           # stage 3 (and the finalize) time out
+    eng.sync()
+    assert eng.error_flags() & 4                     # ERR_COMM_TIMEOUT
+    xs, vs = eng.get_state()
+    eng.close()
+    ref = pic_b200.Engine(N, M, L, 0.05, mode="streaming")
+    ref.set_state(x, v)
+    ref.set_stage_actuation(None, None)
+    ref.run_stage(1); ref.run_stage(2)
+    xr, vr = ref.get_state()
+    ref.close()
+    assert np.array_equal(xs, xr) and np.array_equal(vs, vr)
