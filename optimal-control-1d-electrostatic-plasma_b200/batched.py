@@ -37,6 +37,13 @@ class BatchedPIC:
         slots the other leaves free -- consecutive calls overlap across groups, every env's own sequence of steps is
         unchanged -- and the throughput is that of full waves (measured: 10.6 -> 12.6 M env-steps/s at 512 envs per
         GPU).  Default: 2 when there are at least 64 local envs, else 1."""
+        if interpol == "TSC":
+            # src/control/objective.py:24 hard-codes interpol="CIC" when the reference's Reward re-deposits the state, even
+            # for a TSC env; the device reward uses the env's own (TSC) field energy.  Say so instead of passing it off as
+            # the reference's number (DESIGN.md section 9); the host-side reference Reward gives the CIC value.
+            import warnings
+            warnings.warn("BatchedPIC(interpol='TSC'): the on-device reward uses the TSC field energy, the reference's "
+                          "Reward always re-deposits with CIC (src/control/objective.py:24)", stacklevel=2)
         self.n_envs_total = int(n_envs)
         self.env_lo, self.env_hi = shard_range(n_envs, rank, world_size)
         self.n_envs = self.env_hi - self.env_lo

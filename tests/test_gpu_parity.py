@@ -560,3 +560,22 @@ def test_tiny_and_ragged_configs(mode, N, M):
     n, E = eng.get_fields()
     assert np.abs(E[0] - o["E_mesh"]).max() < 1e-11 * max(1.0, np.abs(o["E_mesh"]).max())
     assert eng.error_flags() == 0
+
+
+def test_tsc_batched_reward_deviation_is_flagged():
+    """The reference's Reward re-deposits the state with CIC even for a TSC env (src/control/objective.py:24); the device
+    reward of a TSC BatchedPIC uses the env's own TSC field energy.  The constructor says so (a warning), and the number
+    returned is exactly the documented one: max(1 - PE_tsc(pre-step state), 0) * alpha + max(1 - ie / r_ie_n, 0) * beta."""
+    from pic_b200 import BatchedPIC
+    B, N = 3, 4000
+    with pytest.warns(UserWarning, match="objective.py:24"):
+        bp = BatchedPIC(B, N=N, N_mesh=250, L=50.0, dt=0.05, max_mode=3, interpol="TSC", alpha=0.7, beta=0.3)
+    rng = np.random.RandomState(4)
+    x = rng.uniform(0, 50.0, (B, N)); v = rng.normal(0, 1, (B, N)) + 3.0 * (rng.uniform(size=(B, N)) < 0.2)
+    bp.set_state(x, v)
+    pe_pre = np.concatenate([e.get_diag()[:, 1] for e in bp.engines])
+    a = rng.uniform(-1, 1, (B, 6))
+    out = bp.step(a, 1)
+    ie = out["input_energy"][0]
+    want = np.maximum(1 - pe_pre / bp.r_pe_n, 0) * 0.7 + np.maximum(1 - ie / bp.r_ie_n, 0) * 0.3
+    assert np.allclose(out["reward"][0], want, rtol=1e-13, atol=0)
